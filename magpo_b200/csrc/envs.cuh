@@ -1,0 +1,11 @@
+// Internal launchers shared between the env kernels and the rollout sequencer.
+#pragma once
+#include "common.cuh"
+
+namespace magpo {
+
+// vmap(env.step) for CoordSum; done_out [B] (optional) receives timestep.last().
+int coordsum_step_launch(cudaStream_t s, const MagpoCoordSumCfg* cfg, int B, const int32_t* action,
+                         MagpoCoordSumState st, MagpoTimeStep ts, uint8_t* done_out);
+
+}  // namespace magpo

@@ -1,0 +1,71 @@
+// Internal launchers shared by the host-side sequencers (sable.cu, actor.cu, rollout.cu, update.cu).
+// Everything works on row-major fp32 activations [rows, C]; a "row" is one token (t, env, agent).
+#pragma once
+#include "common.cuh"
+
+namespace magpo {
+
+constexpr int kD = 64;   // Sable embed_dim supported by the kernels (configs/network/magpo.yaml:4)
+constexpr int kH = 128;  // learner hidden_state_dim / torso width (magpo.yaml:19-31)
+constexpr int kMaxActions = 32;
+constexpr int kMaxAgents = 8;
+
+enum { GEMM_ACCUMULATE = 1, GEMM_RELU = 2 };
+
+// ---- gemm.cu
+int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* W, int ldw,
+            const float* bias, float* Y, int ldy, int flags);
+int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW,
+            int ldw);
+int colsum(cudaStream_t s, int64_t M, int N, const float* dY, int ldy, float* db);
+int transpose(cudaStream_t s, int R, int Cc, const float* in, float* out);
+
+// ---- rowops.cu (all on 64-wide rows unless noted)
+enum { ROW_GELU = 1 };
+// on = RMSNorm_d(x) * scale, general width C (the obs encoder's first layer, sable_network.py:93-101)
+int rms_general_fwd(cudaStream_t s, int64_t R, int C, const float* x, const float* scale, float* y);
+// dscale[c] += sum_r dy[r,c] * x[r,c] * rstd_r   (x is data: no dx)
+int rms_general_bwd_scale(cudaStream_t s, int64_t R, int C, const float* x, const float* dy, float* dscale);
+// y = RMSNorm((gelu?)(z) + res) * scale ; ype = y + pe[step[row]]   (res, ype, pe optional)
+int act_rms_fwd(cudaStream_t s, int64_t R, const float* z, const float* res, const float* scale, int flags,
+                const float* pe, const int32_t* step, int max_step, float* y, float* ype);
+// dpre from dy = dy1+dy2+dy3 (nullable); out = gelu ? dpre * gelu'(z) : dpre ; dscale accumulated
+int act_rms_bwd(cudaStream_t s, int64_t R, const float* z, const float* res, const float* scale, int flags,
+                const float* dy1, const float* dy2, const float* dy3, float* dout, float* dscale);
+// gated = swish(g) * LayerNorm(ret) (flax GroupNorm with one group, retention.py:289-295). g has row stride ldg.
+int gn_gate_fwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float* ret, const float* gn_scale,
+                const float* gn_bias, float* gated);
+int gn_gate_bwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float* ret, const float* gn_scale,
+                const float* gn_bias, const float* dgated, float* dg, int lddg, float* dret, float* dgn_scale,
+                float* dgn_bias);
+// SwiGLU middle: h = swish(gl[:, :64]) * gl[:, 64:]  (torsos.py:96-99)
+int swiglu_fwd(cudaStream_t s, int64_t R, const float* gl, float* h);
+int swiglu_bwd(cudaStream_t s, int64_t R, const float* gl, const float* dh, float* dgl);
+// out[r, :nout] = RMSNorm(gelu(zh)) * scale @ W3[64,nout] + b3     (head layers 1..3, sable_network.py:102-109,274-283)
+int head_fwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, const float* b3,
+             int nout, float* out);
+int head_bwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, int nout,
+             const float* dout, float* dzh, float* dscale, float* dW3, float* db3);
+// decoder input: x = RMSNorm(gelu(Wa[token])) * scale, token = start (0) for the first agent of a timestep else
+// 1 + action of the previous token (decode.py:86-108); xpe = x + pe
+int embed_fwd(cudaStream_t s, int64_t R, int A, const int32_t* action, const float* Wa, const float* scale,
+              const float* pe, const int32_t* step, int max_step, float* x, float* xpe);
+int embed_bwd(cudaStream_t s, int64_t R, int A, int a, const int32_t* action, const float* Wa, const float* scale,
+              const float* dy1, const float* dy2, float* dWa, float* dscale);
+// y = x + pe[step]
+int add_pe(cudaStream_t s, int64_t R, const float* x, const float* pe, const int32_t* step, int max_step, float* y);
+int build_pe_table(cudaStream_t s, int max_step, float* pe);
+int fill_f32(cudaStream_t s, float* p, int64_t n, float v);
+
+// ---- retention.cu : recurrent-form retention over per-env sequences, rows ordered (t, env, agent)
+// q,k,v: column blocks of a packed buffer with row stride ld. H0 [N,64,64] initial state (un-decayed,
+// as stored in the learner state); done [T,N] resets. Hsave (optional) [T,N,64,64] = state after each timestep.
+// Hout (optional) [N,64,64] final state. causal: decoder (masked=True) vs encoder (block-full over agents).
+int retention_fwd(cudaStream_t s, int T, int N, int A, float kappa, bool causal, const float* q, const float* k,
+                  const float* v, int ld, const float* H0, const uint8_t* done, float* ret, float* Hsave,
+                  float* Hout);
+int retention_bwd(cudaStream_t s, int T, int N, int A, float kappa, bool causal, const float* q, const float* k,
+                  const float* v, int ld, const float* H0, const uint8_t* done, const float* Hsave,
+                  const float* dret, float* dq, float* dk, float* dv, int ldd);
+
+}  // namespace magpo

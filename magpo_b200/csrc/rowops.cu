@@ -1,0 +1,505 @@
+// Row-wise (per-token) layers of the Sable guider, forward and hand-derived backward:
+// RMSNorm (+gelu, +residual, +positional encoding), GroupNorm*swish gate, SwiGLU middle, the heads'
+// gelu->RMSNorm->Dense tail, the decoder's action embedding.  Reference: networks/sable_network.py:40-343,
+// networks/retention.py:289-295, networks/torsos.py:79-99, utils/sable/positional_encoding.py:24-58,
+// flax 0.10.3 RMSNorm/GroupNorm arithmetic, backward per Appendix G.
+// One warp owns one 64-wide row (lane l holds columns 2l, 2l+1 -> 256-byte coalesced rows); per-column
+// parameter gradients are accumulated in registers over a grid-stride loop and flushed once per CTA.
+// All of these are HBM-bound: algorithmic traffic = (inputs + outputs) * 256 B per token.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace magpo {
+namespace {
+
+constexpr float kEps = 1e-6f;
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ float2 ld2(const float* __restrict__ p, int64_t row, int ld, int lane) {
+  return *reinterpret_cast<const float2*>(p + row * ld + 2 * lane);
+}
+__device__ __forceinline__ void st2(float* __restrict__ p, int64_t row, int ld, int lane, float2 v) {
+  *reinterpret_cast<float2*>(p + row * ld + 2 * lane) = v;
+}
+__device__ __forceinline__ float swishf(float x) { return x * sigmoid_precise(x); }
+__device__ __forceinline__ float swish_grad(float x) {
+  const float sg = sigmoid_precise(x);
+  return sg * (1.0f + x * (1.0f - sg));
+}
+
+// Flush per-lane column partials (2 columns per lane) of all warps of the CTA into global with one atomic per column.
+__device__ __forceinline__ void flush_cols(float2 part, float* __restrict__ dst, float* sm /*[kWarps*64]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  sm[w * 64 + 2 * lane] = part.x;
+  sm[w * 64 + 2 * lane + 1] = part.y;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) s += sm[i * 64 + threadIdx.x];
+    atomicAdd(dst + threadIdx.x, s);
+  }
+  __syncthreads();
+}
+
+inline unsigned row_grid(int64_t R) { return (unsigned)std::min<int64_t>(ceil_div(R, kWarps), (int64_t)kNumSMs * 8); }
+
+#define ROW_LOOP()                                                               \
+  const int lane = threadIdx.x & 31;                                             \
+  const int64_t wg = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);          \
+  const int64_t wstride = (int64_t)gridDim.x * kWarps;                           \
+  for (int64_t row = wg; row < R; row += wstride)
+
+// ------------------------------------------------------------------ general-width RMSNorm (obs encoder input)
+__global__ void __launch_bounds__(256)
+rms_general_fwd_kernel(int64_t R, int C, const float* __restrict__ x, const float* __restrict__ scale,
+                       float* __restrict__ y) {
+  ROW_LOOP() {
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = x[row * C + c];
+      ss += v * v;
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)C + kEps);
+    for (int c = lane; c < C; c += 32) y[row * C + c] = x[row * C + c] * (rstd * scale[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rms_general_bwd_scale_kernel(int64_t R, int C, const float* __restrict__ x, const float* __restrict__ dy,
+                             float* __restrict__ dscale) {
+  extern __shared__ float sm[];  // [C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int nper = (C + 31) / 32;
+  float part[4] = {0.f, 0.f, 0.f, 0.f};  // C <= 128
+  ROW_LOOP() {
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = x[row * C + c];
+      ss += v * v;
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)C + kEps);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (i < nper && c < C) part[i] += dy[row * C + c] * x[row * C + c] * rstd;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (threadIdx.x & 31) + 32 * i;
+    if (c < C) atomicAdd(&sm[c], part[i]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dscale + c, sm[c]);
+}
+
+// ------------------------------------------------------------------ (gelu) + residual + RMSNorm (+PE)
+__global__ void __launch_bounds__(256)
+act_rms_fwd_kernel(int64_t R, const float* __restrict__ z, const float* __restrict__ res,
+                   const float* __restrict__ scale, int flags, const float* __restrict__ pe,
+                   const int32_t* __restrict__ step, int max_step, float* __restrict__ y, float* __restrict__ ype) {
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
+  ROW_LOOP() {
+    float2 p = ld2(z, row, kD, lane);
+    if (flags & ROW_GELU) { p.x = gelu_tanh(p.x); p.y = gelu_tanh(p.y); }
+    if (res) { const float2 r = ld2(res, row, kD, lane); p.x += r.x; p.y += r.y; }
+    const float ss = warp_sum(p.x * p.x + p.y * p.y);
+    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
+    float2 o = make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
+    if (y) st2(y, row, kD, lane, o);
+    if (ype) {
+      const int st = min(max(step[row], 0), max_step);
+      const float2 e = ld2(pe, st, kD, lane);
+      st2(ype, row, kD, lane, make_float2(o.x + e.x, o.y + e.y));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+act_rms_bwd_kernel(int64_t R, const float* __restrict__ z, const float* __restrict__ res,
+                   const float* __restrict__ scale, int flags, const float* __restrict__ dy1,
+                   const float* __restrict__ dy2, const float* __restrict__ dy3, float* __restrict__ dout,
+                   float* __restrict__ dscale) {
+  __shared__ float sm[kWarps * 64];
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
+  float2 ds = make_float2(0.f, 0.f);
+  ROW_LOOP() {
+    const float2 zz = ld2(z, row, kD, lane);
+    float2 p = zz;
+    if (flags & ROW_GELU) { p.x = gelu_tanh(p.x); p.y = gelu_tanh(p.y); }
+    if (res) { const float2 r = ld2(res, row, kD, lane); p.x += r.x; p.y += r.y; }
+    const float ss = warp_sum(p.x * p.x + p.y * p.y);
+    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
+    float2 d = ld2(dy1, row, kD, lane);
+    if (dy2) { const float2 t = ld2(dy2, row, kD, lane); d.x += t.x; d.y += t.y; }
+    if (dy3) { const float2 t = ld2(dy3, row, kD, lane); d.x += t.x; d.y += t.y; }
+    ds.x += d.x * p.x * rstd;
+    ds.y += d.y * p.y * rstd;
+    const float2 u = make_float2(d.x * sc.x, d.y * sc.y);
+    const float dot = warp_sum(p.x * u.x + p.y * u.y) * (1.0f / kD);
+    const float r3 = rstd * rstd * rstd;
+    float2 dp = make_float2(rstd * u.x - p.x * r3 * dot, rstd * u.y - p.y * r3 * dot);
+    if (flags & ROW_GELU) { dp.x *= gelu_tanh_grad(zz.x); dp.y *= gelu_tanh_grad(zz.y); }
+    st2(dout, row, kD, lane, dp);
+  }
+  flush_cols(ds, dscale, sm);
+}
+
+// ------------------------------------------------------------------ GroupNorm(1 group) * swish gate
+__device__ __forceinline__ void ln_stats(float2 x, float& mean, float& rstd) {
+  mean = warp_sum(x.x + x.y) * (1.0f / kD);
+  const float m2 = warp_sum(x.x * x.x + x.y * x.y) * (1.0f / kD);
+  const float var = fmaxf(0.0f, m2 - mean * mean);  // flax "fast variance"
+  rstd = rsqrtf(var + kEps);
+}
+
+__global__ void __launch_bounds__(256)
+gn_gate_fwd_kernel(int64_t R, const float* __restrict__ g, int ldg, const float* __restrict__ ret,
+                   const float* __restrict__ gs, const float* __restrict__ gb, float* __restrict__ gated) {
+  const float2 sc = *reinterpret_cast<const float2*>(gs + 2 * (threadIdx.x & 31));
+  const float2 bi = *reinterpret_cast<const float2*>(gb + 2 * (threadIdx.x & 31));
+  ROW_LOOP() {
+    const float2 x = ld2(ret, row, kD, lane);
+    const float2 gg = ld2(g, row, ldg, lane);
+    float mean, rstd;
+    ln_stats(x, mean, rstd);
+    const float nx = (x.x - mean) * rstd * sc.x + bi.x;
+    const float ny = (x.y - mean) * rstd * sc.y + bi.y;
+    st2(gated, row, kD, lane, make_float2(swishf(gg.x) * nx, swishf(gg.y) * ny));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_gate_bwd_kernel(int64_t R, const float* __restrict__ g, int ldg, const float* __restrict__ ret,
+                   const float* __restrict__ gs, const float* __restrict__ gb, const float* __restrict__ dgated,
+                   float* __restrict__ dg, int lddg, float* __restrict__ dret, float* __restrict__ dgs,
+                   float* __restrict__ dgb) {
+  __shared__ float sm[kWarps * 64];
+  const float2 sc = *reinterpret_cast<const float2*>(gs + 2 * (threadIdx.x & 31));
+  const float2 bi = *reinterpret_cast<const float2*>(gb + 2 * (threadIdx.x & 31));
+  float2 dS = make_float2(0.f, 0.f), dB = make_float2(0.f, 0.f);
+  ROW_LOOP() {
+    const float2 x = ld2(ret, row, kD, lane);
+    const float2 gg = ld2(g, row, ldg, lane);
+    const float2 dgt = ld2(dgated, row, kD, lane);
+    float mean, rstd;
+    ln_stats(x, mean, rstd);
+    const float2 xh = make_float2((x.x - mean) * rstd, (x.y - mean) * rstd);
+    const float2 nrm = make_float2(xh.x * sc.x + bi.x, xh.y * sc.y + bi.y);
+    st2(dg, row, lddg, lane, make_float2(dgt.x * nrm.x * swish_grad(gg.x), dgt.y * nrm.y * swish_grad(gg.y)));
+    const float2 dn = make_float2(dgt.x * swishf(gg.x), dgt.y * swishf(gg.y));
+    dS.x += dn.x * xh.x; dS.y += dn.y * xh.y;
+    dB.x += dn.x; dB.y += dn.y;
+    const float2 u = make_float2(dn.x * sc.x, dn.y * sc.y);
+    const float mu = warp_sum(u.x + u.y) * (1.0f / kD);
+    const float mux = warp_sum(u.x * xh.x + u.y * xh.y) * (1.0f / kD);
+    st2(dret, row, kD, lane, make_float2(rstd * (u.x - mu - xh.x * mux), rstd * (u.y - mu - xh.y * mux)));
+  }
+  flush_cols(dS, dgs, sm);
+  flush_cols(dB, dgb, sm);
+}
+
+// ------------------------------------------------------------------ SwiGLU middle
+__global__ void __launch_bounds__(256)
+swiglu_fwd_kernel(int64_t R, const float* __restrict__ gl, float* __restrict__ h) {
+  ROW_LOOP() {
+    const float2 a = ld2(gl, row, 2 * kD, lane);
+    const float2 b = ld2(gl + kD, row, 2 * kD, lane);
+    st2(h, row, kD, lane, make_float2(swishf(a.x) * b.x, swishf(a.y) * b.y));
+  }
+}
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(int64_t R, const float* __restrict__ gl, const float* __restrict__ dh, float* __restrict__ dgl) {
+  ROW_LOOP() {
+    const float2 a = ld2(gl, row, 2 * kD, lane);
+    const float2 b = ld2(gl + kD, row, 2 * kD, lane);
+    const float2 d = ld2(dh, row, kD, lane);
+    st2(dgl, row, 2 * kD, lane, make_float2(d.x * b.x * swish_grad(a.x), d.y * b.y * swish_grad(a.y)));
+    st2(dgl + kD, row, 2 * kD, lane, make_float2(d.x * swishf(a.x), d.y * swishf(a.y)));
+  }
+}
+
+// ------------------------------------------------------------------ head tail: gelu -> RMSNorm -> Dense(nout)
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(int64_t R, const float* __restrict__ zh, const float* __restrict__ scale,
+                const float* __restrict__ W3, const float* __restrict__ b3, int nout, float* __restrict__ out) {
+  __shared__ float Ws[kD * kMaxActions];
+  for (int i = threadIdx.x; i < kD * nout; i += blockDim.x) Ws[i] = W3[i];
+  __syncthreads();
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
+  const int lane_ = threadIdx.x & 31;
+  const float bias = lane_ < nout ? b3[lane_] : 0.f;
+  ROW_LOOP() {
+    float2 p = ld2(zh, row, kD, lane);
+    p.x = gelu_tanh(p.x); p.y = gelu_tanh(p.y);
+    const float ss = warp_sum(p.x * p.x + p.y * p.y);
+    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
+    const float2 hn = make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
+    float acc = 0.f;
+    const int j = lane < nout ? lane : 0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const float a = __shfl_sync(0xffffffffu, hn.x, l);
+      const float b = __shfl_sync(0xffffffffu, hn.y, l);
+      acc = fmaf(a, Ws[(2 * l) * nout + j], acc);
+      acc = fmaf(b, Ws[(2 * l + 1) * nout + j], acc);
+    }
+    if (lane < nout) out[row * nout + lane] = acc + bias;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(int64_t R, const float* __restrict__ zh, const float* __restrict__ scale,
+                const float* __restrict__ W3, int nout, const float* __restrict__ dout, float* __restrict__ dzh,
+                float* __restrict__ dscale, float* __restrict__ dW3, float* __restrict__ db3) {
+  __shared__ float Ws[kD * kMaxActions];
+  __shared__ float dWs[kD * kMaxActions];
+  __shared__ float sm[kWarps * 64];
+  __shared__ float dbs[kMaxActions];
+  for (int i = threadIdx.x; i < kD * nout; i += blockDim.x) { Ws[i] = W3[i]; dWs[i] = 0.f; }
+  if (threadIdx.x < kMaxActions) dbs[threadIdx.x] = 0.f;
+  __syncthreads();
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
+  float2 ds = make_float2(0.f, 0.f);
+  float dwx[kMaxActions], dwy[kMaxActions];
+#pragma unroll
+  for (int j = 0; j < kMaxActions; ++j) { dwx[j] = 0.f; dwy[j] = 0.f; }
+  float dbl = 0.f;
+  ROW_LOOP() {
+    const float2 zz = ld2(zh, row, kD, lane);
+    const float2 p = make_float2(gelu_tanh(zz.x), gelu_tanh(zz.y));
+    const float ss = warp_sum(p.x * p.x + p.y * p.y);
+    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
+    const float2 hn = make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
+    const float dol = lane < nout ? dout[row * nout + lane] : 0.f;
+    dbl += dol;
+    float2 dhn = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kMaxActions; ++j) {
+      if (j < nout) {
+        const float dj = __shfl_sync(0xffffffffu, dol, j);
+        dhn.x = fmaf(dj, Ws[(2 * lane) * nout + j], dhn.x);
+        dhn.y = fmaf(dj, Ws[(2 * lane + 1) * nout + j], dhn.y);
+        dwx[j] = fmaf(hn.x, dj, dwx[j]);
+        dwy[j] = fmaf(hn.y, dj, dwy[j]);
+      }
+    }
+    ds.x += dhn.x * p.x * rstd;
+    ds.y += dhn.y * p.y * rstd;
+    const float2 u = make_float2(dhn.x * sc.x, dhn.y * sc.y);
+    const float dot = warp_sum(p.x * u.x + p.y * u.y) * (1.0f / kD);
+    const float r3 = rstd * rstd * rstd;
+    st2(dzh, row, kD, lane,
+        make_float2((rstd * u.x - p.x * r3 * dot) * gelu_tanh_grad(zz.x),
+                    (rstd * u.y - p.y * r3 * dot) * gelu_tanh_grad(zz.y)));
+  }
+  {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < kMaxActions; ++j) {
+      if (j < nout) {
+        atomicAdd(&dWs[(2 * lane) * nout + j], dwx[j]);
+        atomicAdd(&dWs[(2 * lane + 1) * nout + j], dwy[j]);
+      }
+    }
+    if (lane < nout) atomicAdd(&dbs[lane], dbl);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kD * nout; i += blockDim.x) atomicAdd(dW3 + i, dWs[i]);
+  if (threadIdx.x < nout) atomicAdd(db3 + threadIdx.x, dbs[threadIdx.x]);
+  flush_cols(ds, dscale, sm);
+}
+
+// ------------------------------------------------------------------ decoder action embedding
+__device__ __forceinline__ int shifted_token(const int32_t* __restrict__ action, int64_t row, int A) {
+  if (A < 0) return 0;                  // inference, first agent: start-of-timestep token
+  if (A == 0) return 1 + action[row];  // inference, later agents: action[] holds the previous agent's action
+  return (row % A) == 0 ? 0 : 1 + action[row - 1];
+}
+
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(int64_t R, int A, const int32_t* __restrict__ action, const float* __restrict__ Wa,
+                 const float* __restrict__ scale, const float* __restrict__ pe, const int32_t* __restrict__ step,
+                 int max_step, float* __restrict__ x, float* __restrict__ xpe) {
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
+  ROW_LOOP() {
+    const int tok = shifted_token(action, row, A);
+    float2 p = ld2(Wa, tok, kD, lane);
+    p.x = gelu_tanh(p.x); p.y = gelu_tanh(p.y);
+    const float ss = warp_sum(p.x * p.x + p.y * p.y);
+    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
+    const float2 o = make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
+    st2(x, row, kD, lane, o);
+    const int st = min(max(step[row], 0), max_step);
+    const float2 e = ld2(pe, st, kD, lane);
+    st2(xpe, row, kD, lane, make_float2(o.x + e.x, o.y + e.y));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(int64_t R, int A, int a, const int32_t* __restrict__ action, const float* __restrict__ Wa,
+                 const float* __restrict__ scale, const float* __restrict__ dy1, const float* __restrict__ dy2,
+                 float* __restrict__ dWa, float* __restrict__ dscale) {
+  __shared__ float dWs[(kMaxActions + 1) * kD];
+  __shared__ float sm[kWarps * 64];
+  for (int i = threadIdx.x; i < (a + 1) * kD; i += blockDim.x) dWs[i] = 0.f;
+  __syncthreads();
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
+  float2 ds = make_float2(0.f, 0.f);
+  ROW_LOOP() {
+    const int tok = shifted_token(action, row, A);
+    const float2 zz = ld2(Wa, tok, kD, lane);
+    const float2 p = make_float2(gelu_tanh(zz.x), gelu_tanh(zz.y));
+    const float ss = warp_sum(p.x * p.x + p.y * p.y);
+    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
+    float2 d = ld2(dy1, row, kD, lane);
+    if (dy2) { const float2 t = ld2(dy2, row, kD, lane); d.x += t.x; d.y += t.y; }
+    ds.x += d.x * p.x * rstd;
+    ds.y += d.y * p.y * rstd;
+    const float2 u = make_float2(d.x * sc.x, d.y * sc.y);
+    const float dot = warp_sum(p.x * u.x + p.y * u.y) * (1.0f / kD);
+    const float r3 = rstd * rstd * rstd;
+    atomicAdd(&dWs[tok * kD + 2 * lane], (rstd * u.x - p.x * r3 * dot) * gelu_tanh_grad(zz.x));
+    atomicAdd(&dWs[tok * kD + 2 * lane + 1], (rstd * u.y - p.y * r3 * dot) * gelu_tanh_grad(zz.y));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (a + 1) * kD; i += blockDim.x) atomicAdd(dWa + i, dWs[i]);
+  flush_cols(ds, dscale, sm);
+}
+
+__global__ void __launch_bounds__(256)
+add_pe_kernel(int64_t R, const float* __restrict__ x, const float* __restrict__ pe, const int32_t* __restrict__ step,
+              int max_step, float* __restrict__ y) {
+  ROW_LOOP() {
+    const float2 v = ld2(x, row, kD, lane);
+    const int st = min(max(step[row], 0), max_step);
+    const float2 e = ld2(pe, st, kD, lane);
+    st2(y, row, kD, lane, make_float2(v.x + e.x, v.y + e.y));
+  }
+}
+
+// pe[p, 2i] = sin(p * div_i), pe[p, 2i+1] = cos(p * div_i), div_i = exp(2i * (-ln(10000)/64))  (positional_encoding.py:32-58)
+__global__ void pe_table_kernel(int max_step, float* __restrict__ pe) {
+  const int p = blockIdx.x, i = threadIdx.x;  // i in [0, 32)
+  if (p > max_step) return;
+  const float div = expf((float)(2 * i) * (-logf(10000.0f) / (float)kD));
+  const float x = (float)p * div;
+  pe[p * kD + 2 * i] = sinf(x);
+  pe[p * kD + 2 * i + 1] = cosf(x);
+}
+
+__global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+int rms_general_fwd(cudaStream_t s, int64_t R, int C, const float* x, const float* scale, float* y) {
+  if (R <= 0) return MAGPO_OK;
+  rms_general_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, C, x, scale, y);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int rms_general_bwd_scale(cudaStream_t s, int64_t R, int C, const float* x, const float* dy, float* dscale) {
+  if (R <= 0) return MAGPO_OK;
+  if (C > 128) return MAGPO_ERR_UNSUPPORTED;
+  rms_general_bwd_scale_kernel<<<row_grid(R), 256, C * sizeof(float), s>>>(R, C, x, dy, dscale);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int act_rms_fwd(cudaStream_t s, int64_t R, const float* z, const float* res, const float* scale, int flags,
+                const float* pe, const int32_t* step, int max_step, float* y, float* ype) {
+  if (R <= 0) return MAGPO_OK;
+  act_rms_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, z, res, scale, flags, pe, step, max_step, y, ype);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int act_rms_bwd(cudaStream_t s, int64_t R, const float* z, const float* res, const float* scale, int flags,
+                const float* dy1, const float* dy2, const float* dy3, float* dout, float* dscale) {
+  if (R <= 0) return MAGPO_OK;
+  act_rms_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, z, res, scale, flags, dy1, dy2, dy3, dout, dscale);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int gn_gate_fwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float* ret, const float* gn_scale,
+                const float* gn_bias, float* gated) {
+  if (R <= 0) return MAGPO_OK;
+  gn_gate_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, g, ldg, ret, gn_scale, gn_bias, gated);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int gn_gate_bwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float* ret, const float* gn_scale,
+                const float* gn_bias, const float* dgated, float* dg, int lddg, float* dret, float* dgn_scale,
+                float* dgn_bias) {
+  if (R <= 0) return MAGPO_OK;
+  gn_gate_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, g, ldg, ret, gn_scale, gn_bias, dgated, dg, lddg, dret,
+                                                 dgn_scale, dgn_bias);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int swiglu_fwd(cudaStream_t s, int64_t R, const float* gl, float* h) {
+  if (R <= 0) return MAGPO_OK;
+  swiglu_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, gl, h);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int swiglu_bwd(cudaStream_t s, int64_t R, const float* gl, const float* dh, float* dgl) {
+  if (R <= 0) return MAGPO_OK;
+  swiglu_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, gl, dh, dgl);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int head_fwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, const float* b3,
+             int nout, float* out) {
+  if (R <= 0) return MAGPO_OK;
+  if (nout < 1 || nout > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
+  head_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, b3, nout, out);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int head_bwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, int nout,
+             const float* dout, float* dzh, float* dscale, float* dW3, float* db3) {
+  if (R <= 0) return MAGPO_OK;
+  if (nout < 1 || nout > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
+  head_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int embed_fwd(cudaStream_t s, int64_t R, int A, const int32_t* action, const float* Wa, const float* scale,
+              const float* pe, const int32_t* step, int max_step, float* x, float* xpe) {
+  if (R <= 0) return MAGPO_OK;
+  embed_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, A, action, Wa, scale, pe, step, max_step, x, xpe);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int embed_bwd(cudaStream_t s, int64_t R, int A, int a, const int32_t* action, const float* Wa, const float* scale,
+              const float* dy1, const float* dy2, float* dWa, float* dscale) {
+  if (R <= 0) return MAGPO_OK;
+  if (a > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
+  embed_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, A, a, action, Wa, scale, dy1, dy2, dWa, dscale);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int add_pe(cudaStream_t s, int64_t R, const float* x, const float* pe, const int32_t* step, int max_step, float* y) {
+  if (R <= 0) return MAGPO_OK;
+  add_pe_kernel<<<row_grid(R), 256, 0, s>>>(R, x, pe, step, max_step, y);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int build_pe_table(cudaStream_t s, int max_step, float* pe) {
+  pe_table_kernel<<<max_step + 1, 32, 0, s>>>(max_step, pe);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+int fill_f32(cudaStream_t s, float* p, int64_t n, float v) {
+  if (n <= 0) return MAGPO_OK;
+  fill_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 16), 256, 0, s>>>(p, n, v);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+}  // namespace magpo

@@ -45,7 +45,7 @@ def gae(done, value, reward, last_val, last_done, gamma, lam):
     """calculate_gae (multistep.py:51-68). done bool[T,...], value/reward f32[T,...]. fp32 op order kept."""
     T = value.shape[0]
     g = np.float32(gamma)
-    gl = np.float32(np.float32(gamma) * np.float32(lam))
+    gl = np.float32(gamma * lam)  # Python-float product, rounded once (weak-typed constant)
     adv = np.zeros_like(value, dtype=np.float32)
     acc = np.zeros_like(last_val, dtype=np.float32)
     nv = last_val.astype(np.float32)
@@ -320,6 +320,10 @@ def update_step(state, spec, ncfg: nets.NetCfg, sys: SysCfg, grad_allreduce=None
             batch_perm = prng.permutation(k4[1], sys.num_envs)
             agent_perm = prng.permutation(k4[2], ncfg.n_agents)
             mbs.append(make_minibatches(trajs[u], advs[u], tgts[u], prevs[u], batch_perm, agent_perm, M))
+            # quirk kept: `_update_epoch` returns the *permuted* prev_hstates in update_state
+            # (rec_magpo.py:447,471), so from the 2nd epoch on the stored Sable states are a
+            # composition of all earlier env permutations while the trajectory is not.
+            prevs[u] = tuple(np.take(h, batch_perm, axis=0) for h in prevs[u])
         for m in range(M):
             gsum, asum, infos = None, None, []
             for u in range(U):
