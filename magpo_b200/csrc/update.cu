@@ -5,6 +5,8 @@
 // only the advantage normalisation is per slot (:283,356).
 #include "update.cuh"
 
+#include <string.h>
+
 #include "actor.cuh"
 #include "prng.cuh"
 #include "sable.cuh"
@@ -289,6 +291,28 @@ int magpo_actor_forward(magpo_stream_t s_, const MagpoNetCfg* net, const float* 
   mask_logits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(n, mb.action_mask, logits);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
+}
+
+// Test hook: byte offset inside the update workspace of a saved activation (same plan as magpo_minibatch_grads),
+// so that parity tests can compare intermediates with the oracle after a call. Returns -1 for unknown names.
+int64_t magpo_debug_buffer_offset(const MagpoNetCfg* net, int32_t T, int32_t N, const char* name) {
+  if (check_net(net) != MAGPO_OK || !name) return -1;
+  Arena ar(nullptr, SIZE_MAX);
+  UpdateWs w;
+  w.plan(ar, net, T, N, true);
+  struct { const char* n; const void* p; } tab[] = {
+      {"on", w.sa.on}, {"z0", w.sa.z0}, {"xin", w.sa.xin}, {"kqv", w.sa.kqv}, {"qkvg", w.sa.qkvg}, {"ret", w.sa.ret},
+      {"gated", w.sa.gated}, {"o", w.sa.o}, {"x1", w.sa.x1}, {"gl", w.sa.gl}, {"hmid", w.sa.hmid}, {"f", w.sa.f},
+      {"x", w.sa.x}, {"xpe", w.sa.xpe}, {"zh", w.sa.zh}, {"xD", w.sa.xD}, {"xpeD", w.sa.xpeD}, {"qkvg1", w.sa.qkvg1},
+      {"ret1", w.sa.ret1}, {"gated1", w.sa.gated1}, {"o1", w.sa.o1}, {"rpe", w.sa.rpe}, {"qkvg2", w.sa.qkvg2},
+      {"ret2", w.sa.ret2}, {"gated2", w.sa.gated2}, {"o2", w.sa.o2}, {"y", w.sa.y}, {"glD", w.sa.glD},
+      {"hmidD", w.sa.hmidD}, {"fD", w.sa.fD}, {"xd", w.sa.xd}, {"zhD", w.sa.zhD}, {"Hs_enc", w.sa.Hs_enc},
+      {"Hs_self", w.sa.Hs_self}, {"Hs_cross", w.sa.Hs_cross}, {"e", w.aa.e}, {"HU", w.aa.HU}, {"Y", w.aa.Y},
+      {"post", w.aa.post}, {"rzn", w.aa.rzn}, {"ghn", w.aa.ghn}, {"lg", w.lg}, {"ll", w.ll}, {"value", w.value},
+      {"dlg", w.dlg}, {"dll", w.dll}, {"dvalue", w.dvalue}, {"pe", w.pe}};
+  for (auto& e : tab)
+    if (strcmp(e.n, name) == 0) return (int64_t)reinterpret_cast<uintptr_t>(e.p);
+  return -1;
 }
 
 // ------------------------------------------------------------------ parameter table (flax tree paths)

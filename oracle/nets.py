@@ -24,6 +24,16 @@ from . import prng
 
 F32_MIN = float(np.finfo(np.float32).min)
 
+# Optional tap for parity debugging: when set to a dict, forward passes store named intermediates in it
+# (tests compare them with the CUDA path's saved activations).
+RECORD: dict | None = None
+
+
+def _rec(name, t):
+    if RECORD is not None:
+        RECORD[name] = t
+    return t
+
 
 @dataclass
 class NetCfg:
@@ -243,8 +253,10 @@ def msr(p, pre, cfg: NetCfg, key, query, value, hstate, step_count, masked, done
         outs.append(y)
         new_hs.append(nh)
     ret = torch.cat(outs, dim=-1)
+    _rec(f"{pre}/ret", ret)
     ret = groupnorm_rows(ret.reshape(-1, cfg.head_size), p[f"{pre}/group_norm/scale"], p[f"{pre}/group_norm/bias"], cfg.n_head).reshape(ret.shape)
-    out = (swish(key @ p[f"{pre}/w_g"]) * ret) @ p[f"{pre}/w_o"]
+    gated = _rec(f"{pre}/gated", swish(key @ p[f"{pre}/w_g"]) * ret)
+    out = _rec(f"{pre}/out", gated @ p[f"{pre}/w_o"])
     return out, torch.stack(new_hs, dim=1)
 
 
@@ -261,10 +273,10 @@ def encoder_apply(p, cfg: NetCfg, obs, hstate, step_count, dones=None):
     new_h = []
     for b in range(cfg.n_block):
         pre = f"encoder/encoder_block_{b}"
-        xin = rmsnorm(x, p["encoder/ln/scale"])
+        xin = _rec("enc/xin", rmsnorm(x, p["encoder/ln/scale"]))
         ret, nh = msr(p, f"{pre}/retn", cfg, xin, xin, xin, hstate[:, :, b], step_count, masked=False, dones=dones)
-        x1 = rmsnorm(xin + ret, p[f"{pre}/ln1/scale"])
-        x = rmsnorm(x1 + swiglu(p, f"{pre}/ffn", x1), p[f"{pre}/ln2/scale"])
+        x1 = _rec("enc/x1", rmsnorm(xin + ret, p[f"{pre}/ln1/scale"]))
+        x = _rec("enc/x", rmsnorm(x1 + swiglu(p, f"{pre}/ffn", x1), p[f"{pre}/ln2/scale"]))
         new_h.append(nh)
     value = _head(p, "encoder/head", x)
     return value, x, torch.stack(new_h, dim=2)
@@ -272,15 +284,15 @@ def encoder_apply(p, cfg: NetCfg, obs, hstate, step_count, dones=None):
 
 def decoder_apply(p, cfg: NetCfg, action_tok, obs_rep, hs_self, hs_cross, step_count, dones=None):
     """Decoder.__call__ / Decoder.recurrent (sable_network.py:296-343)."""
-    x = rmsnorm(gelu(action_tok @ p["decoder/action_encoder/layers_0/kernel"]), p["decoder/ln/scale"])
+    x = _rec("dec/xD", rmsnorm(gelu(action_tok @ p["decoder/action_encoder/layers_0/kernel"]), p["decoder/ln/scale"]))
     n1, n2 = [], []
     for b in range(cfg.n_block):
         pre = f"decoder/decoder_block_{b}"
         ret, h1 = msr(p, f"{pre}/retn1", cfg, x, x, x, hs_self[:, :, b], step_count, masked=True, dones=dones)
         r = rmsnorm(x + ret, p[f"{pre}/ln1/scale"])
         ret2, h2 = msr(p, f"{pre}/retn2", cfg, r, obs_rep, r, hs_cross[:, :, b], step_count, masked=True, dones=dones)
-        y = rmsnorm(obs_rep + ret2, p[f"{pre}/ln2/scale"])
-        x = rmsnorm(y + swiglu(p, f"{pre}/ffn", y), p[f"{pre}/ln3/scale"])
+        y = _rec("dec/y", rmsnorm(obs_rep + ret2, p[f"{pre}/ln2/scale"]))
+        x = _rec("dec/xd", rmsnorm(y + swiglu(p, f"{pre}/ffn", y), p[f"{pre}/ln3/scale"]))
         n1.append(h1)
         n2.append(h2)
     logit = _head(p, "decoder/head", x)

@@ -1,0 +1,182 @@
+"""-m gpu: Sable guider / GRU learner forward and the full minibatch gradient through the C ABI against the
+torch-CPU oracle (fp32, autograd). Tolerance: rtol 1e-4 of the tensor's scale (north_star: fp32 rtol 1e-4)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from magpo_b200 import _lib as L
+from magpo_b200.learner import NetworkConfig, load_params, param_table, param_views
+from oracle import learner as olr
+from oracle import nets as onets
+
+from gpu_util import dt, from_time_major, rel_err, sync, to_time_major
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_case(seed, U, Ns, T, A, d, a, mask_p=0.85):
+    """Random minibatch in the oracle's layout [N, T*A, ...] for U slots of Ns envs each."""
+    rng = np.random.default_rng(seed)
+    N, C_ = U * Ns, T * A
+    mask = rng.random((N, C_, a)) < mask_p
+    action = rng.integers(0, a, (N, C_))
+    mask[np.arange(N)[:, None], np.arange(C_)[None], action] = True  # taken actions are legal
+    done = rng.random((N, T)) < 0.15
+    done[0, 0] = True
+    return dict(obs=rng.standard_normal((N, C_, d)).astype(np.float32), action_mask=mask,
+                step_count=rng.integers(0, 60, (N, T, 1)).repeat(A, 2).reshape(N, C_).astype(np.int32),
+                action=action.astype(np.int32), done=np.repeat(done, A, 1), value=rng.standard_normal((N, C_)).astype(np.float32),
+                log_prob=(-np.abs(rng.standard_normal((N, C_))) - 1.0).astype(np.float32),
+                adv=rng.standard_normal((N, C_)).astype(np.float32), targets=rng.standard_normal((N, C_)).astype(np.float32),
+                policy_h0=(rng.standard_normal((N, A, 128)) * 0.3).astype(np.float32),
+                prev_hstates=tuple((rng.standard_normal((N, 1, 1, 64, 64)) * 0.05).astype(np.float32) for _ in range(3)))
+
+
+def device_minibatch(mb, T, A, dev):
+    N = mb["obs"].shape[0]
+    t = dict(agents_view=dt(to_time_major(mb["obs"], T, A), dev), action_mask=dt(to_time_major(mb["action_mask"], T, A).astype(np.uint8), dev),
+             step_count=dt(to_time_major(mb["step_count"], T, A), dev),
+             done=dt(np.ascontiguousarray(mb["done"][:, ::A].T).astype(np.uint8), dev),
+             action=dt(to_time_major(mb["action"], T, A), dev), value=dt(to_time_major(mb["value"], T, A), dev),
+             log_prob=dt(to_time_major(mb["log_prob"], T, A), dev), advantages=dt(to_time_major(mb["adv"], T, A), dev),
+             targets=dt(to_time_major(mb["targets"], T, A), dev), policy_h0=dt(mb["policy_h0"], dev))
+    hs = {k: dt(h.reshape(N, 64, 64), dev) for k, h in zip(("encoder", "decoder_self", "decoder_cross"), mb["prev_hstates"])}
+    s = L.struct_of(L.Minibatch, **t)
+    s.sable_h0 = L.struct_of(L.SableHState, **hs)
+    s.T, s.N = T, N
+    return s, (t, hs)
+
+
+def setup_nets(A, d, a, dev, ffn_zero=False, seed=0):
+    cfg = onets.NetCfg(A, d, a)
+    gp, ap = onets.init_guider_params(cfg, seed, ffn_zero=ffn_zero), onets.init_actor_params(cfg, seed + 1)
+    rng = np.random.default_rng(seed + 7)
+    # move every tensor off its special init value (ones / zeros) so that all gradient paths are exercised
+    gp = {k: (v + 0.05 * rng.standard_normal(v.shape)).astype(np.float32) for k, v in gp.items()}
+    ap = {k: (v + 0.05 * rng.standard_normal(v.shape)).astype(np.float32) for k, v in ap.items()}
+    net = NetworkConfig(A, d, a, 100)
+    gt, ng = param_table(net, 0)
+    at, na = param_table(net, 1)
+    gflat, aflat = torch.zeros(ng, device=dev), torch.zeros(na, device=dev)
+    load_params(gflat, gt, gp)
+    load_params(aflat, at, ap)
+    return cfg, net, gp, ap, (gt, ng, gflat), (at, na, aflat)
+
+
+def workspace(net, T, N, dev):
+    lib = L.lib()
+    lib.magpo_update_workspace_bytes.restype = C.c_size_t
+    nbytes = int(lib.magpo_update_workspace_bytes(C.byref(net.c_struct()), T, N))
+    assert nbytes > 0
+    return torch.zeros(nbytes, dtype=torch.uint8, device=dev), nbytes
+
+
+def ws_buffer(ws, net, T, N, name, shape):
+    lib = L.lib()
+    lib.magpo_debug_buffer_offset.restype = C.c_int64
+    off = lib.magpo_debug_buffer_offset(C.byref(net.c_struct()), T, N, name.encode())
+    assert off >= 0, name
+    n = int(np.prod(shape))
+    return ws[off:off + 4 * n].view(torch.float32).reshape(shape).cpu().numpy()
+
+
+@pytest.mark.parametrize("A,d,a,T,N", [(3, 4, 10, 16, 6), (4, 75, 5, 8, 3), (2, 14, 6, 5, 4)])
+def test_guider_and_actor_forward(dev, A, d, a, T, N):
+    cfg, net, gp, ap, (gt, ng, gflat), (at, na, aflat) = setup_nets(A, d, a, dev)
+    mb = make_case(1, 1, N, T, A, d, a)
+    mbs, keep = device_minibatch(mb, T, A, dev)
+    ws, nbytes = workspace(net, T, N, dev)
+    value = torch.zeros(T, N, A, device=dev)
+    logits = torch.zeros(T, N, A, a, device=dev)
+    cnet = net.c_struct()
+    L.call("magpo_guider_forward", L.stream_ptr(), C.byref(cnet), L.ptr(gflat), mbs, L.ptr(value), L.ptr(logits), L.ptr(ws),
+           C.c_size_t(nbytes))
+    p = onets.to_torch(gp)
+    onets.RECORD = rec = {}
+    try:
+        v_ref, _, _, l_ref = onets.sable_apply(p, cfg, torch.tensor(mb["obs"]), torch.tensor(mb["action_mask"]), torch.tensor(mb["step_count"]),
+                                               torch.tensor(mb["action"]), tuple(torch.tensor(h) for h in mb["prev_hstates"]),
+                                               torch.tensor(mb["done"]), T)
+    finally:
+        onets.RECORD = None
+    sync()
+    report = []
+    for mine, theirs in (("xin", "enc/xin"), ("ret", "encoder/encoder_block_0/retn/ret"), ("gated", "encoder/encoder_block_0/retn/gated"),
+                         ("x1", "enc/x1"), ("x", "enc/x"), ("xD", "dec/xD"), ("ret1", "decoder/decoder_block_0/retn1/ret"),
+                         ("ret2", "decoder/decoder_block_0/retn2/ret"), ("y", "dec/y"), ("xd", "dec/xd")):
+        got = from_time_major(ws_buffer(ws, net, T, N, mine, (T, N, A, 64)))
+        report.append((mine, rel_err(got, rec[theirs].detach().numpy())))
+    print("forward intermediates (rel err):", report)
+    ev = rel_err(from_time_major(value.cpu().numpy()), v_ref.numpy())
+    lg = from_time_major(logits.cpu().numpy())
+    legal = mb["action_mask"]
+    el = rel_err(lg[legal], l_ref.numpy()[legal])
+    assert (lg[~legal] == np.finfo(np.float32).min).all()
+    bad = [r for r in report if r[1] > 1e-4]
+    assert not bad and ev < 1e-4 and el < 1e-4, (bad, ev, el)
+    # learner
+    ll = torch.zeros(T, N, A, a, device=dev)
+    L.call("magpo_actor_forward", L.stream_ptr(), C.byref(cnet), L.ptr(aflat), mbs, L.ptr(ll), L.ptr(ws), C.c_size_t(nbytes))
+    _, a_ref = onets.actor_apply(onets.to_torch(ap), cfg, torch.tensor(mb["policy_h0"]), olr.forward_reshape(torch.tensor(mb["obs"]), A),
+                                 olr.forward_reshape(torch.tensor(mb["done"]), A), olr.forward_reshape(torch.tensor(mb["action_mask"]), A))
+    got = ll.cpu().numpy()  # already [T, N, A, a]
+    m = to_time_major(mb["action_mask"], T, A)
+    assert rel_err(got[m], a_ref.numpy()[m]) < 1e-4
+
+
+@pytest.mark.parametrize("A,d,a,T,Ns,U", [(3, 4, 10, 12, 5, 2), (4, 75, 5, 6, 3, 1)])
+def test_minibatch_grads(dev, A, d, a, T, Ns, U):
+    cfg, net, gp, ap, (gt, ng, gflat), (at, na, aflat) = setup_nets(A, d, a, dev)
+    sysc = olr.SysCfg(num_envs=Ns, update_batch_size=U, rollout_length=T, num_minibatches=1)
+    mb = make_case(2, U, Ns, T, A, d, a)
+    N = U * Ns
+    # oracle: per-slot value_and_grad, then the mean over slots (pmean over "batch")
+    gsum = asum = None
+    infos = []
+    for u in range(U):
+        sl = slice(u * Ns, (u + 1) * Ns)
+        part = {k: (tuple(h[sl] for h in v) if k == "prev_hstates" else v[sl]) for k, v in mb.items()}
+        gg, ga, info, _ = olr.minibatch_losses_and_grads(gp, ap, part, cfg, sysc)
+        gsum = gg if gsum is None else {k: gsum[k] + gg[k] for k in gg}
+        asum = ga if asum is None else {k: asum[k] + ga[k] for k in ga}
+        infos.append(info)
+    g_ref = {k: v / U for k, v in gsum.items()}
+    a_ref = {k: v / U for k, v in asum.items()}
+    info_ref = {k: float(np.mean([i[k] for i in infos])) for k in infos[0]}
+    # CUDA
+    mbs, keep = device_minibatch(mb, T, A, dev)
+    ws, nbytes = workspace(net, T, N, dev)
+    adv = mb["adv"].reshape(U, -1)
+    stats = dt(np.stack([adv.mean(1), adv.std(1)], 1).astype(np.float32), dev)
+    env_slot = dt(np.repeat(np.arange(U), Ns).astype(np.int32), dev)
+    grads = torch.zeros(ng + na + 8, device=dev)
+    from magpo_b200.learner import SystemConfig
+    csys = SystemConfig(num_envs=Ns, update_batch_size=U, rollout_length=T, num_minibatches=1).c_struct()
+    cnet = net.c_struct()
+    L.call("magpo_minibatch_grads", L.stream_ptr(), C.byref(cnet), C.byref(csys), L.ptr(gflat), L.ptr(aflat), mbs, L.ptr(env_slot),
+           L.ptr(stats), C.c_float(1.0 / (N * T * A)), L.ptr(grads), L.ptr(ws), C.c_size_t(nbytes))
+    sync()
+    gv = param_views(grads[:ng], gt)
+    av = param_views(grads[ng:ng + na], at)
+    lines, worst = [], 0.0
+    for name, ref in list(g_ref.items()) + list(a_ref.items()):
+        got = (gv if name in gv else av)[name].cpu().numpy()
+        e = rel_err(got, ref)
+        worst = max(worst, e)
+        lines.append(f"{e:10.3e}  |ref|max={np.abs(ref).max():9.3e}  {name}")
+    ls = grads[ng + na:].cpu().numpy()
+    loss_pairs = [("guider_loss", ls[1]), ("entropy", ls[2]), ("value_loss", ls[3]), ("kl_loss", ls[4]), ("actor_loss", ls[6]),
+                  ("actor_kl", ls[7])]
+    for k, v in loss_pairs:
+        lines.append(f"loss {k}: cuda {v:.7f} oracle {info_ref[k]:.7f}")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"grad_report_A{A}_U{U}.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+    for k, v in loss_pairs:
+        assert abs(v - info_ref[k]) <= 1e-4 * max(1.0, abs(info_ref[k])), (k, v, info_ref[k])
+    assert worst < 2e-4, worst
