@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py — end-to-end training throughput of the rec_magpo hot path (rollout + GAE + update).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W    (CPU oracle port on the host cores)
+
+A step = one `_update_step` (rec_magpo.py:106-499): T env steps of U*E envs through guider + learner + env,
+GAE, then P epochs x M minibatches of guider/learner forward+backward, the gradient all-reduce and clip+Adam.
+Metric: agent-env-steps/s = n_gpus * U * E * T * A / step time (whole job). Weak scaling: E per GPU is fixed.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENARIO = dict(num_agents=3, num_actions=10, time_limit=100, maxval=30)  # CoordSum 3x10-30 (coordsum/__init__.py:26-35)
+METRIC, UNIT = "end_to_end_training_agent_env_steps_per_sec", "agent-steps/s"
+PROF_CATS = ["gemm_nn", "gemm_tn", "colsum", "rowops", "retention_fwd", "retention_bwd", "gru_pointwise", "loss", "pack",
+             "optim", "env_step", "sample", "gae", "misc"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--num-envs", type=int, default=4096, help="arch.num_envs per GPU per update-batch slot")
+    ap.add_argument("--update-batch-size", type=int, default=2)
+    ap.add_argument("--rollout-length", type=int, default=128)
+    ap.add_argument("--chunk-envs", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="1 warm-up step, no e2e loop (for runs under ncu only)")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"rec_magpo CoordSum 3x10-30 (A=3, a=10, d=4), num_envs={args.num_envs}/GPU/slot, "
+                        f"update_batch_size={args.update_batch_size}, rollout_length={args.rollout_length}, ppo_epochs=4, "
+                        f"num_minibatches=2, Sable D=64 + GRU H=128 (configs[4] sweep point at configs[1]'s num_envs; LBF/RWARE "
+                        f"dynamics live in un-vendored jumanji, see DESIGN.md)",
+            "num_envs": args.num_envs, "update_batch_size": args.update_batch_size, "rollout_length": args.rollout_length,
+            "ppo_epochs": 4, "num_minibatches": 2, "parallelism": f"dp{n_gpus}",
+            "l2": "working set per step (>10 GB of activations + 400 MB of Sable state) exceeds the 126 MB L2"}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.1)
+        except Exception as e:  # NVML missing: report that instead of clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, as_baseline=False):
+    """The CPU restatement (oracle/) of the same step on the host cores: the reference itself is JAX-only and
+    cannot be installed here (no jax/flax/optax/jumanji wheels), so kind = "port"."""
+    import torch
+    from oracle import coordsum as ocs, learner as olr, nets as onets
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    E = 16  # bounded sample of the workload: 16 of the envs per slot, everything else as configured
+    spec = ocs.CoordSumSpec(**SCENARIO)
+    ncfg = onets.NetCfg(spec.num_agents, spec.obs_dim, spec.action_dim)
+    osys = olr.SysCfg(num_envs=E, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length)
+    state = olr.learner_setup(spec, ncfg, osys, seed=42)
+    steps, warm = (1, 0) if as_baseline else (max(1, args.steps), max(0, min(args.warmup, 1)))
+    for _ in range(warm):
+        olr.update_step(state, spec, ncfg, osys)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        olr.update_step(state, spec, ncfg, osys)
+    dt = (time.perf_counter() - t0) / steps
+    per_step = osys.update_batch_size * E * osys.rollout_length * spec.num_agents
+    val = per_step / dt
+    sample = (f"oracle update_step on {E} envs/slot x U={osys.update_batch_size} x T={osys.rollout_length} "
+              f"(same nets, P=4, M=2), torch CPU fp32 with {cores} threads, {steps} step(s) of {dt:.1f} s")
+    return val, dt, cores, sample
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, dt, cores, sample = run_reference(args)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from magpo_b200 import _lib as L
+    from magpo_b200 import init as minit
+    from magpo_b200.learner import CoordSumVec, MagpoLearner, SystemConfig
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    allreduce = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    env = CoordSumVec(**SCENARIO)
+    sysc = SystemConfig(num_envs=args.num_envs, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length,
+                        chunk_envs=args.chunk_envs)
+    lrn = MagpoLearner(env, sysc, device=dev, allreduce=allreduce, world_size=world)
+    lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, 0), minit.init_actor(env.obs_dim, env.action_dim, 1))
+    env_keys, step_key, _ = minit.setup_keys(42, world, sysc.update_batch_size, sysc.num_envs, dev)
+    lrn.reset(env_keys[rank], step_key)
+    A, T = env.num_agents, sysc.rollout_length
+    per_step = world * sysc.update_batch_size * sysc.num_envs * T * A
+    lib = L.lib()
+    lib.magpo_launch_count.restype = C.c_int64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / k
+
+    for _ in range(1 if args.quick else max(3, args.warmup)):
+        lrn.update_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = lib.magpo_launch_count()
+    ms = timed(lrn.update_step, args.steps)
+    launches = lib.magpo_launch_count() - n0
+
+    # end to end through the public call, host buffers: per step the step key goes up from pinned memory and the
+    # metrics the experiment loop consumes (episode metrics [T,B], the [P,M,8] loss sums, the new key) come back.
+    B = lrn.B
+    key_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+    key_host.copy_(lrn.key.cpu())
+    out_host = {k: torch.zeros_like(v, device="cpu").pin_memory() for k, v in
+                dict(episode_return=lrn.traj["episode_return"], episode_length=lrn.traj["episode_length"],
+                     is_terminal_step=lrn.traj["is_terminal_step"]).items()}
+    loss_host = torch.zeros(sysc.ppo_epochs, sysc.num_minibatches, 8).pin_memory()
+    h2d = key_host.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values()) + loss_host.numel() * 4 + 8
+
+    def e2e_step():
+        lrn.key.copy_(key_host, non_blocking=True)
+        metrics, losses = lrn.update_step()
+        for k, v in out_host.items():
+            v.copy_(metrics[k], non_blocking=True)
+        loss_host.copy_(losses, non_blocking=True)
+        key_host.copy_(lrn.key, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the host reads the metrics every step
+
+    ms_e2e = ms if args.quick else timed(e2e_step, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    out = {"metric": METRIC, "value": per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.summary(),
+           "e2e": {"value": per_step / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches)}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if not args.no_profile:
+        # one more step with per-category CUDA events on the launching stream (bench-only instrumentation)
+        lib.magpo_prof_enable(1 if rank == 0 else 0)
+        lrn.update_step()
+        torch.cuda.synchronize()
+        lib.magpo_prof_enable(0)
+        if rank == 0:
+            brk, total = {}, 0.0
+            for i, name in enumerate(PROF_CATS):
+                msv, work, cnt = C.c_double(), C.c_double(), C.c_int64()
+                lib.magpo_prof_read(i, C.byref(msv), C.byref(work), C.byref(cnt))
+                brk[name] = {"ms": round(msv.value, 3), "launch_scopes": cnt.value, "work": work.value}
+                total += msv.value
+            for v in brk.values():
+                v["share"] = round(v["ms"] / total, 4) if total else 0.0
+            out["breakdown_ms_per_step"] = brk
+            g = brk["gemm_nn"]
+            tf = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            out["roofline"] = {"kernel": "gemm_nn_kernel (fp32 SIMT; all forward and dX GEMMs)", "bound": "tensor", "achieved": tf,
+                               "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                               "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                               if peaks else "fallback 1.4 PFLOP/s sustained",
+                               "note": "share of the profiled step: %.2f; work = 2*M*N*K flops per launch, summed" % g["share"]}
+            hb = peaks.get("hbm_gbs", 6650.0)
+            out["roofline_hbm_kernels"] = {
+                k: {"achieved_GBps": round(brk[k]["work"] / (brk[k]["ms"] * 1e-3) / 1e9, 1) if brk[k]["ms"] else None,
+                    "frac_of_measured_hbm": round(brk[k]["work"] / (brk[k]["ms"] * 1e-3) / 1e9 / hb, 4) if brk[k]["ms"] else None}
+                for k in ("gae", "env_step", "rowops", "loss", "optim", "pack")}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, dt, cores, sample = run_reference(args, as_baseline=True)
+        out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

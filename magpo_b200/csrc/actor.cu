@@ -126,6 +126,7 @@ int actor_forward(cudaStream_t s, const ActorP& p, int T, int N, int A, int d, i
     const float* hu = w.HU + (size_t)t * Rs * kH;
     MAGPO_TRY(gemm_nn(s, Rs, 3 * kH, kH, hu, kH, p.Wh, 3 * kH, nullptr, w.gh, 3 * kH, 0));
     const uint8_t* dn = (t + 1 < T) ? done + (size_t)(t + 1) * N : nullptr;
+    ProfScope ps(PROF_GRU, s, 4.0 * kH * 13 * (double)Rs);
     gru_gate_fwd_kernel<<<g256(Rs * kH), 256, 0, s>>>(
         Rs, A, w.gi + (size_t)t * Rs * 3 * kH, w.gh, p.bhn, hu, dn, w.rzn ? w.rzn + (size_t)t * Rs * 3 * kH : nullptr,
         w.ghn ? w.ghn + (size_t)t * Rs * kH : nullptr, w.Y + (size_t)t * Rs * kH, w.HU + (size_t)(t + 1) * Rs * kH);
@@ -159,9 +160,12 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
   for (int t = T - 1; t >= 0; --t) {
     const size_t o1 = (size_t)t * Rs * kH, o3 = (size_t)t * Rs * 3 * kH;
     const bool last = (t == T - 1);
+    {
+    ProfScope ps(PROF_GRU, s, 4.0 * kH * 14 * (double)Rs);
     gru_gate_bwd_kernel<<<g256(Rs * kH), 256, 0, s>>>(Rs, A, w.dB + o1, last ? nullptr : w.carry,
                                                       last ? nullptr : done + (size_t)(t + 1) * N, w.rzn + o3,
                                                       w.ghn + o1, w.HU + o1, dgi + o3, w.dgh + o3, w.carry);
+    }
     MAGPO_LAUNCH_OK();
     if (t > 0)  // carry += dGH @ Wh^T  (gradient w.r.t. hu_t; masked by done_t when consumed at t-1)
       MAGPO_TRY(gemm_nn(s, Rs, kH, 3 * kH, w.dgh + o3, 3 * kH, pt.WhT, kH, nullptr, w.carry, kH, GEMM_ACCUMULATE));

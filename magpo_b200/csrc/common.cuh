@@ -20,7 +20,25 @@ void set_cuda_error(cudaError_t e, const char* file, int line);
     }                                                         \
   } while (0)
 
-#define MAGPO_LAUNCH_OK() MAGPO_CUDA_OK(cudaGetLastError())
+void note_launch();
+#define MAGPO_LAUNCH_OK()              \
+  do {                                 \
+    ::magpo::note_launch();            \
+    MAGPO_CUDA_OK(cudaGetLastError()); \
+  } while (0)
+
+// Optional per-category device timing (CUDA events on the launching stream), used by bench.py for the live
+// roofline numbers and the per-kernel breakdown. Off by default; zero cost when off.
+enum ProfCat {
+  PROF_GEMM_NN = 0, PROF_GEMM_TN, PROF_COLSUM, PROF_ROWOPS, PROF_RET_FWD, PROF_RET_BWD, PROF_GRU, PROF_LOSS, PROF_PACK,
+  PROF_OPTIM, PROF_ENV, PROF_SAMPLE, PROF_GAE, PROF_MISC, PROF_NUM
+};
+struct ProfScope {
+  int idx;
+  cudaStream_t s;
+  ProfScope(int cat, cudaStream_t s, double work);
+  ~ProfScope();
+};
 
 #define MAGPO_TRY(expr)          \
   do {                           \

@@ -174,6 +174,9 @@ int coordsum_step_launch(cudaStream_t s, const MagpoCoordSumCfg* cfg, int B, con
   if (cfg->num_agents < 1 || cfg->num_actions < 1 || cfg->time_limit < 1 || cfg->maxval < 1) return MAGPO_ERR_ARG;
   if (cfg->num_actions > cfg->time_limit) return MAGPO_ERR_UNSUPPORTED;  // bincount(length=time_limit) would drop entries
   size_t smem = (size_t)kStepWarps * cfg->time_limit * sizeof(int32_t);
+  // algorithmic bytes per env-step: record row + target + actions in; obs, mask, reward, metrics out
+  const int A_ = cfg->num_agents, a_ = cfg->num_actions;
+  ProfScope ps(PROF_ENV, s, (double)B * (4.0 * cfg->time_limit + 12 + 4 * A_ + 8 + 2 * 4 * A_ * (A_ + 1) + a_ * A_ + 16 * A_ + 10));
   coordsum_step_kernel<<<(unsigned)ceil_div(B, kStepWarps), kStepWarps * 32, smem, s>>>(*cfg, B, action, st, ts, done_out);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;

@@ -1,6 +1,9 @@
 // Library-level entry points: version string and CUDA error reporting.
 #include <string.h>
 
+#include <atomic>
+#include <vector>
+
 #include "common.cuh"
 
 namespace magpo {
@@ -11,9 +14,55 @@ void set_cuda_error(cudaError_t e, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
 }
 
+static std::atomic<int64_t> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- profiling
+static bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+static std::vector<ProfRec> g_recs;
+static size_t g_used = 0;
+
+ProfScope::ProfScope(int cat, cudaStream_t st, double work) : idx(-1), s(st) {
+  if (!g_prof_on) return;
+  if (g_used == g_recs.size()) {
+    ProfRec r;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    g_recs.push_back(r);
+  }
+  idx = (int)g_used++;
+  g_recs[idx].cat = cat;
+  g_recs[idx].work = work;
+  cudaEventRecord(g_recs[idx].a, s);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_recs[idx].b, s);
+}
+
 }  // namespace magpo
 
 extern "C" {
+int64_t magpo_launch_count(void) { return magpo::g_launches.load(); }
+// on != 0: start recording (drops earlier records); on == 0: stop.
+int magpo_prof_enable(int on) {
+  magpo::g_prof_on = on != 0;
+  if (on) magpo::g_used = 0;
+  return MAGPO_OK;
+}
+// Sums over the recorded scopes of category `cat`: device ms, declared work (flops or bytes), scope count.
+int magpo_prof_read(int cat, double* ms, double* work, int64_t* count) {
+  using namespace magpo;
+  if (!ms || !work || !count || cat < 0 || cat >= PROF_NUM) return MAGPO_ERR_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return MAGPO_ERR_CUDA;
+  *ms = 0; *work = 0; *count = 0;
+  for (size_t i = 0; i < g_used; ++i) {
+    if (g_recs[i].cat != cat) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_recs[i].a, g_recs[i].b) != cudaSuccess) continue;
+    *ms += t; *work += g_recs[i].work; *count += 1;
+  }
+  return MAGPO_OK;
+}
 const char* magpo_version(void) { return "magpo_b200 0.1 (sm_100a)"; }
 const char* magpo_last_cuda_error(void) { return magpo::g_err; }
 }

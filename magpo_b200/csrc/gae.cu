@@ -64,6 +64,7 @@ extern "C" int magpo_gae(magpo_stream_t s, int32_t T, int32_t B, int32_t A, cons
     return MAGPO_ERR_ARG;
   if (T == 0 || B == 0) return MAGPO_OK;
   const int64_t cols = (int64_t)B * A;
+  ProfScope ps(PROF_GAE, as_stream(s), 17.0 * (double)T * cols + 5.0 * cols);
   gae_kernel<<<(unsigned)ceil_div(cols, 128), 128, 0, as_stream(s)>>>(
       T, B, A, reward, value, done, last_value, last_done, (float)gamma, (float)(gamma * gae_lambda), advantages, targets);
   MAGPO_LAUNCH_OK();

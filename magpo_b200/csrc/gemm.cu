@@ -184,6 +184,7 @@ int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
             const float* bias, float* Y, int ldy, int flags) {
   if (M <= 0 || N <= 0) return MAGPO_OK;
   if (K <= 0) return MAGPO_ERR_ARG;
+  ProfScope ps(PROF_GEMM_NN, s, 2.0 * (double)M * N * K);
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(N, BN));
   gemm_nn_kernel<<<grid, 256, 0, s>>>((int)M, N, K, X, ldx, W, ldw, bias, Y, ldy, flags);
   MAGPO_LAUNCH_OK();
@@ -201,6 +202,7 @@ static int64_t slab_rows(int64_t M, int tiles) {
 int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW,
             int ldw) {
   if (M <= 0 || N <= 0 || K <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_GEMM_TN, s, 2.0 * (double)M * N * K);
   const int nt = (int)ceil_div(N, 64), kt = (int)ceil_div(K, 64);
   const int64_t rows = slab_rows(M, nt * kt);
   dim3 grid((unsigned)ceil_div(M, rows), nt, kt);
@@ -211,6 +213,7 @@ int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
 
 int colsum(cudaStream_t s, int64_t M, int N, const float* dY, int ldy, float* db) {
   if (M <= 0 || N <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_COLSUM, s, 4.0 * (double)M * N);
   const int nt = (int)ceil_div(N, 64);
   int64_t rows = std::max<int64_t>(64, ceil_div(M, (int64_t)(4 * kNumSMs) / nt + 1));
   dim3 grid((unsigned)ceil_div(M, rows), nt);

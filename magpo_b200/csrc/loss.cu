@@ -180,10 +180,13 @@ int adv_stats(cudaStream_t s, int T, int B, int A, const float* adv, const int32
   if (U < 1 || U > 32 || n_env % U) return MAGPO_ERR_ARG;
   const int nps = n_env / U;
   const int64_t total = (int64_t)T * A * nps;
+  ProfScope ps(PROF_LOSS, s, 8.0 * (double)total * U);
   MAGPO_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * U, s));
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(total, 256), 2 * kNumSMs), U);
   adv_stats_kernel<<<grid, 256, 0, s>>>(T, B, A, adv, env_index, n_env, nps, 0, acc);
+  MAGPO_LAUNCH_OK();
   adv_stats_kernel<<<grid, 256, 0, s>>>(T, B, A, adv, env_index, n_env, nps, 1, acc);
+  MAGPO_LAUNCH_OK();
   adv_stats_finish_kernel<<<1, 32, 0, s>>>(U, total, acc, stats);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
@@ -195,6 +198,7 @@ int magpo_losses(cudaStream_t s, int64_t R, int N, int A, int a, const MagpoSysC
                  const int32_t* env_slot, const float* stats, float* dlg, float* dll, float* dvalue,
                  float* loss_sums) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_LOSS, s, (double)R * (16.0 * a + a + 32.0));
   LossHyper hp;
   hp.clip_eps = (float)sys->clip_eps;
   hp.ent_coef = (float)sys->ent_coef;

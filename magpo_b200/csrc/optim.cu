@@ -67,10 +67,13 @@ extern "C" int magpo_clip_adam(magpo_stream_t s_, int64_t n, float* params, cons
   if (n < 0 || !params || !grads || !mu || !nu || !count || !scratch) return MAGPO_ERR_ARG;
   if (n == 0) return MAGPO_OK;
   cudaStream_t s = as_stream(s_);
+  ProfScope ps(PROF_OPTIM, s, 32.0 * (double)n);
   MAGPO_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * 8, s));
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 4);
   sumsq_kernel<<<grid, 256, 0, s>>>(n, grads, grad_scale, scratch);
+  MAGPO_LAUNCH_OK();
   adam_prelude_kernel<<<1, 32, 0, s>>>(scratch, count, max_norm);
+  MAGPO_LAUNCH_OK();
   adam_kernel<<<grid, 256, 0, s>>>(n, params, grads, mu, nu, scratch, grad_scale, lr, max_norm);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;

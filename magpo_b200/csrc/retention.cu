@@ -222,6 +222,7 @@ int retention_fwd(cudaStream_t s, int T, int N, int A, float kappa, bool causal,
   if (T <= 0 || N <= 0) return MAGPO_OK;
   if (A < 1 || A > kMaxAgents || (ld & 3)) return MAGPO_ERR_UNSUPPORTED;
   const size_t smem = (size_t)(3 * A * 64 + A * 16 * 64) * sizeof(float);
+  ProfScope ps(PROF_RET_FWD, s, 4.0 * 4096.0 * (double)T * N * A);
   if (causal) {
     MAGPO_TRY(set_smem(retention_fwd_kernel<true>, smem));
     retention_fwd_kernel<true><<<N, 256, smem, s>>>(T, N, A, kappa, q, k, v, ld, H0, done, ret, Hsave, Hout);
@@ -240,6 +241,7 @@ int retention_bwd(cudaStream_t s, int T, int N, int A, float kappa, bool causal,
   if (T <= 0 || N <= 0) return MAGPO_OK;
   if (A < 1 || A > kMaxAgents || (ld & 3) || (ldd & 3)) return MAGPO_ERR_UNSUPPORTED;
   const size_t smem = (size_t)(4 * A * 64 + A * 16 * 64) * sizeof(float);
+  ProfScope ps(PROF_RET_BWD, s, 10.0 * 4096.0 * (double)T * N * A);
   if (causal) {
     MAGPO_TRY(set_smem(retention_bwd_kernel<true>, smem));
     retention_bwd_kernel<true><<<N, 256, smem, s>>>(T, N, A, kappa, q, k, v, ld, done, Hsave, dret, dq, dk, dv, ldd);

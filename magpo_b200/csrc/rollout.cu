@@ -134,15 +134,21 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
                                   w.sa, value, nullptr, dry ? nullptr : hs.encoder));
   if (!action) return MAGPO_OK;
   for (int i = 0; i < A; ++i) {
-    gather_agent_kernel<<<g256((int64_t)B * kD), 256, 0, s>>>(B, A, i, kD, w.sa.x, w.xrep_i);
-    gather_agent_kernel<<<g256((int64_t)B * kD), 256, 0, s>>>(B, A, i, kD, w.sa.xpe, w.xrep_pe_i);
-    gather_agent_i32_kernel<<<g256(B), 256, 0, s>>>(B, A, i, step_count, w.step_i);
-    MAGPO_LAUNCH_OK();
+    {
+      ProfScope ps(PROF_MISC, s, 4.0 * 256.0 * B);
+      gather_agent_kernel<<<g256((int64_t)B * kD), 256, 0, s>>>(B, A, i, kD, w.sa.x, w.xrep_i);
+      MAGPO_LAUNCH_OK();
+      gather_agent_kernel<<<g256((int64_t)B * kD), 256, 0, s>>>(B, A, i, kD, w.sa.xpe, w.xrep_pe_i);
+      MAGPO_LAUNCH_OK();
+      gather_agent_i32_kernel<<<g256(B), 256, 0, s>>>(B, A, i, step_count, w.step_i);
+      MAGPO_LAUNCH_OK();
+    }
     // the once-per-timestep decay (and the reset on done) is applied when the first agent's token arrives
     MAGPO_TRY(sable_decoder_forward(s, gp, 1, B, 1, i == 0 ? -1 : 0, a, ms, w.prev_action, w.xrep_i, w.xrep_pe_i,
                                     w.step_i, i == 0 ? prev_done : nullptr, hs.decoder_self, hs.decoder_cross,
                                     i == 0 ? kappa : 1.0f, w.pe, w.sa, w.logits_i, nullptr, nullptr,
                                     dry ? nullptr : hs.decoder_self, dry ? nullptr : hs.decoder_cross));
+    ProfScope ps(PROF_SAMPLE, s, (double)B * (5.0 * a + 12.0));
     sample_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, A, i, a, gumbel_rows, w.logits_i, action_mask,
                                                             sample_keys + 2 * i, action, log_prob, w.prev_action,
                                                             masked_logits);
@@ -235,8 +241,11 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
   MAGPO_CUDA_OK(cudaMemcpyAsync(traj.policy_h0, policy_h, BA * kH * sizeof(float), cudaMemcpyDeviceToDevice, s));
   const unsigned gz = g256((int64_t)B * (kD * kD / 4));
   copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, hs.encoder, traj.done, traj.sable_h0.encoder);
+  MAGPO_LAUNCH_OK();
   copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, hs.decoder_self, traj.done, traj.sable_h0.decoder_self);
+  MAGPO_LAUNCH_OK();
   copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, hs.decoder_cross, traj.done, traj.sable_h0.decoder_cross);
+  MAGPO_LAUNCH_OK();
   rollout_keys_kernel<<<1, 32, 0, s>>>(key, T + 1, A, w.sample_keys);
   MAGPO_LAUNCH_OK();
 

@@ -400,12 +400,14 @@ __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
 
 int rms_general_fwd(cudaStream_t s, int64_t R, int C, const float* x, const float* scale, float* y) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, 8.0 * R * C);
   rms_general_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, C, x, scale, y);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
 int rms_general_bwd_scale(cudaStream_t s, int64_t R, int C, const float* x, const float* dy, float* dscale) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, 8.0 * R * C);
   if (C > 128) return MAGPO_ERR_UNSUPPORTED;
   rms_general_bwd_scale_kernel<<<row_grid(R), 256, C * sizeof(float), s>>>(R, C, x, dy, dscale);
   MAGPO_LAUNCH_OK();
@@ -414,6 +416,7 @@ int rms_general_bwd_scale(cudaStream_t s, int64_t R, int C, const float* x, cons
 int act_rms_fwd(cudaStream_t s, int64_t R, const float* z, const float* res, const float* scale, int flags,
                 const float* pe, const int32_t* step, int max_step, float* y, float* ype) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, (res ? 3 : 2) * 256.0 * R + (ype ? 256.0 * R : 0));
   act_rms_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, z, res, scale, flags, pe, step, max_step, y, ype);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
@@ -421,6 +424,7 @@ int act_rms_fwd(cudaStream_t s, int64_t R, const float* z, const float* res, con
 int act_rms_bwd(cudaStream_t s, int64_t R, const float* z, const float* res, const float* scale, int flags,
                 const float* dy1, const float* dy2, const float* dy3, float* dout, float* dscale) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, (2 + (res ? 1 : 0) + 1 + (dy2 ? 1 : 0) + (dy3 ? 1 : 0)) * 256.0 * R);
   act_rms_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, z, res, scale, flags, dy1, dy2, dy3, dout, dscale);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
@@ -428,6 +432,7 @@ int act_rms_bwd(cudaStream_t s, int64_t R, const float* z, const float* res, con
 int gn_gate_fwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float* ret, const float* gn_scale,
                 const float* gn_bias, float* gated) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, 3 * 256.0 * R);
   gn_gate_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, g, ldg, ret, gn_scale, gn_bias, gated);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
@@ -436,6 +441,7 @@ int gn_gate_bwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float*
                 const float* gn_bias, const float* dgated, float* dg, int lddg, float* dret, float* dgn_scale,
                 float* dgn_bias) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, 5 * 256.0 * R);
   gn_gate_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, g, ldg, ret, gn_scale, gn_bias, dgated, dg, lddg, dret,
                                                  dgn_scale, dgn_bias);
   MAGPO_LAUNCH_OK();
@@ -443,12 +449,14 @@ int gn_gate_bwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float*
 }
 int swiglu_fwd(cudaStream_t s, int64_t R, const float* gl, float* h) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, 3 * 256.0 * R);
   swiglu_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, gl, h);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
 int swiglu_bwd(cudaStream_t s, int64_t R, const float* gl, const float* dh, float* dgl) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, 5 * 256.0 * R);
   swiglu_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, gl, dh, dgl);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
@@ -456,6 +464,7 @@ int swiglu_bwd(cudaStream_t s, int64_t R, const float* gl, const float* dh, floa
 int head_fwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, const float* b3,
              int nout, float* out) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, (256.0 + 4.0 * nout) * R);
   if (nout < 1 || nout > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
   head_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, b3, nout, out);
   MAGPO_LAUNCH_OK();
@@ -464,6 +473,7 @@ int head_fwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, con
 int head_bwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, int nout,
              const float* dout, float* dzh, float* dscale, float* dW3, float* db3) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, (512.0 + 4.0 * nout) * R);
   if (nout < 1 || nout > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
   head_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
   MAGPO_LAUNCH_OK();
@@ -472,6 +482,7 @@ int head_bwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, con
 int embed_fwd(cudaStream_t s, int64_t R, int A, const int32_t* action, const float* Wa, const float* scale,
               const float* pe, const int32_t* step, int max_step, float* x, float* xpe) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, (512.0 + 8.0) * R);
   embed_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, A, action, Wa, scale, pe, step, max_step, x, xpe);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
@@ -479,6 +490,7 @@ int embed_fwd(cudaStream_t s, int64_t R, int A, const int32_t* action, const flo
 int embed_bwd(cudaStream_t s, int64_t R, int A, int a, const int32_t* action, const float* Wa, const float* scale,
               const float* dy1, const float* dy2, float* dWa, float* dscale) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, (256.0 + (dy2 ? 256.0 : 0) + 8.0) * R);
   if (a > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
   embed_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, A, a, action, Wa, scale, dy1, dy2, dWa, dscale);
   MAGPO_LAUNCH_OK();
@@ -486,6 +498,7 @@ int embed_bwd(cudaStream_t s, int64_t R, int A, int a, const int32_t* action, co
 }
 int add_pe(cudaStream_t s, int64_t R, const float* x, const float* pe, const int32_t* step, int max_step, float* y) {
   if (R <= 0) return MAGPO_OK;
+  ProfScope ps(PROF_ROWOPS, s, 512.0 * R);
   add_pe_kernel<<<row_grid(R), 256, 0, s>>>(R, x, pe, step, max_step, y);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;

@@ -198,6 +198,7 @@ int magpo_pack_minibatch(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoS
   cudaStream_t s = as_stream(s_);
   const int A = net->n_agents, T = sys->rollout_length, B = sys->update_batch_size * sys->num_envs;
   const int64_t R = (int64_t)T * n_env * A;
+  ProfScope ps(PROF_PACK, s, 2.0 * (double)R * (4.0 * net->obs_dim + net->action_dim + 24.0) + 2.0 * n_env * (3 * 16384.0 + 512.0 * A));
   pack_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(R, 8), (int64_t)kNumSMs * 16), 256, 0, s>>>(
       T, B, A, net->obs_dim, net->action_dim, n_env, traj, advantages, targets, env_index, agent_perm,
       const_cast<float*>(out.agents_view), const_cast<uint8_t*>(out.action_mask), const_cast<int32_t*>(out.step_count),

@@ -85,7 +85,7 @@ def param_views(flat: torch.Tensor, table) -> dict:
         if d1 == 0:
             views[name] = flat[off:off + d0]
         else:
-            views[name] = torch.as_strided(flat, (d0, d1), (ld, 1), off)
+            views[name] = torch.as_strided(flat, (d0, d1), (ld, 1), flat.storage_offset() + off)
     return views
 
 
