@@ -84,6 +84,9 @@ void ActorT::plan(Arena& ar, int a) {
   WhT = ar.get<float>(3 * kH * kH);
   postT = ar.get<float>(kH * kH);
   headT = ar.get<float>((size_t)a * kH);
+  region_n = (int64_t)(reinterpret_cast<uintptr_t>(headT) + (size_t)a * kH * sizeof(float) - reinterpret_cast<uintptr_t>(WiT)) / 4;
+  region_hi = ar.get<float>((size_t)region_n);
+  region_lo = ar.get<float>((size_t)region_n);
 }
 
 int actor_transpose(cudaStream_t s, const ActorP& p, const ActorT& t, int a) {
@@ -91,6 +94,7 @@ int actor_transpose(cudaStream_t s, const ActorP& p, const ActorT& t, int a) {
   MAGPO_TRY(transpose(s, kH, 3 * kH, p.Wh, t.WhT));
   MAGPO_TRY(transpose(s, kH, kH, p.post_w, t.postT));
   MAGPO_TRY(transpose(s, kH, a, p.head_w, t.headT));
+  if (tc_enabled()) MAGPO_TRY(tc_prepare_region(s, t.WiT, t.region_n, t.region_hi, t.region_lo));
   return MAGPO_OK;
 }
 
@@ -115,16 +119,16 @@ void ActorActs::plan(Arena& ar, int64_t R, int64_t Rs, int a, bool with_backward
 }
 
 // RecurrentActor.apply over T steps (base.py:161-184): masked=false raw logits [T*Rs, a].
-int actor_forward(cudaStream_t s, const ActorP& p, int T, int N, int A, int d, int a, const float* agents_view,
+int actor_forward(cudaStream_t s, const ActorP& p, const ActorT* pt, int T, int N, int A, int d, int a, const float* agents_view,
                   const uint8_t* done, const float* h0, const ActorActs& w, float* logits, float* h_out) {
   const int64_t Rs = (int64_t)N * A, R = Rs * T;
-  MAGPO_TRY(gemm_nn(s, R, kH, d, agents_view, d, p.pre_w, kH, p.pre_b, w.e, kH, GEMM_RELU));
-  MAGPO_TRY(gemm_nn(s, R, 3 * kH, kH, w.e, kH, p.Wi, 3 * kH, p.bi, w.gi, 3 * kH, 0));
+  MAGPO_TRY(gemm_nn(s, R, kH, d, agents_view, d, wref(p.pre_w, kH), p.pre_b, w.e, kH, GEMM_RELU));
+  MAGPO_TRY(gemm_nn(s, R, 3 * kH, kH, w.e, kH, wref(p.Wi, 3 * kH, pt ? pt->WiT : nullptr, kH), p.bi, w.gi, 3 * kH, 0));
   mask_rows_kernel<<<g256(Rs * kH), 256, 0, s>>>(Rs, A, h0, done, w.HU);
   MAGPO_LAUNCH_OK();
   for (int t = 0; t < T; ++t) {
     const float* hu = w.HU + (size_t)t * Rs * kH;
-    MAGPO_TRY(gemm_nn(s, Rs, 3 * kH, kH, hu, kH, p.Wh, 3 * kH, nullptr, w.gh, 3 * kH, 0));
+    MAGPO_TRY(gemm_nn(s, Rs, 3 * kH, kH, hu, kH, wref(p.Wh, 3 * kH, pt ? pt->WhT : nullptr, kH), nullptr, w.gh, 3 * kH, 0));
     const uint8_t* dn = (t + 1 < T) ? done + (size_t)(t + 1) * N : nullptr;
     ProfScope ps(PROF_GRU, s, 4.0 * kH * 13 * (double)Rs);
     gru_gate_fwd_kernel<<<g256(Rs * kH), 256, 0, s>>>(
@@ -135,8 +139,8 @@ int actor_forward(cudaStream_t s, const ActorP& p, int T, int N, int A, int d, i
   if (h_out) MAGPO_CUDA_OK(cudaMemcpyAsync(h_out, w.Y + (size_t)(T - 1) * Rs * kH, (size_t)Rs * kH * sizeof(float),
                                            cudaMemcpyDeviceToDevice, s));
   if (logits) {
-    MAGPO_TRY(gemm_nn(s, R, kH, kH, w.Y, kH, p.post_w, kH, p.post_b, w.post, kH, GEMM_RELU));
-    MAGPO_TRY(gemm_nn(s, R, a, kH, w.post, kH, p.head_w, a, p.head_b, logits, a, 0));
+    MAGPO_TRY(gemm_nn(s, R, kH, kH, w.Y, kH, wref(p.post_w, kH, pt ? pt->postT : nullptr, kH), p.post_b, w.post, kH, GEMM_RELU));
+    MAGPO_TRY(gemm_nn(s, R, a, kH, w.post, kH, wref(p.head_w, a), p.head_b, logits, a, 0));
   }
   return MAGPO_OK;
 }
@@ -149,12 +153,12 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
   // head + post torso
   MAGPO_TRY(gemm_tn(s, R, a, kH, w.post, kH, dlogits, a, g.head_w, a));
   MAGPO_TRY(colsum(s, R, a, dlogits, a, g.head_b));
-  MAGPO_TRY(gemm_nn(s, R, kH, a, dlogits, a, pt.headT, kH, nullptr, w.dA, kH, 0));
+  MAGPO_TRY(gemm_nn(s, R, kH, a, dlogits, a, wref(pt.headT, kH), nullptr, w.dA, kH, 0));
   relu_bwd_kernel<<<g256(R * kH), 256, 0, s>>>(R * kH, w.post, w.dA);
   MAGPO_LAUNCH_OK();
   MAGPO_TRY(gemm_tn(s, R, kH, kH, w.Y, kH, w.dA, kH, g.post_w, kH));
   MAGPO_TRY(colsum(s, R, kH, w.dA, kH, g.post_b));
-  MAGPO_TRY(gemm_nn(s, R, kH, kH, w.dA, kH, pt.postT, kH, nullptr, w.dB, kH, 0));  // dB = dL/dY
+  MAGPO_TRY(gemm_nn(s, R, kH, kH, w.dA, kH, wref(pt.postT, kH, p.post_w, kH), nullptr, w.dB, kH, 0));  // dB = dL/dY
   // reverse scan; dgi reuses the gi buffer (dead after the forward)
   float* dgi = w.gi;
   for (int t = T - 1; t >= 0; --t) {
@@ -168,13 +172,13 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
     }
     MAGPO_LAUNCH_OK();
     if (t > 0)  // carry += dGH @ Wh^T  (gradient w.r.t. hu_t; masked by done_t when consumed at t-1)
-      MAGPO_TRY(gemm_nn(s, Rs, kH, 3 * kH, w.dgh + o3, 3 * kH, pt.WhT, kH, nullptr, w.carry, kH, GEMM_ACCUMULATE));
+      MAGPO_TRY(gemm_nn(s, Rs, kH, 3 * kH, w.dgh + o3, 3 * kH, wref(pt.WhT, kH, p.Wh, 3 * kH), nullptr, w.carry, kH, GEMM_ACCUMULATE));
   }
   MAGPO_TRY(gemm_tn(s, R, 3 * kH, kH, w.HU, kH, w.dgh, 3 * kH, g.Wh, 3 * kH));
   MAGPO_TRY(colsum(s, R, kH, w.dgh + 2 * kH, 3 * kH, g.bhn));
   MAGPO_TRY(gemm_tn(s, R, 3 * kH, kH, w.e, kH, dgi, 3 * kH, g.Wi, 3 * kH));
   MAGPO_TRY(colsum(s, R, 3 * kH, dgi, 3 * kH, g.bi));
-  MAGPO_TRY(gemm_nn(s, R, kH, 3 * kH, dgi, 3 * kH, pt.WiT, kH, nullptr, w.dA, kH, 0));  // dA = dL/de (pre-relu mask next)
+  MAGPO_TRY(gemm_nn(s, R, kH, 3 * kH, dgi, 3 * kH, wref(pt.WiT, kH, p.Wi, 3 * kH), nullptr, w.dA, kH, 0));  // dA = dL/de (pre-relu mask next)
   relu_bwd_kernel<<<g256(R * kH), 256, 0, s>>>(R * kH, w.e, w.dA);
   MAGPO_LAUNCH_OK();
   MAGPO_TRY(gemm_tn(s, R, kH, d, agents_view, d, w.dA, kH, g.pre_w, kH));

@@ -180,10 +180,16 @@ __global__ void transpose_kernel(int R, int Cc, const float* __restrict__ in, fl
 }
 }  // namespace
 
-int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* W, int ldw,
-            const float* bias, float* Y, int ldy, int flags) {
+int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, Wref Wr, const float* bias, float* Y,
+            int ldy, int flags) {
   if (M <= 0 || N <= 0) return MAGPO_OK;
   if (K <= 0) return MAGPO_ERR_ARG;
+  if (Wr.wt && !((flags & GEMM_ACCUMULATE) && ((flags & GEMM_RELU) || bias)) && tc_supported(M, N, K, X, ldx, Y, ldy, Wr.ldwt)) {
+    const float *hi, *lo;
+    if (tc_lookup(Wr.wt, &hi, &lo)) return gemm_tc(s, M, N, K, X, ldx, hi, lo, Wr.ldwt, bias, Y, ldy, flags);
+  }
+  const float* W = Wr.w;
+  const int ldw = Wr.ldw;
   ProfScope ps(PROF_GEMM_NN, s, 2.0 * (double)M * N * K);
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(N, BN));
   gemm_nn_kernel<<<grid, 256, 0, s>>>((int)M, N, K, X, ldx, W, ldw, bias, Y, ldy, flags);
@@ -237,7 +243,7 @@ using namespace magpo;
 extern "C" int magpo_test_gemm(magpo_stream_t s, int kind, int64_t M, int N, int K, const float* A, const float* B,
                                const float* bias, float* Cout, int flags) {
   cudaStream_t st = as_stream(s);
-  if (kind == 0) return gemm_nn(st, M, N, K, A, K, B, N, bias, Cout, N, flags);
+  if (kind == 0) return gemm_nn(st, M, N, K, A, K, wref(B, N), bias, Cout, N, flags);
   if (kind == 1) return gemm_tn(st, M, N, K, A, K, B, N, Cout, N);
   if (kind == 2) return colsum(st, M, N, A, N, Cout);
   if (kind == 3) return transpose(st, (int)M, N, A, Cout);

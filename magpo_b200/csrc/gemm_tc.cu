@@ -1,0 +1,469 @@
+// Tensor-core GEMM for the update path:  Y[M,N] (+)= X[M,K] @ B^T (+ bias) (relu),  B given as [N,K] (K-major).
+// fp32 in / fp32 out with fp32-faithful accuracy through the 3xTF32 split
+//     x = x_hi + x_lo  (both exactly representable in TF32, round-to-nearest):   X.B ~= Xhi.Bhi + Xlo.Bhi + Xhi.Blo
+// (dropped term ~2^-22 relative), accumulated in fp32 in tensor memory.
+//
+// Blackwell-native structure (sm_100a): persistent CTAs, one per SM, warp-specialised:
+//   warp 0      TMA producer: X tiles [128 rows x 32 floats] (one 128B-swizzle atom) into an smem ring; B (hi, lo) is loaded
+//               once per CTA and stays resident in shared memory
+//   warps 8-11  converters: split each landed X chunk in place into hi (+ a second buffer for lo), fence to the async proxy
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x3 per k-step into TMEM;
+//               tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 4-7   epilogue: tcgen05.ld (thread = row) -> bias/relu -> 128B-swizzled smem slab -> TMA store
+//               (or TMA reduce-add for Y += ...), double-buffered; TMEM accumulators are double-buffered too.
+// Every mbarrier wait is bounded and traps instead of hanging.
+#include <cuda.h>
+
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace magpo {
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_KC = 32;
+constexpr int TC_CHUNK_BYTES = TC_BM * TC_KC * 4;  // 16 KiB
+constexpr int TC_THREADS = 384;
+constexpr int TC_MAX_STAGES = 6;
+constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
+
+struct TcParams {
+  int M, N, K, BN, kchunks, stages, flags, num_row_tiles, tmem_cols;
+  const float* bias;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 24)) __trap();  // never hang the GPU: a lost arrival becomes a launch failure
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  h &= 0xFFFFE000u;
+  hi = __uint_as_float(h);
+  const float r = x - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  l &= 0xFFFFE000u;
+  lo = __uint_as_float(l);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBh,
+               const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmY, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (everything TMA touches is 1024-byte aligned)
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_chunk_bytes = p.BN * 128;
+  uint8_t* sBh = base;
+  uint8_t* sBl = sBh + (size_t)p.kchunks * b_chunk_bytes;
+  uint8_t* sA = sBl + (size_t)p.kchunks * b_chunk_bytes;          // stages x {hi 16K, lo 16K}
+  uint8_t* sOut = sA + (size_t)p.stages * 2 * TC_CHUNK_BYTES;      // 2 x 16K
+  float* sBias = reinterpret_cast<float*>(sOut + 2 * TC_CHUNK_BYTES);  // 256 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
+  uint64_t* full_raw = bars;
+  uint64_t* full_conv = bars + TC_MAX_STAGES;
+  uint64_t* empty = bars + 2 * TC_MAX_STAGES;
+  uint64_t* tmem_full = bars + 3 * TC_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* b_ready = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * p.BN;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_raw[i], 1);
+      mbar_init(&full_conv[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    mbar_init(b_ready, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 128 && threadIdx.x < 256) {  // epilogue threads stage the bias slice
+    const int j = threadIdx.x - 128;
+    for (int c = j; c < p.BN; c += 128) sBias[c] = p.bias ? p.bias[n0 + c] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(b_ready, 2u * p.kchunks * b_chunk_bytes);
+      for (int c = 0; c < p.kchunks; ++c) {
+        tma_load_2d(sBh + (size_t)c * b_chunk_bytes, &tmBh, c * TC_KC, n0, b_ready);
+        tma_load_2d(sBl + (size_t)c * b_chunk_bytes, &tmBl, c * TC_KC, n0, b_ready);
+      }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_row_tiles; tile += gridDim.x) {
+        for (int c = 0; c < p.kchunks; ++c, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
+          mbar_expect_tx(&full_raw[s], TC_CHUNK_BYTES);
+          tma_load_2d(sA + (size_t)s * 2 * TC_CHUNK_BYTES, &tmX, c * TC_KC, tile * TC_BM, &full_raw[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(p.BN);
+      mbar_wait(b_ready, 0);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.num_row_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+        for (int c = 0; c < p.kchunks; ++c, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&full_conv[s], (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA + (size_t)s * 2 * TC_CHUNK_BYTES);
+          const uint32_t a_lo = a_hi + TC_CHUNK_BYTES;
+          const uint32_t b_hi = smem_u32(sBh + (size_t)c * b_chunk_bytes);
+          const uint32_t b_lo = smem_u32(sBl + (size_t)c * b_chunk_bytes);
+#pragma unroll
+          for (int k = 0; k < TC_KC / 8; ++k) {
+            const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes along K inside the swizzle atom
+            umma_tf32(tmem_d, umma_desc_k_sw128(a_lo + ko), umma_desc_k_sw128(b_hi + ko), idesc, (c | k) ? 1u : 0u);
+            umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_lo + ko), idesc, 1u);
+            umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_hi + ko), idesc, 1u);
+          }
+          umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int et = threadIdx.x - 128;     // 0..127
+    const int sub = warp & 3;             // TMEM sub-partition of this warp: lanes [32*sub, 32*sub+32)
+    const int row = sub * 32 + lane;      // row of the tile this thread owns
+    const bool relu = p.flags & GEMM_RELU, accumulate = p.flags & GEMM_ACCUMULATE;
+    const int nslab = p.BN / 32;
+    uint32_t ti = 0, slab_it = 0;
+    for (int tile = blockIdx.x; tile < p.num_row_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      mbar_wait(&tmem_full[acc], (ti >> 1) & 1);
+      tc_fence_after();
+      for (int sl = 0; sl < nslab; ++sl, ++slab_it) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.BN + sl * 32), v);
+        if (sl == nslab - 1) {  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        uint8_t* buf = sOut + (size_t)(slab_it & 1) * TC_CHUNK_BYTES;
+        if (et == 0) bulk_wait_read<1>();  // the store that last used this buffer has finished reading it
+        named_bar_sync(1, 128);
+        float4* dst_row = reinterpret_cast<float4*>(buf + (size_t)row * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = __uint_as_float(v[4 * j + 0]) + sBias[sl * 32 + 4 * j + 0];
+          o.y = __uint_as_float(v[4 * j + 1]) + sBias[sl * 32 + 4 * j + 1];
+          o.z = __uint_as_float(v[4 * j + 2]) + sBias[sl * 32 + 4 * j + 2];
+          o.w = __uint_as_float(v[4 * j + 3]) + sBias[sl * 32 + 4 * j + 3];
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          dst_row[j ^ (row & 7)] = o;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          if (accumulate) tma_reduce_add_2d(&tmY, buf, n0 + sl * 32, tile * TC_BM);
+          else tma_store_2d(&tmY, buf, n0 + sl * 32, tile * TC_BM);
+          bulk_commit();
+        }
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  } else if (warp >= 8) {
+    // ===================== converters: fp32 -> (tf32 hi, tf32 lo) =====================
+    const int ct = threadIdx.x - 256;  // 0..127
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_row_tiles; tile += gridDim.x) {
+      for (int c = 0; c < p.kchunks; ++c, ++it) {
+        const int s = it % p.stages;
+        mbar_wait(&full_raw[s], (it / p.stages) & 1);
+        float4* hi = reinterpret_cast<float4*>(sA + (size_t)s * 2 * TC_CHUNK_BYTES);
+        float4* lo = hi + TC_CHUNK_BYTES / 16;
+#pragma unroll
+        for (int i = 0; i < TC_CHUNK_BYTES / 16 / 128; ++i) {
+          const int idx = ct + i * 128;
+          const float4 x = hi[idx];
+          float4 h, l;
+          split_tf32(x.x, h.x, l.x);
+          split_tf32(x.y, h.y, l.y);
+          split_tf32(x.z, h.z, l.z);
+          split_tf32(x.w, h.w, l.w);
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_conv[s]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_region_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float h, l;
+    split_tf32(x[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major [rows, cols] fp32 matrix with leading dimension ld; box = [box_rows, 32 floats], 128B swizzle
+bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct TcRegion {
+  const float* base;
+  int64_t n;
+  const float *hi, *lo;
+};
+std::vector<TcRegion> g_regions;
+bool env_tc_default() {
+  const char* e = getenv("MAGPO_TENSOR_CORES");  // "0" forces the fp32 SIMT GEMMs everywhere
+  return !(e && e[0] == '0');
+}
+bool g_tc_enabled = env_tc_default();
+bool g_attr_set = false;
+
+}  // namespace
+
+void tc_set_enabled(bool on) { g_tc_enabled = on; }
+bool tc_enabled() { return g_tc_enabled; }
+
+// Split a weight region into TF32 hi/lo copies and remember the mapping so that GEMMs on any sub-matrix find them.
+int tc_prepare_region(cudaStream_t s, const float* base, int64_t n, float* hi, float* lo) {
+  if (n <= 0) return MAGPO_OK;
+  split_region_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 4 * kNumSMs), 256, 0, s>>>(n, base, hi, lo);
+  MAGPO_LAUNCH_OK();
+  for (auto& r : g_regions)
+    if (r.base == base) {
+      r.n = n; r.hi = hi; r.lo = lo;
+      return MAGPO_OK;
+    }
+  g_regions.push_back(TcRegion{base, n, hi, lo});
+  return MAGPO_OK;
+}
+
+bool tc_lookup(const float* w, const float** hi, const float** lo) {
+  for (const auto& r : g_regions)
+    if (w >= r.base && w < r.base + r.n) {
+      *hi = r.hi + (w - r.base);
+      *lo = r.lo + (w - r.base);
+      return true;
+    }
+  return false;
+}
+
+// Pick the N tile and ring depth; false when the shape does not fit the kernel.
+static bool tc_plan(int64_t M, int N, int K, TcParams* p, uint32_t* smem_bytes) {
+  if (K % TC_KC || K < TC_KC || N % 32 || M < 1) return false;
+  const int cands[] = {256, 192, 128, 96, 64, 32};
+  for (int bn : cands) {
+    if (N % bn) continue;
+    const uint32_t b_bytes = (uint32_t)K * bn * 8;
+    const uint32_t fixed = b_bytes + 2 * TC_CHUNK_BYTES + 256 * 4 + 256 + 1024 /*alignment slack*/;
+    if (fixed + 2 * 2 * TC_CHUNK_BYTES > TC_SMEM_LIMIT) continue;
+    int stages = (int)((TC_SMEM_LIMIT - fixed) / (2 * TC_CHUNK_BYTES));
+    stages = std::min(stages, TC_MAX_STAGES);
+    p->BN = bn;
+    p->kchunks = K / TC_KC;
+    p->stages = stages;
+    int cols = 32;
+    while (cols < 2 * bn) cols <<= 1;
+    p->tmem_cols = cols;
+    *smem_bytes = fixed + (uint32_t)stages * 2 * TC_CHUNK_BYTES;
+    return true;
+  }
+  return false;
+}
+
+bool tc_supported(int64_t M, int N, int K, const float* X, int ldx, const float* Y, int ldy, int ldb) {
+  if (!g_tc_enabled || !get_encode()) return false;
+  if ((ldx & 3) || (ldy & 3) || (ldb & 3)) return false;
+  if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
+  TcParams p;
+  uint32_t smem;
+  return M >= 256 && tc_plan(M, N, K, &p, &smem);
+}
+
+// Y[M,N] (+)= X[M,K] @ B^T with B = Bhi + Blo given as [N,K] row-major (leading dimension ldb).
+int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* Bhi, const float* Blo, int ldb,
+            const float* bias, float* Y, int ldy, int flags) {
+  TcParams p;
+  uint32_t smem;
+  if (!tc_plan(M, N, K, &p, &smem)) return MAGPO_ERR_UNSUPPORTED;
+  if ((flags & GEMM_ACCUMULATE) && ((flags & GEMM_RELU) || bias)) return MAGPO_ERR_UNSUPPORTED;
+  p.M = (int)M; p.N = N; p.K = K; p.flags = flags; p.bias = bias;
+  p.num_row_tiles = (int)ceil_div(M, TC_BM);
+  CUtensorMap tmX, tmBh, tmBl, tmY;
+  if (!make_map(&tmX, X, M, K, ldx, TC_BM) || !make_map(&tmBh, Bhi, N, K, ldb, p.BN) || !make_map(&tmBl, Blo, N, K, ldb, p.BN) ||
+      !make_map(&tmY, Y, M, N, ldy, TC_BM))
+    return MAGPO_ERR_ARG;
+  if (!g_attr_set) {
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    g_attr_set = true;
+  }
+  const int n_tiles = N / p.BN;
+  dim3 grid((unsigned)std::max(1, std::min(p.num_row_tiles, kNumSMs / n_tiles)), (unsigned)n_tiles);
+  ProfScope ps(PROF_GEMM_NN, s, 2.0 * (double)M * N * K);
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmX, tmBh, tmBl, tmY, p);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+}  // namespace magpo
+
+using namespace magpo;
+
+// Test hook: Y = X @ W (+bias) through the tensor-core path. WT is W^T [N,K] row-major; scratch holds 2*N*K floats.
+extern "C" int magpo_test_gemm_tc(magpo_stream_t s_, int64_t M, int N, int K, const float* X, int ldx, const float* WT,
+                                  float* scratch, const float* bias, float* Y, int ldy, int flags) {
+  cudaStream_t s = as_stream(s_);
+  if (!tc_supported(M, N, K, X, ldx, Y, ldy, K)) return MAGPO_ERR_UNSUPPORTED;
+  MAGPO_TRY(tc_prepare_region(s, WT, (int64_t)N * K, scratch, scratch + (int64_t)N * K));
+  return gemm_tc(s, M, N, K, X, ldx, scratch, scratch + (int64_t)N * K, K, bias, Y, ldy, flags);
+}
+extern "C" int magpo_set_tensor_cores(int on) {
+  tc_set_enabled(on != 0);
+  return MAGPO_OK;
+}

@@ -12,8 +12,27 @@ constexpr int kMaxAgents = 8;
 
 enum { GEMM_ACCUMULATE = 1, GEMM_RELU = 2 };
 
+// A weight operand: `w` is [K,N] row-major (leading dimension ldw) for the fp32 SIMT kernel; `wt` (optional) is the
+// same matrix transposed, [N,K] row-major (ldwt), whose TF32 hi/lo split has been registered with
+// tc_prepare_region() — when present and the shape fits, the GEMM runs on the tcgen05 tensor-core kernel.
+struct Wref {
+  const float* w;
+  int ldw;
+  const float* wt;
+  int ldwt;
+};
+inline Wref wref(const float* w, int ldw, const float* wt = nullptr, int ldwt = 0) { return Wref{w, ldw, wt, ldwt}; }
+
 // ---- gemm.cu
-int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* W, int ldw,
+int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, Wref W, const float* bias, float* Y,
+            int ldy, int flags);
+// ---- gemm_tc.cu (tcgen05 + TMA, 3xTF32)
+void tc_set_enabled(bool on);
+bool tc_enabled();
+int tc_prepare_region(cudaStream_t s, const float* base, int64_t n, float* hi, float* lo);
+bool tc_lookup(const float* w, const float** hi, const float** lo);
+bool tc_supported(int64_t M, int N, int K, const float* X, int ldx, const float* Y, int ldy, int ldb);
+int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* Bhi, const float* Blo, int ldb,
             const float* bias, float* Y, int ldy, int flags);
 int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW,
             int ldw);

@@ -12,10 +12,10 @@
 namespace magpo {
 
 // sable.cu
-int sable_encoder_forward(cudaStream_t s, const GuiderP& p, int T, int N, int A, int d, int max_step,
+int sable_encoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int A, int d, int max_step,
                           const float* agents_view, const int32_t* step, const uint8_t* done, const float* H0,
                           float kappa, const float* pe, const SableActs& w, float* value, float* Hsave, float* Hout);
-int sable_decoder_forward(cudaStream_t s, const GuiderP& p, int T, int N, int ret_A, int embed_A, int a,
+int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int ret_A, int embed_A, int a,
                           int max_step, const int32_t* action, const float* x_rep, const float* x_rep_pe,
                           const int32_t* step, const uint8_t* done, const float* Hself0, const float* Hcross0,
                           float kappa, const float* pe, const SableActs& w, float* logits, float* Hs_self,
@@ -130,7 +130,7 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
                 const uint8_t* prev_done, const uint32_t* sample_keys, MagpoSableHState hs, bool dry,
                 int32_t* action, float* log_prob, float* value, float* masked_logits, const RolloutWs& w) {
   const int A = net->n_agents, d = net->obs_dim, a = net->action_dim, ms = net->max_step_count;
-  MAGPO_TRY(sable_encoder_forward(s, gp, 1, B, A, d, ms, agents_view, step_count, prev_done, hs.encoder, kappa, w.pe,
+  MAGPO_TRY(sable_encoder_forward(s, gp, nullptr, 1, B, A, d, ms, agents_view, step_count, prev_done, hs.encoder, kappa, w.pe,
                                   w.sa, value, nullptr, dry ? nullptr : hs.encoder));
   if (!action) return MAGPO_OK;
   for (int i = 0; i < A; ++i) {
@@ -144,7 +144,7 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
       MAGPO_LAUNCH_OK();
     }
     // the once-per-timestep decay (and the reset on done) is applied when the first agent's token arrives
-    MAGPO_TRY(sable_decoder_forward(s, gp, 1, B, 1, i == 0 ? -1 : 0, a, ms, w.prev_action, w.xrep_i, w.xrep_pe_i,
+    MAGPO_TRY(sable_decoder_forward(s, gp, nullptr, 1, B, 1, i == 0 ? -1 : 0, a, ms, w.prev_action, w.xrep_i, w.xrep_pe_i,
                                     w.step_i, i == 0 ? prev_done : nullptr, hs.decoder_self, hs.decoder_cross,
                                     i == 0 ? kappa : 1.0f, w.pe, w.sa, w.logits_i, nullptr, nullptr,
                                     dry ? nullptr : hs.decoder_self, dry ? nullptr : hs.decoder_cross));
@@ -201,7 +201,7 @@ int magpo_actor_step(magpo_stream_t s_, const MagpoNetCfg* net, int32_t B, const
   w.plan(ar, net, B, 0);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
   const ActorP ap = ActorP::bind(const_cast<float*>(actor), net->obs_dim, net->action_dim);
-  return actor_forward(as_stream(s_), ap, 1, B, net->n_agents, net->obs_dim, net->action_dim, agents_view, done,
+  return actor_forward(as_stream(s_), ap, nullptr, 1, B, net->n_agents, net->obs_dim, net->action_dim, agents_view, done,
                        policy_h, w.aa, nullptr, policy_h);
 }
 
@@ -257,7 +257,7 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
     int32_t* act = traj.action + (size_t)t * BA;
     MAGPO_TRY(get_actions(s, net, B, E, gp, kappa, obs, mask, stepc, prev_done, w.sample_keys + (size_t)t * A * 2, hs,
                           false, act, traj.log_prob + (size_t)t * BA, traj.value + (size_t)t * BA, nullptr, w));
-    MAGPO_TRY(actor_forward(s, ap, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
+    MAGPO_TRY(actor_forward(s, ap, nullptr, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
     MagpoTimeStep o = ts;
     o.reward = traj.reward + (size_t)t * BA;
     o.agents_view = traj.agents_view + (size_t)(t + 1) * BA * d;

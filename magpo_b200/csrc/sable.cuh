@@ -9,6 +9,8 @@ namespace magpo {
 struct GuiderT {
   float *WobsT, *qkvgT, *woT, *ffn_glT, *ffn_outT, *h0T;
   float *qkvg1T, *wo1T, *qkvg2T, *wo2T, *dffn_glT, *dffn_outT, *dh0T;
+  float *region_hi, *region_lo;  // TF32 hi/lo split of [WobsT, dh0T + 64*64)
+  int64_t region_n;
   void plan(Arena& ar, int d);
 };
 int guider_transpose(cudaStream_t s, const GuiderP& p, const GuiderT& t, int d);
@@ -38,8 +40,8 @@ struct SableBatch {
 };
 
 // SableNetwork.__call__ (sable_network.py:412-441): value [R], raw (un-masked) logits [R,a].
-int sable_train_forward(cudaStream_t s, const GuiderP& p, const SableBatch& b, const SableActs& w, float* value,
-                        float* logits, bool save_states);
+int sable_train_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, const SableBatch& b, const SableActs& w,
+                        float* value, float* logits, bool save_states);
 // Backward of the above given dL/dlogits [R,a] (zero at illegal actions) and dL/dvalue [R]; grads accumulate into g.
 int sable_train_backward(cudaStream_t s, const GuiderP& p, const GuiderT& pt, const SableBatch& b, const SableActs& w,
                          const float* dlogits, const float* dvalue, const GuiderP& g);

@@ -109,11 +109,15 @@ struct UpdateWs {
   SableActs sa;
   ActorActs aa;
   float *pe, *lg, *ll, *value, *dlg, *dll, *dvalue;
+  float *g_hi, *g_lo, *a_hi, *a_lo;  // TF32 hi/lo images of the two flat parameter buffers (dX operands)
   void plan(Arena& ar, const MagpoNetCfg* net, int T, int N, bool with_backward) {
     const int A = net->n_agents, a = net->action_dim, d = net->obs_dim;
     const int64_t Rs = (int64_t)N * A, R = Rs * T;
     gt.plan(ar, d);
     at.plan(ar, a);
+    const int64_t n_g = GuiderP::bind(nullptr, d, a).total, n_a = ActorP::bind(nullptr, d, a).total;
+    g_hi = ar.get<float>((size_t)n_g); g_lo = ar.get<float>((size_t)n_g);
+    a_hi = ar.get<float>((size_t)n_a); a_lo = ar.get<float>((size_t)n_a);
     sa.plan(ar, R, (int64_t)T * N, d, with_backward);
     aa.plan(ar, R, Rs, a, with_backward);
     pe = ar.get<float>((size_t)(net->max_step_count + 1) * kD);
@@ -244,9 +248,13 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
   MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
   MAGPO_TRY(guider_transpose(s, gp, w.gt, d));
   MAGPO_TRY(actor_transpose(s, ap, w.at, a));
+  if (tc_enabled()) {
+    MAGPO_TRY(tc_prepare_region(s, guider, gp.total, w.g_hi, w.g_lo));
+    MAGPO_TRY(tc_prepare_region(s, actor, ap.total, w.a_hi, w.a_lo));
+  }
   const SableBatch b = make_batch(net, mb, w.pe);
-  MAGPO_TRY(sable_train_forward(s, gp, b, w.sa, w.value, w.lg, true));
-  MAGPO_TRY(actor_forward(s, ap, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
+  MAGPO_TRY(sable_train_forward(s, gp, &w.gt, b, w.sa, w.value, w.lg, true));
+  MAGPO_TRY(actor_forward(s, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
   MAGPO_TRY(magpo_losses(s, R, N, A, a, sys, inv_tokens, w.lg, w.ll, mb.action_mask, mb.action, mb.log_prob,
                          mb.advantages, w.value, mb.value, mb.targets, env_slot, adv_stats_, w.dlg, w.dll, w.dvalue,
                          loss_sums));
@@ -268,7 +276,7 @@ int magpo_guider_forward(magpo_stream_t s_, const MagpoNetCfg* net, const float*
   const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim);
   MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
   const SableBatch b = make_batch(net, mb, w.pe);
-  MAGPO_TRY(sable_train_forward(s, gp, b, w.sa, value, logits, false));
+  MAGPO_TRY(sable_train_forward(s, gp, nullptr, b, w.sa, value, logits, false));
   const int64_t n = (int64_t)mb.T * mb.N * net->n_agents * net->action_dim;
   mask_logits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(n, mb.action_mask, logits);
   MAGPO_LAUNCH_OK();
@@ -286,7 +294,7 @@ int magpo_actor_forward(magpo_stream_t s_, const MagpoNetCfg* net, const float* 
   w.plan(ar, net, mb.T, mb.N, false);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
   const ActorP ap = ActorP::bind(const_cast<float*>(actor), net->obs_dim, net->action_dim);
-  MAGPO_TRY(actor_forward(s, ap, mb.T, mb.N, net->n_agents, net->obs_dim, net->action_dim, mb.agents_view, mb.done,
+  MAGPO_TRY(actor_forward(s, ap, nullptr, mb.T, mb.N, net->n_agents, net->obs_dim, net->action_dim, mb.agents_view, mb.done,
                           mb.policy_h0, w.aa, logits, nullptr));
   const int64_t n = (int64_t)mb.T * mb.N * net->n_agents * net->action_dim;
   mask_logits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(n, mb.action_mask, logits);

@@ -116,9 +116,10 @@ def test_gae_bit_exact(dev, T, B, A):
                                np.repeat(last_done[:, None], A, -1), 0.99, 0.95)
     adv = torch.zeros(T, B, A, device=dev)
     tgt = torch.zeros(T, B, A, device=dev)
-    L.call("magpo_gae", L.stream_ptr(), T, B, A, L.ptr(dt(reward, dev)), L.ptr(dt(value, dev)),
-           L.ptr(dt(done_env.astype(np.uint8), dev)), L.ptr(dt(last_value, dev)), L.ptr(dt(last_done.astype(np.uint8), dev)),
-           C.c_double(0.99), C.c_double(0.95), L.ptr(adv), L.ptr(tgt))
+    keep = [dt(reward, dev), dt(value, dev), dt(done_env.astype(np.uint8), dev), dt(last_value, dev),
+            dt(last_done.astype(np.uint8), dev)]  # device tensors must outlive the call
+    L.call("magpo_gae", L.stream_ptr(), T, B, A, *[L.ptr(k) for k in keep], C.c_double(0.99), C.c_double(0.95), L.ptr(adv),
+           L.ptr(tgt))
     assert (adv.cpu().numpy() == adv_ref).all()
     assert (tgt.cpu().numpy() == tgt_ref).all()
     # O(T^2) direct sum (size-independent property)
@@ -144,20 +145,22 @@ def test_gemm_blocks(dev, M, N, K):
     b = rng.standard_normal(N).astype(np.float32)
     Y = torch.zeros(M, N, device=dev)
     s = L.stream_ptr()
-    L.call("magpo_test_gemm", s, 0, C.c_int64(M), N, K, L.ptr(dt(X, dev)), L.ptr(dt(W, dev)), L.ptr(dt(b, dev)), L.ptr(Y), 0)
+    Xd, Wd, bd = dt(X, dev), dt(W, dev), dt(b, dev)
+    L.call("magpo_test_gemm", s, 0, C.c_int64(M), N, K, L.ptr(Xd), L.ptr(Wd), L.ptr(bd), L.ptr(Y), 0)
     ref = X.astype(np.float64) @ W.astype(np.float64) + b
     assert rel_err(Y.cpu().numpy(), ref) < 2e-6
-    L.call("magpo_test_gemm", s, 0, C.c_int64(M), N, K, L.ptr(dt(X, dev)), L.ptr(dt(W, dev)), L.ptr(dt(b, dev)), L.ptr(Y), 3)
+    L.call("magpo_test_gemm", s, 0, C.c_int64(M), N, K, L.ptr(Xd), L.ptr(Wd), L.ptr(bd), L.ptr(Y), 3)
     assert rel_err(Y.cpu().numpy(), np.maximum(2 * ref, 0)) < 2e-6  # accumulate + relu
     dY = rng.standard_normal((M, N)).astype(np.float32)
     dW = torch.zeros(K, N, device=dev)
-    L.call("magpo_test_gemm", s, 1, C.c_int64(M), N, K, L.ptr(dt(X, dev)), L.ptr(dt(dY, dev)), None, L.ptr(dW), 0)
+    dYd = dt(dY, dev)
+    L.call("magpo_test_gemm", s, 1, C.c_int64(M), N, K, L.ptr(Xd), L.ptr(dYd), None, L.ptr(dW), 0)
     assert rel_err(dW.cpu().numpy(), X.astype(np.float64).T @ dY.astype(np.float64)) < 1e-5
     db = torch.zeros(N, device=dev)
-    L.call("magpo_test_gemm", s, 2, C.c_int64(M), N, K, L.ptr(dt(dY, dev)), None, None, L.ptr(db), 0)
+    L.call("magpo_test_gemm", s, 2, C.c_int64(M), N, K, L.ptr(dYd), None, None, L.ptr(db), 0)
     assert rel_err(db.cpu().numpy(), dY.astype(np.float64).sum(0)) < 1e-5
     WT = torch.zeros(N, K, device=dev)
-    L.call("magpo_test_gemm", s, 3, C.c_int64(K), N, K, L.ptr(dt(W, dev)), None, None, L.ptr(WT), 0)
+    L.call("magpo_test_gemm", s, 3, C.c_int64(K), N, K, L.ptr(Wd), None, None, L.ptr(WT), 0)
     assert (WT.cpu().numpy() == W.T).all()
 
 
@@ -199,11 +202,37 @@ def test_retention_scan_equals_chunkwise_reference(dev, causal, T, N, A):
     # the chunk's next_hstate (retention.py:88-92) equals the scan's final state
     assert rel_err(Hout.cpu().numpy(), nh_ref.numpy()) < 2e-5
     dpk = torch.zeros(T, N, A, 256, device=dev)
+    dretd = dt(tm(dret), dev)
     db = dpk.data_ptr()
     L.call("magpo_test_retention", s, 1, T, N, A, C.c_float(kappa), int(causal), C.c_void_p(base), C.c_void_p(base + 256),
-           C.c_void_p(base + 512), 256, L.ptr(H0d), L.ptr(done_d), None, L.ptr(Hs), None, L.ptr(dt(tm(dret), dev)),
+           C.c_void_p(base + 512), 256, L.ptr(H0d), L.ptr(done_d), None, L.ptr(Hs), None, L.ptr(dretd),
            C.c_void_p(db), C.c_void_p(db + 256), C.c_void_p(db + 512), 256)
     out = dpk.cpu().numpy()
     assert rel_err(out[..., 0:64], tm(gq)) < 5e-5
     assert rel_err(out[..., 64:128], tm(gk)) < 5e-5
     assert rel_err(out[..., 128:192], tm(gv)) < 5e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (4096, 256, 64), (777, 128, 64), (512, 192, 64), (2048, 384, 128), (3000, 128, 128),
+                                   (1024, 64, 256), (1500, 64, 192), (2000, 128, 384), (300, 64, 64), (40000, 256, 64)])
+def test_gemm_tensor_core_3xtf32(dev, M, N, K):
+    """tcgen05 + TMA GEMM (3xTF32 split) against fp64: fp32-faithful accuracy, bias / relu / accumulate epilogues,
+    sub-matrix views (leading dimensions larger than the logical width)."""
+    rng = np.random.default_rng(5)
+    ldx, ldy = K + 64, N + 32
+    Xf = rng.standard_normal((M, ldx)).astype(np.float32)
+    W = (rng.standard_normal((K, N)) * 0.3).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    Xd, WTd, bd = dt(Xf, dev), dt(np.ascontiguousarray(W.T), dev), dt(b, dev)
+    scratch = torch.zeros(2 * N * K, device=dev)
+    Y = torch.full((M, ldy), 7.0, device=dev)
+    s = L.stream_ptr()
+    ref = Xf[:, :K].astype(np.float64) @ W.astype(np.float64)
+    L.call("magpo_test_gemm_tc", s, C.c_int64(M), N, K, L.ptr(Xd), ldx, L.ptr(WTd), L.ptr(scratch), L.ptr(bd), L.ptr(Y), ldy, 0)
+    out = Y.cpu().numpy()
+    assert rel_err(out[:, :N], ref + b) < 2e-6
+    assert (out[:, N:] == 7.0).all()  # nothing written outside the logical width
+    L.call("magpo_test_gemm_tc", s, C.c_int64(M), N, K, L.ptr(Xd), ldx, L.ptr(WTd), L.ptr(scratch), L.ptr(bd), L.ptr(Y), ldy, 2)
+    assert rel_err(Y.cpu().numpy()[:, :N], np.maximum(ref + b, 0)) < 2e-6
+    L.call("magpo_test_gemm_tc", s, C.c_int64(M), N, K, L.ptr(Xd), ldx, L.ptr(WTd), L.ptr(scratch), None, L.ptr(Y), ldy, 1)
+    assert rel_err(Y.cpu().numpy()[:, :N], np.maximum(ref + b, 0) + ref) < 2e-6  # TMA reduce-add
