@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--num-envs", type=int, default=4096, help="arch.num_envs per GPU per update-batch slot")
     ap.add_argument("--update-batch-size", type=int, default=2)
     ap.add_argument("--rollout-length", type=int, default=128)
-    ap.add_argument("--chunk-envs", type=int, default=1024)
+    ap.add_argument("--chunk-envs", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--quick", action="store_true", help="1 warm-up step, no e2e loop (for runs under ncu only)")
@@ -211,6 +211,19 @@ def main():
            "e2e": {"value": per_step / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches)}
 
+    # phase split of one more step (CUDA events on the launching stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
+    ev[0].record(); lrn.rollout(); ev[1].record(); lrn.gae(); ev[2].record()
+    for p_ in range(sysc.ppo_epochs):
+        lrn.epoch_indices(p_ == 0)
+        for m_ in range(sysc.num_minibatches):
+            lrn.minibatch_grads(m_)
+            lrn.apply_grads()
+    ev[3].record()
+    torch.cuda.synchronize()
+    out["phase_ms"] = {"rollout_and_bootstrap": round(ev[0].elapsed_time(ev[1]), 3), "gae": round(ev[1].elapsed_time(ev[2]), 3),
+                       "update": round(ev[2].elapsed_time(ev[3]), 3)}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -208,6 +208,7 @@ static int64_t slab_rows(int64_t M, int tiles) {
 int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW,
             int ldw) {
   if (M <= 0 || N <= 0 || K <= 0) return MAGPO_OK;
+  if (tc_tn_supported(M, N, K, X, ldx, dY, ldy, dW, ldw)) return gemm_tc_tn(s, M, N, K, X, ldx, dY, ldy, dW, ldw);
   ProfScope ps(PROF_GEMM_TN, s, 2.0 * (double)M * N * K);
   const int nt = (int)ceil_div(N, 64), kt = (int)ceil_div(K, 64);
   const int64_t rows = slab_rows(M, nt * kt);

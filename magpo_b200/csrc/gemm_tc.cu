@@ -313,6 +313,164 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+
+// =====================================================================================================================
+// Weight-gradient GEMM on the tensor cores:  dW[K,N] += X[M,K]^T @ dY[M,N]   (K in {64,128}; reduction over the rows).
+// Both operands are activations and are consumed exactly as they lie in memory: a [32 rows x 32 floats] TMA box is an
+// MN-major (M/N contiguous) 128B-swizzled UMMA operand whose 8-row groups are the K=8 steps of kind::tf32. Both operands are
+// split into TF32 hi/lo by the converter warps. Each CTA reduces a contiguous slab of rows into one TMEM accumulator and
+// adds it to dW with a TMA reduce-add, so the cross-CTA reduction needs no extra pass.
+constexpr int TN_RC = 32;          // rows per pipeline stage
+constexpr int TN_BOX = TN_RC * 128;  // bytes of one [32 x 32 floats] box
+
+struct TnParams {
+  int K, BN, stages, tmem_cols;
+  int64_t M, rows_per_cta;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  // LBO = stride between 32-float column blocks (one box), SBO = stride between 8-row groups
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(TN_BOX >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  const __grid_constant__ CUtensorMap tmDW, const TnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int x_bytes = (p.K / 32) * TN_BOX, y_bytes = (p.BN / 32) * TN_BOX;
+  const int raw_bytes = x_bytes + y_bytes;  // per stage: [X hi | dY hi | X lo | dY lo]
+  uint8_t* sStage = base;
+  uint8_t* sOut = sStage + (size_t)p.stages * 2 * raw_bytes;  // 2 x 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * TC_CHUNK_BYTES);
+  uint64_t* full_raw = bars;
+  uint64_t* full_conv = bars + TC_MAX_STAGES;
+  uint64_t* empty = bars + 2 * TC_MAX_STAGES;
+  uint64_t* tmem_full = bars + 3 * TC_MAX_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * p.BN;
+  const int64_t row_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+  const int64_t row_end = row_begin + p.rows_per_cta < p.M ? row_begin + p.rows_per_cta : p.M;
+  const int nchunks = row_begin < row_end ? (int)((row_end - row_begin + TN_RC - 1) / TN_RC) : 0;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_raw[i], 1);
+      mbar_init(&full_conv[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (nchunks > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < nchunks; ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
+          mbar_expect_tx(&full_raw[s], (uint32_t)raw_bytes);
+          uint8_t* st = sStage + (size_t)s * 2 * raw_bytes;
+          const int r0 = (int)(row_begin + (int64_t)it * TN_RC);
+          for (int kb = 0; kb < p.K / 32; ++kb) tma_load_2d(st + kb * TN_BOX, &tmX, kb * 32, r0, &full_raw[s]);
+          for (int nb = 0; nb < p.BN / 32; ++nb) tma_load_2d(st + x_bytes + nb * TN_BOX, &tmDY, n0 + nb * 32, r0, &full_raw[s]);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // kind::tf32, fp32 accumulate, A and B MN-major, M = K (of the GEMM), N = BN
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) |
+                               ((uint32_t)(p.K >> 4) << 24);
+        for (int it = 0; it < nchunks; ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&full_conv[s], (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t x_hi = smem_u32(sStage + (size_t)s * 2 * raw_bytes);
+          const uint32_t y_hi = x_hi + x_bytes, x_lo = x_hi + raw_bytes, y_lo = y_hi + raw_bytes;
+#pragma unroll
+          for (int g = 0; g < TN_RC / 8; ++g) {
+            const uint32_t go = g * 1024;  // next 8-row group = next K=8 step
+            umma_tf32(tmem_base, umma_desc_mn_sw128(x_lo + go), umma_desc_mn_sw128(y_hi + go), idesc, (it | g) ? 1u : 0u);
+            umma_tf32(tmem_base, umma_desc_mn_sw128(x_hi + go), umma_desc_mn_sw128(y_lo + go), idesc, 1u);
+            umma_tf32(tmem_base, umma_desc_mn_sw128(x_hi + go), umma_desc_mn_sw128(y_hi + go), idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(tmem_full);
+      }
+    } else if (warp >= 4 && warp < 8) {
+      const int et = threadIdx.x - 128;
+      const int sub = warp & 3;
+      // M = 128: lane l of sub-partition s holds row 32 s + l.  M = 64: rows 16 s + l live in lanes l < 16.
+      const bool m64 = p.K == 64;
+      const int row = m64 ? sub * 16 + lane : sub * 32 + lane;
+      const bool active = !m64 || lane < 16;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int nslab = p.BN / 32;
+      for (int sl = 0; sl < nslab; ++sl) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(sl * 32), v);
+        uint8_t* buf = sOut + (size_t)(sl & 1) * TC_CHUNK_BYTES;
+        if (et == 0) bulk_wait_read<1>();
+        named_bar_sync(1, 128);
+        if (active) {
+          float4* dst_row = reinterpret_cast<float4*>(buf + (size_t)row * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst_row[j ^ (row & 7)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          tma_reduce_add_2d(&tmDW, buf, n0 + sl * 32, 0);
+          bulk_commit();
+        }
+      }
+      if (et == 0) bulk_wait_all();
+    } else if (warp >= 8) {
+      const int ct = threadIdx.x - 256;
+      const int nvec = raw_bytes / 16;
+      for (int it = 0; it < nchunks; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(&full_raw[s], (it / p.stages) & 1);
+        float4* hi = reinterpret_cast<float4*>(sStage + (size_t)s * 2 * raw_bytes);
+        float4* lo = hi + nvec;
+        for (int idx = ct; idx < nvec; idx += 128) {
+          const float4 x = hi[idx];
+          float4 h, l;
+          split_tf32(x.x, h.x, l.x);
+          split_tf32(x.y, h.y, l.y);
+          split_tf32(x.z, h.z, l.z);
+          split_tf32(x.w, h.w, l.w);
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_conv[s]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(256)
 split_region_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -451,6 +609,61 @@ int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
   return MAGPO_OK;
 }
 
+
+static bool tn_plan(int N, int K, TnParams* p, uint32_t* smem_bytes) {
+  if ((K != 64 && K != 128) || N % 32) return false;
+  const int cands[] = {256, 192, 128, 96, 64, 32};
+  for (int bn : cands) {
+    if (N % bn) continue;
+    const uint32_t raw = (uint32_t)(K / 32 + bn / 32) * TN_BOX;
+    const uint32_t fixed = 2 * TC_CHUNK_BYTES + 256 + 1024;
+    if (fixed + 2 * 2 * raw > TC_SMEM_LIMIT) continue;
+    p->K = K;
+    p->BN = bn;
+    p->stages = std::min<int>(TC_MAX_STAGES, (int)((TC_SMEM_LIMIT - fixed) / (2 * raw)));
+    int cols = 32;
+    while (cols < bn) cols <<= 1;
+    p->tmem_cols = cols;
+    *smem_bytes = fixed + (uint32_t)p->stages * 2 * raw;
+    return true;
+  }
+  return false;
+}
+
+bool tc_tn_supported(int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, const float* dW, int ldw) {
+  if (!g_tc_enabled || !get_encode()) return false;
+  if ((ldx & 3) || (ldy & 3) || (ldw & 3)) return false;
+  if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(dY) & 15) || (reinterpret_cast<uintptr_t>(dW) & 15)) return false;
+  TnParams p;
+  uint32_t smem;
+  return M >= 256 && tn_plan(N, K, &p, &smem);
+}
+
+// dW[K,N] += X[M,K]^T @ dY[M,N]
+int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw) {
+  TnParams p;
+  uint32_t smem;
+  if (!tn_plan(N, K, &p, &smem)) return MAGPO_ERR_UNSUPPORTED;
+  p.M = M;
+  const int n_tiles = N / p.BN;
+  const int64_t chunks = ceil_div(M, TN_RC);
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(chunks, kNumSMs / n_tiles));
+  p.rows_per_cta = ceil_div(chunks, gx) * TN_RC;
+  CUtensorMap tmX, tmDY, tmDW;
+  // boxes of [32 rows x 32 floats] for the operands; the accumulator slab is [K rows x 32 floats]
+  if (!make_map(&tmX, X, M, K, ldx, TN_RC) || !make_map(&tmDY, dY, M, N, ldy, TN_RC) || !make_map(&tmDW, dW, K, N, ldw, K))
+    return MAGPO_ERR_ARG;
+  static bool attr = false;
+  if (!attr) {
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    attr = true;
+  }
+  ProfScope ps(PROF_GEMM_TN, s, 2.0 * (double)M * N * K);
+  gemm_tc_tn_kernel<<<dim3((unsigned)gx, (unsigned)n_tiles), TC_THREADS, smem, s>>>(tmX, tmDY, tmDW, p);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
 }  // namespace magpo
 
 using namespace magpo;
@@ -466,4 +679,10 @@ extern "C" int magpo_test_gemm_tc(magpo_stream_t s_, int64_t M, int N, int K, co
 extern "C" int magpo_set_tensor_cores(int on) {
   tc_set_enabled(on != 0);
   return MAGPO_OK;
+}
+
+extern "C" int magpo_test_gemm_tc_tn(magpo_stream_t s_, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy,
+                                     float* dW, int ldw) {
+  if (!tc_tn_supported(M, N, K, X, ldx, dY, ldy, dW, ldw)) return MAGPO_ERR_UNSUPPORTED;
+  return gemm_tc_tn(as_stream(s_), M, N, K, X, ldx, dY, ldy, dW, ldw);
 }

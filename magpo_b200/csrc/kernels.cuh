@@ -34,6 +34,8 @@ bool tc_lookup(const float* w, const float** hi, const float** lo);
 bool tc_supported(int64_t M, int N, int K, const float* X, int ldx, const float* Y, int ldy, int ldb);
 int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* Bhi, const float* Blo, int ldb,
             const float* bias, float* Y, int ldy, int flags);
+bool tc_tn_supported(int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, const float* dW, int ldw);
+int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw);
 int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW,
             int ldw);
 int colsum(cudaStream_t s, int64_t M, int N, const float* dY, int ldy, float* db);

@@ -200,7 +200,7 @@ def test_retention_scan_equals_chunkwise_reference(dev, causal, T, N, A):
     if not ts_done.any(axis=1).all():
         pass
     # the chunk's next_hstate (retention.py:88-92) equals the scan's final state
-    assert rel_err(Hout.cpu().numpy(), nh_ref.numpy()) < 2e-5
+    assert rel_err(Hout.cpu().numpy(), nh_ref.detach().numpy()) < 2e-5
     dpk = torch.zeros(T, N, A, 256, device=dev)
     dretd = dt(tm(dret), dev)
     db = dpk.data_ptr()
@@ -230,9 +230,28 @@ def test_gemm_tensor_core_3xtf32(dev, M, N, K):
     ref = Xf[:, :K].astype(np.float64) @ W.astype(np.float64)
     L.call("magpo_test_gemm_tc", s, C.c_int64(M), N, K, L.ptr(Xd), ldx, L.ptr(WTd), L.ptr(scratch), L.ptr(bd), L.ptr(Y), ldy, 0)
     out = Y.cpu().numpy()
-    assert rel_err(out[:, :N], ref + b) < 2e-6
+    tol = 2e-6 * max(1.0, (K / 64) ** 0.5)  # error grows like sqrt(K) as in any fp32 dot product
+    assert rel_err(out[:, :N], ref + b) < tol
     assert (out[:, N:] == 7.0).all()  # nothing written outside the logical width
     L.call("magpo_test_gemm_tc", s, C.c_int64(M), N, K, L.ptr(Xd), ldx, L.ptr(WTd), L.ptr(scratch), L.ptr(bd), L.ptr(Y), ldy, 2)
-    assert rel_err(Y.cpu().numpy()[:, :N], np.maximum(ref + b, 0)) < 2e-6
+    assert rel_err(Y.cpu().numpy()[:, :N], np.maximum(ref + b, 0)) < tol
     L.call("magpo_test_gemm_tc", s, C.c_int64(M), N, K, L.ptr(Xd), ldx, L.ptr(WTd), L.ptr(scratch), None, L.ptr(Y), ldy, 1)
-    assert rel_err(Y.cpu().numpy()[:, :N], np.maximum(ref + b, 0) + ref) < 2e-6  # TMA reduce-add
+    assert rel_err(Y.cpu().numpy()[:, :N], np.maximum(ref + b, 0) + ref) < tol  # TMA reduce-add
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (4096, 256, 64), (777, 128, 64), (50000, 64, 64), (2048, 384, 128), (3000, 128, 128),
+                                   (300, 192, 64), (33000, 384, 128)])
+def test_gemm_tensor_core_tn_weight_grad(dev, M, N, K):
+    """dW += X^T dY on tcgen05 with MN-major operands (both split 3xTF32), TMA reduce-add across CTAs; accumulates
+    into existing contents and respects leading dimensions."""
+    rng = np.random.default_rng(6)
+    ldx, ldy, ldw = K + 64, N + 32, N + 64
+    Xf = rng.standard_normal((M, ldx)).astype(np.float32)
+    dYf = rng.standard_normal((M, ldy)).astype(np.float32)
+    init = rng.standard_normal((K, ldw)).astype(np.float32)
+    Xd, dYd, dW = dt(Xf, dev), dt(dYf, dev), dt(init, dev)
+    L.call("magpo_test_gemm_tc_tn", L.stream_ptr(), C.c_int64(M), N, K, L.ptr(Xd), ldx, L.ptr(dYd), ldy, L.ptr(dW), ldw)
+    ref = Xf[:, :K].astype(np.float64).T @ dYf[:, :N].astype(np.float64) + init[:, :N]
+    out = dW.cpu().numpy()
+    assert rel_err(out[:, :N], ref) < 3e-6 * max(1.0, (M / 1000) ** 0.5)
+    assert (out[:, N:] == init[:, N:]).all()
