@@ -329,9 +329,11 @@ struct TnParams {
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
-  // LBO = stride between 32-float column blocks (one box), SBO = stride between 8-row groups
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(TN_BOX >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
+  // 32-bit MN-major operands must use the 128B swizzle with a 32-byte base (UMMA layout type SWIZZLE_128B_BASE32B,
+  // TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the atom is 4 K-rows x 128 B, a K=8 step spans two atoms.
+  // LBO = stride between 32-float column blocks (one TMA box), SBO = stride between 4-row groups.
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(TN_BOX >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)1 << 61);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -499,7 +501,8 @@ EncodeTiledFn get_encode() {
 }
 
 // row-major [rows, cols] fp32 matrix with leading dimension ld; box = [box_rows, 32 floats], 128B swizzle
-bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int cols, int ld, int box_rows) {
+bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int cols, int ld, int box_rows,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -507,7 +510,7 @@ bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int cols, int ld,
   cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct TcRegion {
@@ -651,7 +654,8 @@ int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx,
   p.rows_per_cta = ceil_div(chunks, gx) * TN_RC;
   CUtensorMap tmX, tmDY, tmDW;
   // boxes of [32 rows x 32 floats] for the operands; the accumulator slab is [K rows x 32 floats]
-  if (!make_map(&tmX, X, M, K, ldx, TN_RC) || !make_map(&tmDY, dY, M, N, ldy, TN_RC) || !make_map(&tmDW, dW, K, N, ldw, K))
+  if (!make_map(&tmX, X, M, K, ldx, TN_RC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map(&tmDY, dY, M, N, ldy, TN_RC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) || !make_map(&tmDW, dW, K, N, ldw, K))
     return MAGPO_ERR_ARG;
   static bool attr = false;
   if (!attr) {

@@ -45,6 +45,20 @@ retention_fwd_kernel(int T, int N, int A, float kappa, const float* __restrict__
     if (H0) h = ld4(H0 + ((int64_t)n * 64 + r0 + a) * 64 + c0);
     H[a][0] = h.x; H[a][1] = h.y; H[a][2] = h.z; H[a][3] = h.w;
   }
+  // software pipeline: the q,k,v rows of step t+1 are fetched into registers while step t is computed
+  float pq[2], pk[2], pv[2];
+  auto fetch = [&](int t) {
+    const int64_t b0 = ((int64_t)t * N + n) * A;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * 256;
+      if (idx < A * 64) {
+        const int64_t off = (b0 + (idx >> 6)) * ld + (idx & 63);
+        pq[j] = q[off]; pk[j] = k[off]; pv[j] = v[off];
+      }
+    }
+  };
+  fetch(0);
   for (int t = 0; t < T; ++t) {
     const float lam = (done && done[(int64_t)t * N + n]) ? 0.0f : kappa;
 #pragma unroll
@@ -52,13 +66,13 @@ retention_fwd_kernel(int T, int N, int A, float kappa, const float* __restrict__
 #pragma unroll
       for (int b = 0; b < 4; ++b) H[a][b] *= lam;
     const int64_t base = ((int64_t)t * N + n) * A;
-    for (int idx = tid; idx < A * 64; idx += 256) {
-      const int64_t off = (base + (idx >> 6)) * ld + (idx & 63);
-      qs[idx] = q[off];
-      ks[idx] = k[off];
-      vs[idx] = v[off];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * 256;
+      if (idx < A * 64) { qs[idx] = pq[j]; ks[idx] = pk[j]; vs[idx] = pv[j]; }
     }
     __syncthreads();
+    if (t + 1 < T) fetch(t + 1);
     if (!CAUSAL) {
       for (int i = 0; i < A; ++i) {
         const float4 kr = ld4(ks + i * 64 + r0), vc = ld4(vs + i * 64 + c0);
@@ -128,22 +142,35 @@ retention_bwd_kernel(int T, int N, int A, float kappa, const float* __restrict__
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) G[a][b] = 0.f;
-  for (int t = T - 1; t >= 0; --t) {
-    const int64_t base = ((int64_t)t * N + n) * A;
-    for (int idx = tid; idx < A * 64; idx += 256) {
-      const int64_t row = base + (idx >> 6);
-      const int c = idx & 63;
-      qs[idx] = q[row * ld + c];
-      ks[idx] = k[row * ld + c];
-      vs[idx] = v[row * ld + c];
-      ds[idx] = dret[row * 64 + c];
+  // software pipeline: rows and the saved state of step t-1 are fetched while step t is processed
+  float pq[2], pk[2], pv[2], pd[2];
+  float4 ph[4];
+  auto fetch = [&](int t) {
+    const int64_t b0 = ((int64_t)t * N + n) * A;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * 256;
+      if (idx < A * 64) {
+        const int64_t row = b0 + (idx >> 6);
+        const int c = idx & 63;
+        pq[j] = q[row * ld + c]; pk[j] = k[row * ld + c]; pv[j] = v[row * ld + c]; pd[j] = dret[row * 64 + c];
+      }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const float4 h = ld4(Hsave + (((int64_t)t * N + n) * 64 + r0 + a) * 64 + c0);
-      H[a][0] = h.x; H[a][1] = h.y; H[a][2] = h.z; H[a][3] = h.w;
+    for (int a = 0; a < 4; ++a) ph[a] = ld4(Hsave + (((int64_t)t * N + n) * 64 + r0 + a) * 64 + c0);
+  };
+  fetch(T - 1);
+  for (int t = T - 1; t >= 0; --t) {
+    const int64_t base = ((int64_t)t * N + n) * A;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * 256;
+      if (idx < A * 64) { qs[idx] = pq[j]; ks[idx] = pk[j]; vs[idx] = pv[j]; ds[idx] = pd[j]; }
     }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { H[a][0] = ph[a].x; H[a][1] = ph[a].y; H[a][2] = ph[a].z; H[a][3] = ph[a].w; }
     __syncthreads();
+    if (t > 0) fetch(t - 1);
     if (!CAUSAL) {
       for (int i = 0; i < A; ++i) {
         const float4 qr = ld4(qs + i * 64 + r0), dc = ld4(ds + i * 64 + c0);

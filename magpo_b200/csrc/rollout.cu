@@ -107,6 +107,8 @@ inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n, 256); }
 struct RolloutWs {
   SableActs sa;
   ActorActs aa;
+  GuiderT gt;  // transposed weights + TF32 hi/lo images: the rollout GEMMs run on the tensor cores as well
+  ActorT at;
   float *pe, *xrep_i, *xrep_pe_i, *logits_i;
   int32_t *step_i, *prev_action;
   uint32_t* sample_keys;
@@ -114,6 +116,8 @@ struct RolloutWs {
     const int64_t R = (int64_t)B * net->n_agents;
     sa.plan(ar, R, B, net->obs_dim, false);
     aa.plan(ar, R, R, net->action_dim, false);
+    gt.plan(ar, net->obs_dim);
+    at.plan(ar, net->action_dim);
     pe = ar.get<float>((size_t)(net->max_step_count + 1) * kD);
     xrep_i = ar.get<float>((size_t)B * kD);
     xrep_pe_i = ar.get<float>((size_t)B * kD);
@@ -125,12 +129,12 @@ struct RolloutWs {
 };
 
 // One SableNetwork.get_actions over B envs (T=1 recurrent step). hs updated in place unless `dry` (bootstrap).
-int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, const GuiderP& gp, float kappa,
+int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, const GuiderP& gp, const GuiderT* gt, float kappa,
                 const float* agents_view, const uint8_t* action_mask, const int32_t* step_count,
                 const uint8_t* prev_done, const uint32_t* sample_keys, MagpoSableHState hs, bool dry,
                 int32_t* action, float* log_prob, float* value, float* masked_logits, const RolloutWs& w) {
   const int A = net->n_agents, d = net->obs_dim, a = net->action_dim, ms = net->max_step_count;
-  MAGPO_TRY(sable_encoder_forward(s, gp, nullptr, 1, B, A, d, ms, agents_view, step_count, prev_done, hs.encoder, kappa, w.pe,
+  MAGPO_TRY(sable_encoder_forward(s, gp, gt, 1, B, A, d, ms, agents_view, step_count, prev_done, hs.encoder, kappa, w.pe,
                                   w.sa, value, nullptr, dry ? nullptr : hs.encoder));
   if (!action) return MAGPO_OK;
   for (int i = 0; i < A; ++i) {
@@ -144,7 +148,7 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
       MAGPO_LAUNCH_OK();
     }
     // the once-per-timestep decay (and the reset on done) is applied when the first agent's token arrives
-    MAGPO_TRY(sable_decoder_forward(s, gp, nullptr, 1, B, 1, i == 0 ? -1 : 0, a, ms, w.prev_action, w.xrep_i, w.xrep_pe_i,
+    MAGPO_TRY(sable_decoder_forward(s, gp, gt, 1, B, 1, i == 0 ? -1 : 0, a, ms, w.prev_action, w.xrep_i, w.xrep_pe_i,
                                     w.step_i, i == 0 ? prev_done : nullptr, hs.decoder_self, hs.decoder_cross,
                                     i == 0 ? kappa : 1.0f, w.pe, w.sa, w.logits_i, nullptr, nullptr,
                                     dry ? nullptr : hs.decoder_self, dry ? nullptr : hs.decoder_cross));
@@ -187,7 +191,7 @@ int magpo_sable_get_actions(magpo_stream_t s_, const MagpoNetCfg* net, int32_t B
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
   MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
   const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim);
-  return get_actions(s, net, B, gumbel_rows, gp, net_kappa(net), agents_view, action_mask, step_count, prev_done,
+  return get_actions(s, net, B, gumbel_rows, gp, nullptr, net_kappa(net), agents_view, action_mask, step_count, prev_done,
                      sample_keys, hs, false, action, log_prob, value, logits, w);
 }
 
@@ -228,6 +232,14 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
   MagpoCoordSumState* cst = static_cast<MagpoCoordSumState*>(env_state);
 
   MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
+  const GuiderT* gtp = nullptr;
+  const ActorT* atp = nullptr;
+  if (tc_enabled()) {  // parameters are constant during the rollout: one transpose + TF32 split up front
+    MAGPO_TRY(guider_transpose(s, gp, w.gt, d));
+    MAGPO_TRY(actor_transpose(s, ap, w.at, a));
+    gtp = &w.gt;
+    atp = &w.at;
+  }
   if (carry_over) {  // LearnerState.timestep of the previous call becomes observation slot 0
     MAGPO_CUDA_OK(cudaMemcpyAsync(traj.done, traj.done + (size_t)T * B, B, cudaMemcpyDeviceToDevice, s));
     MAGPO_CUDA_OK(cudaMemcpyAsync(traj.agents_view, traj.agents_view + (size_t)T * BA * d, BA * d * sizeof(float),
@@ -255,9 +267,9 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
     const int32_t* stepc = traj.step_count + (size_t)t * BA;
     const uint8_t* prev_done = traj.done + (size_t)t * B;
     int32_t* act = traj.action + (size_t)t * BA;
-    MAGPO_TRY(get_actions(s, net, B, E, gp, kappa, obs, mask, stepc, prev_done, w.sample_keys + (size_t)t * A * 2, hs,
+    MAGPO_TRY(get_actions(s, net, B, E, gp, gtp, kappa, obs, mask, stepc, prev_done, w.sample_keys + (size_t)t * A * 2, hs,
                           false, act, traj.log_prob + (size_t)t * BA, traj.value + (size_t)t * BA, nullptr, w));
-    MAGPO_TRY(actor_forward(s, ap, nullptr, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
+    MAGPO_TRY(actor_forward(s, ap, atp, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
     MagpoTimeStep o = ts;
     o.reward = traj.reward + (size_t)t * BA;
     o.agents_view = traj.agents_view + (size_t)(t + 1) * BA * d;
@@ -269,7 +281,7 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
     MAGPO_TRY(coordsum_step_launch(s, ccfg, B, act, *cst, o, traj.done + (size_t)(t + 1) * B));
   }
   // bootstrap value (rec_magpo.py:202-208): a full get_actions of which only the value is kept
-  MAGPO_TRY(get_actions(s, net, B, E, gp, kappa, traj.agents_view + (size_t)T * BA * d, nullptr,
+  MAGPO_TRY(get_actions(s, net, B, E, gp, gtp, kappa, traj.agents_view + (size_t)T * BA * d, nullptr,
                         traj.step_count + (size_t)T * BA, traj.done + (size_t)T * B, nullptr, hs, true, nullptr, nullptr,
                         traj.last_value, nullptr, w));
   return MAGPO_OK;
