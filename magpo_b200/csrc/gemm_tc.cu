@@ -536,22 +536,30 @@ int tc_prepare_region(cudaStream_t s, const float* base, int64_t n, float* hi, f
   if (n <= 0) return MAGPO_OK;
   split_region_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 4 * kNumSMs), 256, 0, s>>>(n, base, hi, lo);
   MAGPO_LAUNCH_OK();
-  for (auto& r : g_regions)
-    if (r.base == base) {
-      r.n = n; r.hi = hi; r.lo = lo;
-      return MAGPO_OK;
-    }
+  // Workspaces are re-planned between calls (rollout vs. update, different T/N): drop every older registration whose
+  // source range touches memory this one claims (its source or its hi/lo images) — a stale range must never match.
+  auto overlaps = [](const float* a, int64_t na, const float* b, int64_t nb) { return a < b + nb && b < a + na; };
+  for (size_t i = 0; i < g_regions.size();) {
+    const TcRegion& r = g_regions[i];
+    if (overlaps(r.base, r.n, base, n) || overlaps(r.base, r.n, hi, n) || overlaps(r.base, r.n, lo, n) ||
+        overlaps(r.hi, r.n, base, n) || overlaps(r.lo, r.n, base, n))
+      g_regions.erase(g_regions.begin() + (long)i);
+    else
+      ++i;
+  }
   g_regions.push_back(TcRegion{base, n, hi, lo});
   return MAGPO_OK;
 }
 
 bool tc_lookup(const float* w, const float** hi, const float** lo) {
-  for (const auto& r : g_regions)
+  for (auto it = g_regions.rbegin(); it != g_regions.rend(); ++it) {
+    const TcRegion& r = *it;
     if (w >= r.base && w < r.base + r.n) {
       *hi = r.hi + (w - r.base);
       *lo = r.lo + (w - r.base);
       return true;
     }
+  }
   return false;
 }
 
