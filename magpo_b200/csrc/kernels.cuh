@@ -82,6 +82,10 @@ int fill_f32(cudaStream_t s, float* p, int64_t n, float v);
 // q,k,v: column blocks of a packed buffer with row stride ld. H0 [N,64,64] initial state (un-decayed,
 // as stored in the learner state); done [T,N] resets. Hsave (optional) [T,N,64,64] = state after each timestep.
 // Hout (optional) [N,64,64] final state. causal: decoder (masked=True) vs encoder (block-full over agents).
+// For T > 1 the chunkwise tensor-core kernels (retention_chunk.cu) run instead of the scan and Hsave holds only the
+// state entering each chunk: [retention_num_chunks(T, A), N, 64, 64].
+int retention_chunk_len(int A);
+int retention_num_chunks(int T, int A);
 int retention_fwd(cudaStream_t s, int T, int N, int A, float kappa, bool causal, const float* q, const float* k,
                   const float* v, int ld, const float* H0, const uint8_t* done, float* ret, float* Hsave,
                   float* Hout);

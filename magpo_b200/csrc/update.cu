@@ -145,6 +145,8 @@ SableBatch make_batch(const MagpoNetCfg* net, const MagpoMinibatch& mb, const fl
   return b;
 }
 
+int g_debug_skip = 0;  // tools/bench_phases.py only: bit0 guider fwd+bwd, bit1 learner fwd+bwd, bit2 guider bwd, bit3 learner bwd
+
 int check_mb(const MagpoMinibatch& mb) {
   if (mb.T < 1 || mb.N < 1 || !mb.agents_view || !mb.action_mask || !mb.step_count || !mb.done || !mb.action ||
       !mb.sable_h0.encoder || !mb.sable_h0.decoder_self || !mb.sable_h0.decoder_cross)
@@ -253,13 +255,14 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
     MAGPO_TRY(tc_prepare_region(s, actor, ap.total, w.a_hi, w.a_lo));
   }
   const SableBatch b = make_batch(net, mb, w.pe);
-  MAGPO_TRY(sable_train_forward(s, gp, &w.gt, b, w.sa, w.value, w.lg, true));
-  MAGPO_TRY(actor_forward(s, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
+  const int skip = g_debug_skip;
+  if (!(skip & 1)) MAGPO_TRY(sable_train_forward(s, gp, &w.gt, b, w.sa, w.value, w.lg, true));
+  if (!(skip & 2)) MAGPO_TRY(actor_forward(s, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
   MAGPO_TRY(magpo_losses(s, R, N, A, a, sys, inv_tokens, w.lg, w.ll, mb.action_mask, mb.action, mb.log_prob,
                          mb.advantages, w.value, mb.value, mb.targets, env_slot, adv_stats_, w.dlg, w.dll, w.dvalue,
                          loss_sums));
-  MAGPO_TRY(sable_train_backward(s, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
-  MAGPO_TRY(actor_backward(s, ap, w.at, T, N, A, d, a, mb.agents_view, mb.done, w.aa, w.dll, ag));
+  if (!(skip & 5)) MAGPO_TRY(sable_train_backward(s, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
+  if (!(skip & 10)) MAGPO_TRY(actor_backward(s, ap, w.at, T, N, A, d, a, mb.agents_view, mb.done, w.aa, w.dll, ag));
   return MAGPO_OK;
 }
 
@@ -299,6 +302,12 @@ int magpo_actor_forward(magpo_stream_t s_, const MagpoNetCfg* net, const float* 
   const int64_t n = (int64_t)mb.T * mb.N * net->n_agents * net->action_dim;
   mask_logits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(n, mb.action_mask, logits);
   MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+// Timing hook for tools/bench_phases.py (never set by the product path): skip parts of magpo_minibatch_grads.
+int magpo_debug_set_skip(int mask) {
+  g_debug_skip = mask;
   return MAGPO_OK;
 }
 
