@@ -79,6 +79,8 @@ inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n, 256); }
 
 }  // namespace
 
+bool g_force_stepwise = false;  // tests / tools: A/B the persistent scans against the per-timestep GEMM + gate kernels
+
 void ActorT::plan(Arena& ar, int a) {
   WiT = ar.get<float>(3 * kH * kH);
   WhT = ar.get<float>(3 * kH * kH);
@@ -126,7 +128,10 @@ int actor_forward(cudaStream_t s, const ActorP& p, const ActorT* pt, int T, int 
   MAGPO_TRY(gemm_nn(s, R, 3 * kH, kH, w.e, kH, wref(p.Wi, 3 * kH, pt ? pt->WiT : nullptr, kH), p.bi, w.gi, 3 * kH, 0));
   mask_rows_kernel<<<g256(Rs * kH), 256, 0, s>>>(Rs, A, h0, done, w.HU);
   MAGPO_LAUNCH_OK();
-  for (int t = 0; t < T; ++t) {
+  const float *wh_hi = nullptr, *wh_lo = nullptr;
+  const bool scan = T > 1 && w.rzn && pt && tc_enabled() && !g_force_stepwise && tc_lookup(pt->WhT, &wh_hi, &wh_lo);
+  if (scan) MAGPO_TRY(gru_scan_fwd(s, T, N, A, w.gi, wh_hi, wh_lo, p.bhn, done, w.rzn, w.ghn, w.Y, w.HU));
+  for (int t = 0; t < T && !scan; ++t) {
     const float* hu = w.HU + (size_t)t * Rs * kH;
     MAGPO_TRY(gemm_nn(s, Rs, 3 * kH, kH, hu, kH, wref(p.Wh, 3 * kH, pt ? pt->WhT : nullptr, kH), nullptr, w.gh, 3 * kH, 0));
     const uint8_t* dn = (t + 1 < T) ? done + (size_t)(t + 1) * N : nullptr;
@@ -161,7 +166,10 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
   MAGPO_TRY(gemm_nn(s, R, kH, kH, w.dA, kH, wref(pt.postT, kH, p.post_w, kH), nullptr, w.dB, kH, 0));  // dB = dL/dY
   // reverse scan; dgi reuses the gi buffer (dead after the forward)
   float* dgi = w.gi;
-  for (int t = T - 1; t >= 0; --t) {
+  const float *wh_hi = nullptr, *wh_lo = nullptr;
+  const bool scan = T > 1 && tc_enabled() && !g_force_stepwise && tc_lookup(p.Wh, &wh_hi, &wh_lo);
+  if (scan) MAGPO_TRY(gru_scan_bwd(s, T, N, A, w.dB, w.rzn, w.ghn, w.HU, done, wh_hi, wh_lo, dgi, w.dgh));
+  for (int t = T - 1; t >= 0 && !scan; --t) {
     const size_t o1 = (size_t)t * Rs * kH, o3 = (size_t)t * Rs * 3 * kH;
     const bool last = (t == T - 1);
     {
@@ -187,3 +195,8 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
 }
 
 }  // namespace magpo
+
+extern "C" int magpo_debug_force_gru_stepwise(int on) {
+  magpo::g_force_stepwise = on != 0;
+  return MAGPO_OK;
+}

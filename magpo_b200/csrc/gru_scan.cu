@@ -1,0 +1,574 @@
+// Persistent tensor-core GRU scans for the learner's update (ScannedRNN over T steps, networks/base.py:124-142, flax
+// GRUCell of SURVEY.md Appendix A8; BPTT per Appendix G).
+//
+// The recurrence is independent per (env, agent) row, so one CTA owns a tile of 128 rows for the whole sequence:
+//   * the hidden state never leaves the SM: it lives in registers (exact fp32) and, split into TF32 hi/lo images, in shared
+//     memory as the K-major 128B-swizzled A operand of tcgen05.mma;
+//   * W_h (hi/lo images, 384 KiB) does not fit beside it, so it is streamed from L2 every timestep through a TMA ring;
+//   * accumulators live in tensor memory; the gate math runs straight out of tcgen05.ld registers, fused with the loads of
+//     the batched input-side pre-activations and the stores of everything the backward needs. The gate warps read TMEM with
+//     the 16x256b fragment shape (4 lanes = 32 consecutive bytes of a row), so each of their global accesses covers whole
+//     32-byte sectors; a service warp keeps the next timestep's inputs flowing into L2 with cp.async.bulk.prefetch.
+// Per timestep and tile the forward issues 16 pieces x 12 MMAs (M=128, N=96: the r|z|n columns of one block of 32 hidden
+// units, so that the gates of block jb run while the tensor core works on block jb+1), the backward 12 pieces x 12 MMAs
+// (N=128; the contraction index is ordered (block, gate) so that the MMAs of a block start as soon as its dgh is written).
+// 3xTF32 throughout (fp32-faithful). warps 0-15: gates, warp 16: TMA producer, warp 17: MMA issuer, warp 18: L2 prefetch
+// (warp 19 only donates its registers to the gate warps through setmaxnreg).
+#include <cuda.h>
+
+#include "actor.cuh"
+#include "tc_ptx.cuh"
+
+namespace magpo {
+using namespace tcp;
+namespace {
+
+constexpr int GS_GATE_WARPS = 16;
+constexpr int GS_GATE_THREADS = GS_GATE_WARPS * 32;
+constexpr int GS_THREADS = GS_GATE_THREADS + 128;  // + one warpgroup of service warps
+constexpr int GS_CHUNK = 128 * 128;            // bytes of one [128 rows x 32 floats] operand chunk
+constexpr int GS_STAGES = 4;
+constexpr int GS_FWD_STAGE = 2 * 96 * 128;     // [96 x 32] hi + lo
+constexpr int GS_BWD_STAGE = 2 * GS_CHUNK;     // [128 x 32] hi + lo
+constexpr uint32_t GS_SMEM = 227 * 1024;
+
+// tcgen05.ld 16x256b.x1: 16 lanes x 8 columns; lane l of the warp receives r[2h + e] = (row l/4 + 8h, column 2(l%4) + e)
+// (probed with tools/probes/tmem_layout_probe.cu).
+__device__ __forceinline__ void tmem_ld_frag_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// both 16-lane halves of the warp's sub-partition: v[4 half + 2h + e]
+__device__ __forceinline__ void tmem_ld_patch_nowait(uint32_t taddr, uint32_t* v) {
+  tmem_ld_frag_nowait(taddr, v);
+  tmem_ld_frag_nowait(taddr + (16u << 16), v + 4);
+}
+
+// A gate warp owns 32 rows x 8 of every 32 hidden units; a thread the 4 x 2 patch rows {rr = 2 half + h} x columns {2m + e}.
+// Value index inside an 8-vector: 4 (rr >> 1) + 2 (rr & 1) + e.
+struct GateGeom {
+  int m;             // lane % 4
+  int row[4];        // row inside the 128-row tile
+  int64_t grow[4];   // global row
+  bool valid[4];
+};
+__device__ __forceinline__ int vidx(int rr, int e) { return (rr >> 1) * 4 + 2 * (rr & 1) + e; }
+
+__device__ __forceinline__ GateGeom make_geom(int sp, int lane, int64_t tile_row0, int64_t Rs) {
+  GateGeom gg;
+  gg.m = lane & 3;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    gg.row[rr] = sp * 32 + (rr >> 1) * 16 + (rr & 1) * 8 + (lane >> 2);
+    gg.grow[rr] = tile_row0 + gg.row[rr];
+    gg.valid[rr] = gg.grow[rr] < Rs;
+  }
+  return gg;
+}
+// 8 values of the patch from a row-major [rows, width] slab (col = first column of the warp's 8-column slab)
+__device__ __forceinline__ void load_patch(float* v, const float* slab, int width, int col, const GateGeom& gg) {
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    float2 x = make_float2(0.f, 0.f);
+    if (gg.valid[rr]) x = __ldg(reinterpret_cast<const float2*>(slab + gg.grow[rr] * width + col + 2 * gg.m));
+    v[vidx(rr, 0)] = x.x;
+    v[vidx(rr, 1)] = x.y;
+  }
+}
+__device__ __forceinline__ void store_patch(const float* v, float* slab, int width, int col, const GateGeom& gg) {
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr)
+    if (gg.valid[rr])
+      *reinterpret_cast<float2*>(slab + gg.grow[rr] * width + col + 2 * gg.m) = make_float2(v[vidx(rr, 0)], v[vidx(rr, 1)]);
+}
+// the patch as TF32 hi / lo images in a 128B-swizzled K-major [128 rows x 32 floats] chunk (c0 = first column, multiple of 8)
+__device__ __forceinline__ void store_patch_split(uint8_t* chunk_hi, uint8_t* chunk_lo, int c0, const float* v, const GateGeom& gg) {
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    float2 h, l;
+    split_tf32(v[vidx(rr, 0)], h.x, l.x);
+    split_tf32(v[vidx(rr, 1)], h.y, l.y);
+    const int row = gg.row[rr];
+    const int unit = ((c0 >> 2) + (gg.m >> 1)) ^ (row & 7);
+    const int off = row * 128 + unit * 16 + (gg.m & 1) * 8;
+    *reinterpret_cast<float2*>(chunk_hi + off) = h;
+    *reinterpret_cast<float2*>(chunk_lo + off) = l;
+  }
+}
+
+// The update only needs fp32-faithful (not bit-identical) gates: ex2.approx-based forms, abs error ~1e-7
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+// one warp: pull `bytes` contiguous bytes (multiple of 16) towards L2
+__device__ __forceinline__ void l2_prefetch(const void* ptr, int64_t bytes, int lane) {
+  const int64_t per = ((bytes / 32 + 15) / 16) * 16;
+  const int64_t off = per * lane;
+  if (off >= bytes) return;
+  const int64_t n = (bytes - off < per ? bytes - off : per) & ~int64_t(15);
+  if (n > 0)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(ptr) + off), "r"((uint32_t)n) : "memory");
+}
+
+__device__ __forceinline__ void regs_gate_warps() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;"); }
+__device__ __forceinline__ void regs_service_warps() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); }
+
+__device__ __forceinline__ uint32_t idesc_tf32(int n) {  // kind::tf32, fp32 accumulate, A and B K-major, M = 128
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint64_t gtimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// timeline probe (GRU_TIMELINE=1 tools/diag_gru.py): CTA 0 records %globaltimer at the hand-over points of the first steps
+#define GS_STAMP(role, idx)                                                                     \
+  do {                                                                                          \
+    if (p.dbg && blockIdx.x == 0 && (idx) < 1024) p.dbg[(role) * 1024 + (idx)] = gtimer();      \
+  } while (0)
+
+struct GruFwdArgs {
+  unsigned long long* dbg;
+  int T, N, A;
+  int64_t Rs;
+  const float* gi;      // [T, Rs, 384]  x @ Wi + bi
+  const float* bhn;     // [128]
+  const uint8_t* done;  // [T, N]
+  float* rzn;           // [T, Rs, 384]
+  float* ghn;           // [T, Rs, 128]
+  float* Y;             // [T, Rs, 128]
+  float* HU;            // [T+1, Rs, 128]; HU[0] is the (masked) initial state
+};
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
+gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const GruFwdArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sAhi = base;                      // 4 chunks
+  uint8_t* sAlo = sAhi + 4 * GS_CHUNK;       // 4 chunks
+  uint8_t* sB = sAlo + 4 * GS_CHUNK;         // GS_STAGES x {hi 12K, lo 12K}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + GS_STAGES * GS_FWD_STAGE);
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = bars + GS_STAGES;
+  uint64_t* acc_full = bars + 2 * GS_STAGES;  // 4
+  uint64_t* a_ready = acc_full + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 1);
+  volatile int* progress = reinterpret_cast<volatile int*>(tmem_ptr + 1);  // timesteps started by the gate warps (prefetch throttle)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = p.T;
+  const int64_t tile_row0 = (int64_t)blockIdx.x * 128;
+  const int64_t tile_rows = p.Rs - tile_row0 < 128 ? p.Rs - tile_row0 : 128;
+
+  if (warp == GS_GATE_WARPS + 1 && lane == 0) {
+    for (int i = 0; i < GS_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 1);
+    mbar_init(a_ready, GS_GATE_WARPS);
+    *progress = 0;
+    fence_barrier_init();
+  } else if (warp == GS_GATE_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp >= GS_GATE_WARPS) {
+    regs_service_warps();
+    if (warp == GS_GATE_WARPS) {
+      // ===================== TMA producer: W_h^T pieces, the same 16 every timestep =====================
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int t = 0; t < T; ++t)
+          for (int jb = 0; jb < 4; ++jb)
+            for (int kc = 0; kc < 4; ++kc, ++it) {
+              const int s = it % GS_STAGES;
+              mbar_wait(&b_empty[s], ((it / GS_STAGES) & 1) ^ 1);
+              GS_STAMP(0, it);
+              mbar_expect_tx(&b_full[s], GS_FWD_STAGE);
+              uint8_t* st = sB + (size_t)s * GS_FWD_STAGE;
+#pragma unroll
+              for (int g = 0; g < 3; ++g) {
+                tma_load_2d(st + g * 4096, &tmWh, kc * 32, g * kH + 32 * jb, &b_full[s]);
+                tma_load_2d(st + GS_FWD_STAGE / 2 + g * 4096, &tmWl, kc * 32, g * kH + 32 * jb, &b_full[s]);
+              }
+            }
+      }
+    } else if (warp == GS_GATE_WARPS + 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        const uint32_t idesc = idesc_tf32(96);
+        const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
+        uint32_t it = 0;
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(a_ready, t & 1);
+          tc_fence_after();
+          GS_STAMP(1, t * 16);
+          for (int jb = 0; jb < 4; ++jb) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)(jb * 96);
+            for (int kc = 0; kc < 4; ++kc, ++it) {
+              const int s = it % GS_STAGES;
+              mbar_wait(&b_full[s], (it / GS_STAGES) & 1);
+              tc_fence_after();
+              if (kc == 0) GS_STAMP(1, t * 16 + 1 + jb * 2);
+              const uint32_t a_hi = a_hi0 + kc * GS_CHUNK, a_lo = a_lo0 + kc * GS_CHUNK;
+              const uint32_t b_hi = smem_u32(sB + (size_t)s * GS_FWD_STAGE), b_lo = b_hi + GS_FWD_STAGE / 2;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ko = k * 32;
+                umma_tf32(tmem_d, umma_desc_k_sw128(a_lo + ko), umma_desc_k_sw128(b_hi + ko), idesc, (kc | k) ? 1u : 0u);
+                umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_lo + ko), idesc, 1u);
+                umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_hi + ko), idesc, 1u);
+              }
+              umma_commit(&b_empty[s]);
+            }
+            umma_commit(&acc_full[jb]);
+            GS_STAMP(1, t * 16 + 2 + jb * 2);
+          }
+        }
+      }
+    } else if (warp == GS_GATE_WARPS + 2) {
+      // ============ L2 prefetch of the next timestep's input pre-activations (one contiguous block per tile) ============
+      l2_prefetch(p.gi + tile_row0 * (3 * kH), tile_rows * 3 * kH * 4, lane);
+      for (int t = 0; t + 1 < T; ++t) {
+        while (*progress < t + 1) __nanosleep(256);  // step t has started
+        l2_prefetch(p.gi + ((int64_t)(t + 1) * p.Rs + tile_row0) * (3 * kH), tile_rows * 3 * kH * 4, lane);
+      }
+    }
+  } else {
+    regs_gate_warps();
+    // ===================== gates: warp = (32 rows, 8 of every 32 hidden units), thread = 4 x 2 patch =====================
+    const int sp = warp & 3, cq = warp >> 2;
+    const GateGeom gg = make_geom(sp, lane, tile_row0, p.Rs);
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(sp * 32) << 16);
+    float h[32];  // masked previous state: block jb at [8 jb, 8 jb + 8)
+    float bh[8];
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+      load_patch(&h[8 * jb], p.HU, kH, 32 * jb + 8 * cq, gg);
+      store_patch_split(sAhi + jb * GS_CHUNK, sAlo + jb * GS_CHUNK, 8 * cq, &h[8 * jb], gg);
+      bh[2 * jb] = p.bhn[32 * jb + 8 * cq + 2 * gg.m];
+      bh[2 * jb + 1] = p.bhn[32 * jb + 8 * cq + 2 * gg.m + 1];
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready);
+
+    for (int t = 0; t < T; ++t) {
+      if (threadIdx.x == 0) *progress = t + 1;
+      const int64_t slab = (int64_t)t * p.Rs;
+      bool keep[4];  // row is live and not reset before the next step
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        keep[rr] = gg.valid[rr] && !((t + 1 < T) && p.done[(int64_t)(t + 1) * p.N + gg.grow[rr] / p.A]);
+#pragma unroll
+      for (int jb = 0; jb < 4; ++jb) {
+        const int j0 = 32 * jb + 8 * cq;
+        float gi_r[8], gi_z[8], gi_n[8];
+        load_patch(gi_r, p.gi + slab * (3 * kH), 3 * kH, j0, gg);
+        load_patch(gi_z, p.gi + slab * (3 * kH), 3 * kH, kH + j0, gg);
+        load_patch(gi_n, p.gi + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
+        if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 0);
+        mbar_wait(&acc_full[jb], t & 1);
+        tc_fence_after();
+        if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 1);
+        uint32_t ar[8], az[8], an[8];
+        const uint32_t tcol = tmem_lane + (uint32_t)(jb * 96 + 8 * cq);
+        tmem_ld_patch_nowait(tcol, ar);
+        tmem_ld_patch_nowait(tcol + 32, az);
+        tmem_ld_patch_nowait(tcol + 64, an);
+        tmem_ld_wait();
+        if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 2);
+        float y_[8];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = vidx(rr, e);
+            const float r = sigmoid_fast(gi_r[i] + __uint_as_float(ar[i]));
+            const float z = sigmoid_fast(gi_z[i] + __uint_as_float(az[i]));
+            const float ghn = __uint_as_float(an[i]) + bh[2 * jb + e];
+            const float n = tanh_fast(gi_n[i] + r * ghn);
+            const float hn = (1.0f - z) * n + z * h[8 * jb + i];
+            gi_r[i] = r; gi_z[i] = z; gi_n[i] = n;  // reuse as output registers
+            ar[i] = __float_as_uint(ghn);
+            y_[i] = hn;
+            h[8 * jb + i] = keep[rr] ? hn : 0.0f;
+          }
+        if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 3);
+        store_patch(gi_r, p.rzn + slab * (3 * kH), 3 * kH, j0, gg);
+        store_patch(gi_z, p.rzn + slab * (3 * kH), 3 * kH, kH + j0, gg);
+        store_patch(gi_n, p.rzn + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
+        store_patch(reinterpret_cast<const float*>(ar), p.ghn + slab * kH, kH, j0, gg);
+        store_patch(y_, p.Y + slab * kH, kH, j0, gg);
+        store_patch(&h[8 * jb], p.HU + (slab + p.Rs) * kH, kH, j0, gg);
+        if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 4);
+      }
+      if (t + 1 < T) {
+        // every MMA of this step has completed (acc_full[3] was observed): the A operand may be replaced
+#pragma unroll
+        for (int jb = 0; jb < 4; ++jb) store_patch_split(sAhi + jb * GS_CHUNK, sAlo + jb * GS_CHUNK, 8 * cq, &h[8 * jb], gg);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);  // one arrival per warp: 512 serialized shared-memory arrivals cost microseconds
+        if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + 3) * 6 + 5);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GS_GATE_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+struct GruBwdArgs {
+  int T, N, A;
+  int64_t Rs;
+  const float* dY;      // [T, Rs, 128]
+  const float* rzn;     // [T, Rs, 384]
+  const float* ghn;     // [T, Rs, 128]
+  const float* HU;      // [T+1, Rs, 128]
+  const uint8_t* done;  // [T, N]
+  float* dgi;           // [T, Rs, 384]  [da_r, da_z, da_n]
+  float* dgh;           // [T, Rs, 384]  [da_r, da_z, da_n * r]
+};
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
+gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const GruBwdArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = base;                         // 3 slots (gate r, z, n of the current block) x {hi 16K, lo 16K}
+  uint8_t* sB = sA + 3 * GS_BWD_STAGE;        // GS_STAGES x {hi 16K, lo 16K}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + GS_STAGES * GS_BWD_STAGE);
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = bars + GS_STAGES;
+  uint64_t* a_full = bars + 2 * GS_STAGES;   // the three slots of a block are handed over together
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* acc_full = a_empty + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  volatile int* progress = reinterpret_cast<volatile int*>(tmem_ptr + 1);  // timesteps started by the gate warps (prefetch throttle)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = p.T;
+  const int64_t tile_row0 = (int64_t)blockIdx.x * 128;
+  const int64_t tile_rows = p.Rs - tile_row0 < 128 ? p.Rs - tile_row0 : 128;
+
+  if (warp == GS_GATE_WARPS + 1 && lane == 0) {
+    for (int i = 0; i < GS_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(a_full, GS_GATE_WARPS);
+    mbar_init(a_empty, 1);
+    mbar_init(acc_full, 1);
+    *progress = 0;
+    fence_barrier_init();
+  } else if (warp == GS_GATE_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp >= GS_GATE_WARPS) {
+    regs_service_warps();
+    if (warp == GS_GATE_WARPS) {
+      // ============ TMA producer: W_h pieces [128 outputs x 32 contraction columns], order (block, gate) ============
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int si = 0; si + 1 < T; ++si)
+          for (int jb = 0; jb < 4; ++jb)
+            for (int g = 0; g < 3; ++g, ++it) {
+              const int s = it % GS_STAGES;
+              mbar_wait(&b_empty[s], ((it / GS_STAGES) & 1) ^ 1);
+              mbar_expect_tx(&b_full[s], GS_BWD_STAGE);
+              uint8_t* st = sB + (size_t)s * GS_BWD_STAGE;
+              tma_load_2d(st, &tmWh, g * kH + 32 * jb, 0, &b_full[s]);
+              tma_load_2d(st + GS_CHUNK, &tmWl, g * kH + 32 * jb, 0, &b_full[s]);
+            }
+      }
+    } else if (warp == GS_GATE_WARPS + 1) {
+      // ===================== MMA issuer: carry[128 rows, 128] = dgh_t @ W_h^T =====================
+      if (lane == 0) {
+        const uint32_t idesc = idesc_tf32(128);
+        uint32_t it = 0;
+        for (int si = 0; si + 1 < T; ++si) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)((si & 1) * 128);
+          for (int jb = 0; jb < 4; ++jb) {
+            const uint32_t n = (uint32_t)si * 4 + jb;
+            mbar_wait(a_full, n & 1);
+            for (int g = 0; g < 3; ++g, ++it) {
+              const int s = it % GS_STAGES;
+              mbar_wait(&b_full[s], (it / GS_STAGES) & 1);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(sA + (size_t)g * GS_BWD_STAGE), a_lo = a_hi + GS_CHUNK;
+              const uint32_t b_hi = smem_u32(sB + (size_t)s * GS_BWD_STAGE), b_lo = b_hi + GS_CHUNK;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ko = k * 32;
+                umma_tf32(tmem_d, umma_desc_k_sw128(a_lo + ko), umma_desc_k_sw128(b_hi + ko), idesc, (jb | g | k) ? 1u : 0u);
+                umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_lo + ko), idesc, 1u);
+                umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_hi + ko), idesc, 1u);
+              }
+              umma_commit(&b_empty[s]);
+            }
+            umma_commit(a_empty);
+          }
+          umma_commit(acc_full);
+        }
+      }
+    } else if (warp == GS_GATE_WARPS + 2) {
+      // ===================== L2 prefetch of the saved activations, about one timestep ahead of the gates =====================
+      for (int si = 0; si < T; ++si) {
+        while (*progress < si) __nanosleep(256);  // step si-1 has started
+        const int64_t r0 = (int64_t)(T - 1 - si) * p.Rs + tile_row0;
+        l2_prefetch(p.dY + r0 * kH, tile_rows * kH * 4, lane);
+        l2_prefetch(p.rzn + r0 * (3 * kH), tile_rows * 3 * kH * 4, lane);
+        l2_prefetch(p.ghn + r0 * kH, tile_rows * kH * 4, lane);
+        l2_prefetch(p.HU + r0 * kH, tile_rows * kH * 4, lane);
+      }
+    }
+  } else {
+    regs_gate_warps();
+    // ============ gate backward: warp = (32 rows, 8 of every 32 hidden units), thread = 4 x 2 patch ============
+    const int sp = warp & 3, cq = warp >> 2;
+    const GateGeom gg = make_geom(sp, lane, tile_row0, p.Rs);
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(sp * 32) << 16);
+    float cz[32];  // dh_{t+1} * z_{t+1}
+#pragma unroll
+    for (int i = 0; i < 32; ++i) cz[i] = 0.0f;
+
+    for (int si = 0; si < T; ++si) {
+      const int t = T - 1 - si;
+      if (threadIdx.x == 0) *progress = si + 1;
+      const int64_t slab = (int64_t)t * p.Rs;
+      const bool has_carry = si > 0;
+      bool use_carry[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        use_carry[rr] = has_carry && gg.valid[rr] && !p.done[(int64_t)(t + 1) * p.N + gg.grow[rr] / p.A];
+      const uint32_t tmem_acc = tmem_lane + (uint32_t)(((si + 1) & 1) * 128);  // written by the MMAs of step si-1
+      const bool feed = t > 0;  // the carry of step 0 goes nowhere
+#pragma unroll
+      for (int jb = 0; jb < 4; ++jb) {
+        const int j0 = 32 * jb + 8 * cq;
+        float dy[8], r_[8], z_[8], n_[8], gh_[8], hu[8];
+        load_patch(dy, p.dY + slab * kH, kH, j0, gg);
+        load_patch(r_, p.rzn + slab * (3 * kH), 3 * kH, j0, gg);
+        load_patch(z_, p.rzn + slab * (3 * kH), 3 * kH, kH + j0, gg);
+        load_patch(n_, p.rzn + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
+        load_patch(gh_, p.ghn + slab * kH, kH, j0, gg);
+        load_patch(hu, p.HU + slab * kH, kH, j0, gg);
+        uint32_t acc[8];
+        if (has_carry) {
+          if (jb == 0) {
+            mbar_wait(acc_full, (si - 1) & 1);
+            tc_fence_after();
+          }
+          tmem_ld_patch_nowait(tmem_acc + (uint32_t)j0, acc);
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = vidx(rr, e);
+            float dh = dy[i];
+            if (use_carry[rr]) dh += cz[8 * jb + i] + __uint_as_float(acc[i]);
+            const float r = r_[i], z = z_[i], n = n_[i];
+            const float dan = dh * (1.0f - z) * (1.0f - n * n);
+            const float daz = dh * (hu[i] - n) * z * (1.0f - z);
+            const float dar = dan * gh_[i] * r * (1.0f - r);
+            cz[8 * jb + i] = dh * z;
+            r_[i] = dar; z_[i] = daz; n_[i] = dan; gh_[i] = dan * r;  // reuse as output registers
+          }
+        store_patch(r_, p.dgi + slab * (3 * kH), 3 * kH, j0, gg);
+        store_patch(z_, p.dgi + slab * (3 * kH), 3 * kH, kH + j0, gg);
+        store_patch(n_, p.dgi + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
+        store_patch(r_, p.dgh + slab * (3 * kH), 3 * kH, j0, gg);
+        store_patch(z_, p.dgh + slab * (3 * kH), 3 * kH, kH + j0, gg);
+        store_patch(gh_, p.dgh + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
+        if (feed) {
+          const uint32_t n = (uint32_t)si * 4 + jb;
+          mbar_wait(a_empty, (n & 1) ^ 1);
+          store_patch_split(sA, sA + GS_CHUNK, 8 * cq, r_, gg);
+          store_patch_split(sA + GS_BWD_STAGE, sA + GS_BWD_STAGE + GS_CHUNK, 8 * cq, z_, gg);
+          store_patch_split(sA + 2 * GS_BWD_STAGE, sA + 2 * GS_BWD_STAGE + GS_CHUNK, 8 * cq, gh_, gg);
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GS_GATE_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+}  // namespace
+
+unsigned long long* g_gru_dbg = nullptr;
+
+// HU[0] must already hold the masked initial state. WhT_hi/lo: TF32 images of W_h^T [384, 128].
+int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const float* WhT_hi, const float* WhT_lo, const float* bhn,
+                 const uint8_t* done, float* rzn, float* ghn, float* Y, float* HU) {
+  const int64_t Rs = (int64_t)N * A;
+  CUtensorMap tmh, tml;
+  if (!tc_make_map(&tmh, WhT_hi, 3 * kH, kH, kH, 32) || !tc_make_map(&tml, WhT_lo, 3 * kH, kH, kH, 32)) return MAGPO_ERR_ARG;
+  static bool attr = false;
+  if (!attr) {
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+    attr = true;
+  }
+  GruFwdArgs a{g_gru_dbg, T, N, A, Rs, gi, bhn, done, rzn, ghn, Y, HU};
+  // per row and step: 3xTF32 MMAs are the pipe work; bytes: gi 1536 read, rzn+ghn+Y+HU 3072 written
+  ProfScope ps(PROF_GRU, s, 4608.0 * (double)Rs * T);
+  gru_scan_fwd_kernel<<<(unsigned)ceil_div(Rs, 128), GS_THREADS, GS_SMEM, s>>>(tmh, tml, a);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+// Wh_hi/lo: TF32 images of W_h [128, 384] (un-transposed).
+int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const float* rzn, const float* ghn, const float* HU,
+                 const uint8_t* done, const float* Wh_hi, const float* Wh_lo, float* dgi, float* dgh) {
+  const int64_t Rs = (int64_t)N * A;
+  CUtensorMap tmh, tml;
+  if (!tc_make_map(&tmh, Wh_hi, kH, 3 * kH, 3 * kH, 128) || !tc_make_map(&tml, Wh_lo, kH, 3 * kH, 3 * kH, 128)) return MAGPO_ERR_ARG;
+  static bool attr = false;
+  if (!attr) {
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+    attr = true;
+  }
+  GruBwdArgs a{T, N, A, Rs, dY, rzn, ghn, HU, done, dgi, dgh};
+  ProfScope ps(PROF_GRU, s, 6144.0 * (double)Rs * T);
+  gru_scan_bwd_kernel<<<(unsigned)ceil_div(Rs, 128), GS_THREADS, GS_SMEM, s>>>(tmh, tml, a);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+}  // namespace magpo
+
+// GRU_TIMELINE=1 tools/diag_gru.py: device buffer of 3 x 1024 uint64 %globaltimer stamps written by CTA 0 of the forward scan
+extern "C" int magpo_debug_gru_timeline(unsigned long long* buf) {
+  magpo::g_gru_dbg = buf;
+  return MAGPO_OK;
+}

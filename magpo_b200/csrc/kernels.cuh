@@ -36,8 +36,15 @@ int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
             const float* bias, float* Y, int ldy, int flags);
 bool tc_tn_supported(int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, const float* dW, int ldw);
 int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw);
+// TMA map (CUtensorMap*) of a row-major fp32 [rows, cols] matrix (leading dimension ld): boxes of [box_rows x 32 floats], 128B swizzle
+bool tc_make_map(void* tensor_map, const float* ptr, int64_t rows, int cols, int ld, int box_rows);
 int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW,
             int ldw);
+// ---- gru_scan.cu: persistent tcgen05 GRU scans over T steps (one CTA per 128 rows, W_h streamed through a TMA ring)
+int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const float* WhT_hi, const float* WhT_lo, const float* bhn,
+                 const uint8_t* done, float* rzn, float* ghn, float* Y, float* HU);
+int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const float* rzn, const float* ghn, const float* HU,
+                 const uint8_t* done, const float* Wh_hi, const float* Wh_lo, float* dgi, float* dgh);
 int colsum(cudaStream_t s, int64_t M, int N, const float* dY, int ldy, float* db);
 int transpose(cudaStream_t s, int R, int Cc, const float* in, float* out);
 

@@ -128,7 +128,7 @@ def test_guider_and_actor_forward(dev, A, d, a, T, N):
     assert rel_err(got[m], a_ref.numpy()[m]) < 1e-4
 
 
-@pytest.mark.parametrize("A,d,a,T,Ns,U", [(3, 4, 10, 12, 5, 2), (4, 75, 5, 6, 3, 1)])
+@pytest.mark.parametrize("A,d,a,T,Ns,U", [(3, 4, 10, 12, 5, 2), (4, 75, 5, 6, 3, 1), (3, 4, 10, 9, 50, 2)])
 def test_minibatch_grads(dev, A, d, a, T, Ns, U):
     cfg, net, gp, ap, (gt, ng, gflat), (at, na, aflat) = setup_nets(A, d, a, dev)
     sysc = olr.SysCfg(num_envs=Ns, update_batch_size=U, rollout_length=T, num_minibatches=1)

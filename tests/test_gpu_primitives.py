@@ -165,7 +165,7 @@ def test_gemm_blocks(dev, M, N, K):
 
 
 @pytest.mark.parametrize("causal", [False, True])
-@pytest.mark.parametrize("T,N,A", [(12, 5, 3), (40, 3, 4), (1, 7, 1), (9, 2, 8)])
+@pytest.mark.parametrize("T,N,A", [(12, 5, 3), (40, 3, 4), (1, 7, 1), (9, 2, 8), (9, 100, 3), (16, 300, 2)])
 def test_retention_scan_equals_chunkwise_reference(dev, causal, T, N, A):
     """The recurrent-form CUDA scan (fwd + bwd) against the oracle's chunkwise D-matrix/xi form with autograd."""
     rng = np.random.default_rng(3)

@@ -45,6 +45,10 @@ def timeit(fn, reps=args.reps):
 
 print(f"E={args.num_envs} U={args.update_batch_size} T={args.rollout_length} chunk={lrn.chunk}")
 print(f"rollout+bootstrap      {timeit(lrn.rollout):9.3f} ms")
+import time
+torch.cuda.synchronize()
+t0 = time.perf_counter(); lrn.rollout(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"  host enqueue time of one rollout call {1e3 * (t1 - t0):9.3f} ms (then {1e3 * (t2 - t1):.3f} ms until the GPU drained)")
 print(f"gae                    {timeit(lrn.gae):9.3f} ms")
 lrn.epoch_indices(True)
 res = {}
@@ -59,4 +63,14 @@ print(f"  guider fwd           {res['all'] - res['no guider'] - (res['all'] - re
 print(f"  guider bwd           {res['all'] - res['no guider bwd']:9.3f} ms")
 print(f"  learner fwd          {res['all'] - res['no learner'] - (res['all'] - res['no learner bwd']):9.3f} ms")
 print(f"  learner bwd          {res['all'] - res['no learner bwd']:9.3f} ms")
+lib.magpo_debug_force_gru_stepwise(1)
+lib.magpo_debug_set_skip(1)
+a = timeit(lambda: lrn.minibatch_grads(0))
+lib.magpo_debug_set_skip(1 | 8)
+b = timeit(lambda: lrn.minibatch_grads(0))
+lib.magpo_debug_set_skip(3)
+c = timeit(lambda: lrn.minibatch_grads(0))
+print(f"  (per-timestep GRU path: learner fwd {b - c:9.3f} ms, bwd {a - b:9.3f} ms)")
+lib.magpo_debug_force_gru_stepwise(0)
+lib.magpo_debug_set_skip(0)
 print(f"apply_grads            {timeit(lrn.apply_grads):9.3f} ms")
