@@ -232,8 +232,10 @@ def main():
     if not args.no_profile:
         # one more step with per-category CUDA events on the launching stream (bench-only instrumentation)
         lib.magpo_prof_enable(1 if rank == 0 else 0)
+        lrn.graph_rollout = False  # the per-category events are recorded by eager launches, not by a graph replay
         lrn.update_step()
         torch.cuda.synchronize()
+        lrn.graph_rollout = True
         lib.magpo_prof_enable(0)
         if rank == 0:
             brk, total = {}, 0.0

@@ -43,6 +43,11 @@ ProfScope::~ProfScope() {
 
 extern "C" {
 int64_t magpo_launch_count(void) { return magpo::g_launches.load(); }
+// A host that replays a captured graph of library calls adds the launches of each replay (negative n: undo a capture pass).
+int magpo_launch_count_add(int64_t n) {
+  magpo::g_launches.fetch_add(n, std::memory_order_relaxed);
+  return MAGPO_OK;
+}
 // on != 0: start recording (drops earlier records); on == 0: stop.
 int magpo_prof_enable(int on) {
   magpo::g_prof_on = on != 0;

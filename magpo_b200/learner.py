@@ -144,8 +144,12 @@ def alloc_timestep(B, A, d, a, dev) -> dict:
 class MagpoLearner:
     """All device buffers of one rank + `update_step()` (rollout, GAE, P epochs x M minibatches)."""
 
-    def __init__(self, env: CoordSumVec, sys: SystemConfig, device="cuda:0", allreduce=None, world_size: int = 1):
+    def __init__(self, env: CoordSumVec, sys: SystemConfig, device="cuda:0", allreduce=None, world_size: int = 1,
+                 graph_rollout: bool = True):
         self.env, self.sys, self.dev = env, sys, torch.device(device)
+        # The T-step rollout is ~90 short launches per env step: after the first (eager) call it is replayed from one
+        # CUDA graph, the way XLA runs command-buffer-compatible FFI handlers. All its operands are device-resident.
+        self.graph_rollout, self._rollout_graph, self._rollout_graph_launches = graph_rollout, None, 0
         self.net = NetworkConfig(env.num_agents, env.obs_dim, env.action_dim, env.time_limit)
         self.allreduce, self.world_size = allreduce, world_size
         self.c_net, self.c_sys = self.net.c_struct(), sys.c_struct()
@@ -240,13 +244,29 @@ class MagpoLearner:
         torch.cuda.current_stream().synchronize()  # `keys` must outlive the launch
 
     # ------------------------------------------------------------------ the step
-    def rollout(self) -> None:
-        s = L.stream_ptr()
-        L.call("magpo_rollout", s, C.byref(self.c_net), C.byref(self.c_sys), self.env.kind, C.byref(self.env.cfg),
+    def _rollout_call(self, carry_over: int) -> None:
+        L.call("magpo_rollout", L.stream_ptr(), C.byref(self.c_net), C.byref(self.c_sys), self.env.kind, C.byref(self.env.cfg),
                C.byref(self.env.state_struct(self.env_state)), self._ts_struct(), L.ptr(self.guider), L.ptr(self.actor),
                L.ptr(self.key), L.struct_of(L.SableHState, **self.hs), L.ptr(self.policy_h), self._traj_struct(),
-               0 if self.first_rollout else 1, L.ptr(self.workspace), C.c_size_t(self.ws_bytes))
-        self.first_rollout = False
+               carry_over, L.ptr(self.workspace), C.c_size_t(self.ws_bytes))
+
+    def rollout(self) -> None:
+        if self.first_rollout or not self.graph_rollout:
+            self._rollout_call(0 if self.first_rollout else 1)
+            self.first_rollout = False
+            return
+        lib = L.lib()
+        if self._rollout_graph is None:
+            lib.magpo_launch_count.restype = C.c_int64
+            n0 = lib.magpo_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._rollout_call(1)
+            self._rollout_graph_launches = int(lib.magpo_launch_count() - n0)
+            lib.magpo_launch_count_add(C.c_int64(-self._rollout_graph_launches))  # capturing launched nothing
+            self._rollout_graph = g
+        self._rollout_graph.replay()
+        lib.magpo_launch_count_add(C.c_int64(self._rollout_graph_launches))
 
     def gae(self) -> None:
         T, B, A = self.sys.rollout_length, self.B, self.net.n_agents

@@ -140,7 +140,8 @@ def test_minibatch_grads(dev, A, d, a, T, Ns, U):
     for u in range(U):
         sl = slice(u * Ns, (u + 1) * Ns)
         part = {k: (tuple(h[sl] for h in v) if k == "prev_hstates" else v[sl]) for k, v in mb.items()}
-        gg, ga, info, _ = olr.minibatch_losses_and_grads(gp, ap, part, cfg, sysc)
+        # fp64 oracle: the comparison then measures the CUDA path's own rounding, not the sum of two fp32 roundings
+        gg, ga, info, _ = olr.minibatch_losses_and_grads(gp, ap, part, cfg, sysc, dtype=torch.float64)
         gsum = gg if gsum is None else {k: gsum[k] + gg[k] for k in gg}
         asum = ga if asum is None else {k: asum[k] + ga[k] for k in ga}
         infos.append(info)
