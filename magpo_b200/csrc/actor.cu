@@ -124,7 +124,8 @@ void ActorActs::plan(Arena& ar, int64_t R, int64_t Rs, int a, bool with_backward
 int actor_forward(cudaStream_t s, const ActorP& p, const ActorT* pt, int T, int N, int A, int d, int a, const float* agents_view,
                   const uint8_t* done, const float* h0, const ActorActs& w, float* logits, float* h_out) {
   const int64_t Rs = (int64_t)N * A, R = Rs * T;
-  MAGPO_TRY(gemm_nn(s, R, kH, d, agents_view, d, wref(p.pre_w, kH), p.pre_b, w.e, kH, GEMM_RELU));
+  if (thin_k_ok(d, kH, kH, p.pre_w, w.e, kH)) MAGPO_TRY(thin_k_fwd(s, R, d, kH, agents_view, d, p.pre_w, kH, p.pre_b, w.e, kH, 1));
+  else MAGPO_TRY(gemm_nn(s, R, kH, d, agents_view, d, wref(p.pre_w, kH), p.pre_b, w.e, kH, GEMM_RELU));
   MAGPO_TRY(gemm_nn(s, R, 3 * kH, kH, w.e, kH, wref(p.Wi, 3 * kH, pt ? pt->WiT : nullptr, kH), p.bi, w.gi, 3 * kH, 0));
   mask_rows_kernel<<<g256(Rs * kH), 256, 0, s>>>(Rs, A, h0, done, w.HU);
   MAGPO_LAUNCH_OK();
@@ -145,7 +146,8 @@ int actor_forward(cudaStream_t s, const ActorP& p, const ActorT* pt, int T, int 
                                            cudaMemcpyDeviceToDevice, s));
   if (logits) {
     MAGPO_TRY(gemm_nn(s, R, kH, kH, w.Y, kH, wref(p.post_w, kH, pt ? pt->postT : nullptr, kH), p.post_b, w.post, kH, GEMM_RELU));
-    MAGPO_TRY(gemm_nn(s, R, a, kH, w.post, kH, wref(p.head_w, a), p.head_b, logits, a, 0));
+    if (thin_n_ok(kH, a, w.post, kH)) MAGPO_TRY(thin_n_fwd(s, R, kH, a, w.post, kH, p.head_w, a, p.head_b, logits, a));
+    else MAGPO_TRY(gemm_nn(s, R, a, kH, w.post, kH, wref(p.head_w, a), p.head_b, logits, a, 0));
   }
   return MAGPO_OK;
 }
@@ -156,11 +158,15 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
                    const ActorP& g) {
   const int64_t Rs = (int64_t)N * A, R = Rs * T;
   // head + post torso
-  MAGPO_TRY(gemm_tn(s, R, a, kH, w.post, kH, dlogits, a, g.head_w, a));
-  MAGPO_TRY(colsum(s, R, a, dlogits, a, g.head_b));
-  MAGPO_TRY(gemm_nn(s, R, kH, a, dlogits, a, wref(pt.headT, kH), nullptr, w.dA, kH, 0));
-  relu_bwd_kernel<<<g256(R * kH), 256, 0, s>>>(R * kH, w.post, w.dA);
-  MAGPO_LAUNCH_OK();
+  if (thin_n_ok(kH, a, w.post, kH)) {  // dW, db, dX and the relu mask of the post torso in one pass
+    MAGPO_TRY(thin_n_bwd(s, R, kH, a, w.post, kH, dlogits, a, p.head_w, a, 1, w.dA, kH, g.head_w, a, g.head_b));
+  } else {
+    MAGPO_TRY(gemm_tn(s, R, a, kH, w.post, kH, dlogits, a, g.head_w, a));
+    MAGPO_TRY(colsum(s, R, a, dlogits, a, g.head_b));
+    MAGPO_TRY(gemm_nn(s, R, kH, a, dlogits, a, wref(pt.headT, kH), nullptr, w.dA, kH, 0));
+    relu_bwd_kernel<<<g256(R * kH), 256, 0, s>>>(R * kH, w.post, w.dA);
+    MAGPO_LAUNCH_OK();
+  }
   MAGPO_TRY(gemm_tn(s, R, kH, kH, w.Y, kH, w.dA, kH, g.post_w, kH));
   MAGPO_TRY(colsum(s, R, kH, w.dA, kH, g.post_b));
   MAGPO_TRY(gemm_nn(s, R, kH, kH, w.dA, kH, wref(pt.postT, kH, p.post_w, kH), nullptr, w.dB, kH, 0));  // dB = dL/dY
@@ -189,8 +195,12 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
   MAGPO_TRY(gemm_nn(s, R, kH, 3 * kH, dgi, 3 * kH, wref(pt.WiT, kH, p.Wi, 3 * kH), nullptr, w.dA, kH, 0));  // dA = dL/de (pre-relu mask next)
   relu_bwd_kernel<<<g256(R * kH), 256, 0, s>>>(R * kH, w.e, w.dA);
   MAGPO_LAUNCH_OK();
-  MAGPO_TRY(gemm_tn(s, R, kH, d, agents_view, d, w.dA, kH, g.pre_w, kH));
-  MAGPO_TRY(colsum(s, R, kH, w.dA, kH, g.pre_b));
+  if (thin_k_ok(d, kH, kH, w.dA, w.dA, kH)) {
+    MAGPO_TRY(thin_k_bwd(s, R, d, kH, agents_view, d, w.dA, kH, g.pre_w, kH, g.pre_b));
+  } else {
+    MAGPO_TRY(gemm_tn(s, R, kH, d, agents_view, d, w.dA, kH, g.pre_w, kH));
+    MAGPO_TRY(colsum(s, R, kH, w.dA, kH, g.pre_b));
+  }
   return MAGPO_OK;
 }
 

@@ -82,6 +82,25 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// Sum of NV per-lane values across the warp (NV a power of two): afterwards v[0] of lane l holds the warp total of value
+// index l >> (5 - log2 NV). NV - 1 + (5 - log2 NV) shuffles instead of 5 NV.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], int lane) {
+  int bit = 16;
+#pragma unroll
+  for (int half = NV / 2; half >= 1; half >>= 1, bit >>= 1) {
+    const bool up = lane & bit;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  for (; bit >= 1; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
+}
+template <int NV> struct Log2 { static constexpr int v = 1 + Log2<NV / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
 // flax nn.gelu(approximate=True)

@@ -184,6 +184,14 @@ int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, Wr
             int ldy, int flags) {
   if (M <= 0 || N <= 0) return MAGPO_OK;
   if (K <= 0) return MAGPO_ERR_ARG;
+  if (Wr.wt && K > 256 && K % 128 == 0 && !bias && !(flags & GEMM_RELU) && tc_supported(M, N, 128, X, ldx, Y, ldy, Wr.ldwt)) {
+    // a [K > 256, N] weight (hi + lo images) does not fit in shared memory beside the pipeline: run K in slices of 128 that
+    // accumulate into Y (TMA reduce-add) instead of falling back to 32-column tiles that re-read X four times
+    for (int k0 = 0; k0 < K; k0 += 128)
+      MAGPO_TRY(gemm_nn(s, M, N, 128, X + k0, ldx, wref(Wr.w + (size_t)k0 * Wr.ldw, Wr.ldw, Wr.wt + k0, Wr.ldwt), nullptr, Y, ldy,
+                        k0 ? (flags | GEMM_ACCUMULATE) : flags));
+    return MAGPO_OK;
+  }
   if (Wr.wt && !((flags & GEMM_ACCUMULATE) && ((flags & GEMM_RELU) || bias)) && tc_supported(M, N, K, X, ldx, Y, ldy, Wr.ldwt)) {
     const float *hi, *lo;
     if (tc_lookup(Wr.wt, &hi, &lo)) return gemm_tc(s, M, N, K, X, ldx, hi, lo, Wr.ldwt, bias, Y, ldy, flags);

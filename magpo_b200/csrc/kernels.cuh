@@ -48,6 +48,24 @@ int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const flo
 int colsum(cudaStream_t s, int64_t M, int N, const float* dY, int ldy, float* db);
 int transpose(cudaStream_t s, int R, int Cc, const float* in, float* out);
 
+// ---- thin.cu: dense layers with a thin side (K <= 16 or N <= 16), HBM-bound streaming kernels
+bool thin_k_ok(int K, int N, int ldw, const float* W, const float* Y, int ldy);
+bool thin_n_ok(int K, int N, const float* X, int ldx);
+bool obs_embed_ok(int d);
+int thin_k_fwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* W, int ldw, const float* bias,
+               float* Y, int ldy, int relu);
+int thin_k_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, float* dW, int lddw,
+               float* db);
+int thin_n_fwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* W, int ldw, const float* bias,
+               float* Y, int ldy);
+int thin_n_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, const float* W, int ldw,
+               int relu_mask, float* dX, int lddx, float* dW, int lddw, float* db);
+int obs_embed_fwd(cudaStream_t s, int64_t R, int d, const float* obs, const float* obs_scale, const float* Wobs,
+                  const float* ln_scale, const float* pe, const int32_t* step, int max_step, float* on, float* z0, float* xin,
+                  float* kqv);
+int obs_embed_bwd(cudaStream_t s, int64_t R, int d, const float* obs, const float* obs_scale, const float* Wobs, const float* dz0,
+                  float* dWobs, float* dscale);
+
 // ---- rowops.cu (all on 64-wide rows unless noted)
 enum { ROW_GELU = 1 };
 // on = RMSNorm_d(x) * scale, general width C (the obs encoder's first layer, sable_network.py:93-101)

@@ -224,90 +224,129 @@ swiglu_bwd_kernel(int64_t R, const float* __restrict__ gl, const float* __restri
 }
 
 // ------------------------------------------------------------------ head tail: gelu -> RMSNorm -> Dense(nout)
+// gelu(x) and gelu'(x) from one tanh
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+  const float c = 0.7978845608028654f;
+  const float x2 = x * x;
+  const float t = tanhf(c * (x + 0.044715f * x * x2));
+  g = 0.5f * x * (1.0f + t);
+  dg = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * (1.0f + 3.0f * 0.044715f * x2);
+}
+
+
+// The last Dense's weights live in registers: lane l holds rows 2l, 2l+1 of W3 [64, nout] (padded to NV columns).
+template <int NV>
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(int64_t R, const float* __restrict__ zh, const float* __restrict__ scale,
                 const float* __restrict__ W3, const float* __restrict__ b3, int nout, float* __restrict__ out) {
-  __shared__ float Ws[kD * kMaxActions];
-  for (int i = threadIdx.x; i < kD * nout; i += blockDim.x) Ws[i] = W3[i];
-  __syncthreads();
-  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
   const int lane_ = threadIdx.x & 31;
-  const float bias = lane_ < nout ? b3[lane_] : 0.f;
-  ROW_LOOP() {
-    float2 p = ld2(zh, row, kD, lane);
-    p.x = gelu_tanh(p.x); p.y = gelu_tanh(p.y);
-    const float ss = warp_sum(p.x * p.x + p.y * p.y);
-    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
-    const float2 hn = make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
-    float acc = 0.f;
-    const int j = lane < nout ? lane : 0;
+  float w0[NV], w1[NV];
 #pragma unroll
-    for (int l = 0; l < 32; ++l) {
-      const float a = __shfl_sync(0xffffffffu, hn.x, l);
-      const float b = __shfl_sync(0xffffffffu, hn.y, l);
-      acc = fmaf(a, Ws[(2 * l) * nout + j], acc);
-      acc = fmaf(b, Ws[(2 * l + 1) * nout + j], acc);
+  for (int j = 0; j < NV; ++j) {
+    w0[j] = j < nout ? W3[(2 * lane_) * nout + j] : 0.f;
+    w1[j] = j < nout ? W3[(2 * lane_ + 1) * nout + j] : 0.f;
+  }
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * lane_);
+  const int mine = lane_ >> (5 - Log2<NV>::v);
+  const bool writer = (lane_ & ((32 >> Log2<NV>::v) - 1)) == 0 && mine < nout;
+  const float bias = mine < nout ? b3[mine] : 0.f;
+  constexpr int UN = 4;  // rows in flight per warp
+  const int lane = lane_;
+  const int64_t wg = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5), wstride = (int64_t)gridDim.x * kWarps;
+  for (int64_t row0 = wg; row0 < R; row0 += UN * wstride) {
+    float2 zz[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) zz[u] = row0 + u * wstride < R ? ld2(zh, row0 + u * wstride, kD, lane) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t row = row0 + u * wstride;
+      if (row >= R) break;
+      const float2 p = make_float2(gelu_tanh(zz[u].x), gelu_tanh(zz[u].y));
+      const float ss = warp_sum(p.x * p.x + p.y * p.y);
+      const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
+      const float2 hn = make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
+      float v[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = fmaf(hn.x, w0[j], hn.y * w1[j]);
+      warp_reduce_scatter<NV>(v, lane);
+      if (writer) out[row * nout + mine] = v[0] + bias;
     }
-    if (lane < nout) out[row * nout + lane] = acc + bias;
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(int64_t R, const float* __restrict__ zh, const float* __restrict__ scale,
                 const float* __restrict__ W3, int nout, const float* __restrict__ dout, float* __restrict__ dzh,
                 float* __restrict__ dscale, float* __restrict__ dW3, float* __restrict__ db3) {
-  __shared__ float Ws[kD * kMaxActions];
-  __shared__ float dWs[kD * kMaxActions];
+  __shared__ float dWs[kD * NV];
   __shared__ float sm[kWarps * 64];
-  __shared__ float dbs[kMaxActions];
-  for (int i = threadIdx.x; i < kD * nout; i += blockDim.x) { Ws[i] = W3[i]; dWs[i] = 0.f; }
-  if (threadIdx.x < kMaxActions) dbs[threadIdx.x] = 0.f;
+  __shared__ float dbs[NV];
+  for (int i = threadIdx.x; i < kD * NV; i += blockDim.x) dWs[i] = 0.f;
+  if (threadIdx.x < NV) dbs[threadIdx.x] = 0.f;
   __syncthreads();
-  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
+  const int lane_ = threadIdx.x & 31;
+  float w0[NV], w1[NV], dwx[NV], dwy[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    w0[j] = j < nout ? W3[(2 * lane_) * nout + j] : 0.f;
+    w1[j] = j < nout ? W3[(2 * lane_ + 1) * nout + j] : 0.f;
+    dwx[j] = 0.f; dwy[j] = 0.f;
+  }
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * lane_);
   float2 ds = make_float2(0.f, 0.f);
-  float dwx[kMaxActions], dwy[kMaxActions];
-#pragma unroll
-  for (int j = 0; j < kMaxActions; ++j) { dwx[j] = 0.f; dwy[j] = 0.f; }
   float dbl = 0.f;
-  ROW_LOOP() {
-    const float2 zz = ld2(zh, row, kD, lane);
-    const float2 p = make_float2(gelu_tanh(zz.x), gelu_tanh(zz.y));
-    const float ss = warp_sum(p.x * p.x + p.y * p.y);
-    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
-    const float2 hn = make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
-    const float dol = lane < nout ? dout[row * nout + lane] : 0.f;
-    dbl += dol;
-    float2 dhn = make_float2(0.f, 0.f);
+  constexpr int UN = NV <= 8 ? 4 : 2;  // rows in flight per warp
+  const int lane = lane_;
+  const int64_t wg = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5), wstride = (int64_t)gridDim.x * kWarps;
+  for (int64_t row0 = wg; row0 < R; row0 += UN * wstride) {
+    float2 zs[UN];
+    float dls[UN];
 #pragma unroll
-    for (int j = 0; j < kMaxActions; ++j) {
-      if (j < nout) {
-        const float dj = __shfl_sync(0xffffffffu, dol, j);
-        dhn.x = fmaf(dj, Ws[(2 * lane) * nout + j], dhn.x);
-        dhn.y = fmaf(dj, Ws[(2 * lane + 1) * nout + j], dhn.y);
+    for (int u = 0; u < UN; ++u) {
+      const int64_t row = row0 + u * wstride;
+      const bool ok = row < R;
+      zs[u] = ok ? ld2(zh, row, kD, lane) : make_float2(0.f, 0.f);
+      dls[u] = (ok && lane < nout) ? dout[row * nout + lane] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t row = row0 + u * wstride;
+      if (row >= R) break;
+      const float2 zz = zs[u];
+      float2 p, gp;
+      gelu_both(zz.x, p.x, gp.x);
+      gelu_both(zz.y, p.y, gp.y);
+      const float ss = warp_sum(p.x * p.x + p.y * p.y);
+      const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
+      const float2 hn = make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
+      const float dol = dls[u];
+      dbl += dol;
+      float2 dhn = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float dj = __shfl_sync(0xffffffffu, dol, j);  // zero for j >= nout
+        dhn.x = fmaf(dj, w0[j], dhn.x);
+        dhn.y = fmaf(dj, w1[j], dhn.y);
         dwx[j] = fmaf(hn.x, dj, dwx[j]);
         dwy[j] = fmaf(hn.y, dj, dwy[j]);
       }
+      ds.x += dhn.x * p.x * rstd;
+      ds.y += dhn.y * p.y * rstd;
+      const float2 u2 = make_float2(dhn.x * sc.x, dhn.y * sc.y);
+      const float dot = warp_sum(p.x * u2.x + p.y * u2.y) * (1.0f / kD);
+      const float r3 = rstd * rstd * rstd;
+      st2(dzh, row, kD, lane, make_float2((rstd * u2.x - p.x * r3 * dot) * gp.x, (rstd * u2.y - p.y * r3 * dot) * gp.y));
     }
-    ds.x += dhn.x * p.x * rstd;
-    ds.y += dhn.y * p.y * rstd;
-    const float2 u = make_float2(dhn.x * sc.x, dhn.y * sc.y);
-    const float dot = warp_sum(p.x * u.x + p.y * u.y) * (1.0f / kD);
-    const float r3 = rstd * rstd * rstd;
-    st2(dzh, row, kD, lane,
-        make_float2((rstd * u.x - p.x * r3 * dot) * gelu_tanh_grad(zz.x),
-                    (rstd * u.y - p.y * r3 * dot) * gelu_tanh_grad(zz.y)));
   }
-  {
-    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < kMaxActions; ++j) {
-      if (j < nout) {
-        atomicAdd(&dWs[(2 * lane) * nout + j], dwx[j]);
-        atomicAdd(&dWs[(2 * lane + 1) * nout + j], dwy[j]);
-      }
+  for (int j = 0; j < NV; ++j) {
+    if (j < nout) {
+      atomicAdd(&dWs[(2 * lane_) * nout + j], dwx[j]);
+      atomicAdd(&dWs[(2 * lane_ + 1) * nout + j], dwy[j]);
     }
-    if (lane < nout) atomicAdd(&dbs[lane], dbl);
   }
+  if (lane_ < nout) atomicAdd(&dbs[lane_], dbl);
   __syncthreads();
   for (int i = threadIdx.x; i < kD * nout; i += blockDim.x) atomicAdd(dW3 + i, dWs[i]);
   if (threadIdx.x < nout) atomicAdd(db3 + threadIdx.x, dbs[threadIdx.x]);
@@ -466,7 +505,10 @@ int head_fwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, con
   if (R <= 0) return MAGPO_OK;
   ProfScope ps(PROF_ROWOPS, s, (256.0 + 4.0 * nout) * R);
   if (nout < 1 || nout > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
-  head_fwd_kernel<<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, b3, nout, out);
+  if (nout == 1) head_fwd_kernel<1><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, b3, nout, out);
+  else if (nout <= 8) head_fwd_kernel<8><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, b3, nout, out);
+  else if (nout <= 16) head_fwd_kernel<16><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, b3, nout, out);
+  else head_fwd_kernel<32><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, b3, nout, out);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
@@ -475,7 +517,10 @@ int head_bwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, con
   if (R <= 0) return MAGPO_OK;
   ProfScope ps(PROF_ROWOPS, s, (512.0 + 4.0 * nout) * R);
   if (nout < 1 || nout > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
-  head_bwd_kernel<<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
+  if (nout == 1) head_bwd_kernel<1><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
+  else if (nout <= 8) head_bwd_kernel<8><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
+  else if (nout <= 16) head_bwd_kernel<16><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
+  else head_bwd_kernel<32><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }

@@ -74,9 +74,13 @@ int sable_encoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
                           const float* agents_view, const int32_t* step, const uint8_t* done, const float* H0,
                           float kappa, const float* pe, const SableActs& w, float* value, float* Hsave, float* Hout) {
   const int64_t R = (int64_t)T * N * A;
-  MAGPO_TRY(rms_general_fwd(s, R, d, agents_view, p.obs_scale, w.on));
-  MAGPO_TRY(gemm_nn(s, R, kD, d, w.on, d, wref(p.Wobs, kD), nullptr, w.z0, kD, 0));
-  MAGPO_TRY(act_rms_fwd(s, R, w.z0, nullptr, p.ln, ROW_GELU, pe, step, max_step, w.xin, w.kqv));
+  if (obs_embed_ok(d)) {
+    MAGPO_TRY(obs_embed_fwd(s, R, d, agents_view, p.obs_scale, p.Wobs, p.ln, pe, step, max_step, w.on, w.z0, w.xin, w.kqv));
+  } else {
+    MAGPO_TRY(rms_general_fwd(s, R, d, agents_view, p.obs_scale, w.on));
+    MAGPO_TRY(gemm_nn(s, R, kD, d, w.on, d, wref(p.Wobs, kD), nullptr, w.z0, kD, 0));
+    MAGPO_TRY(act_rms_fwd(s, R, w.z0, nullptr, p.ln, ROW_GELU, pe, step, max_step, w.xin, w.kqv));
+  }
   MAGPO_TRY(gemm_nn(s, R, 4 * kD, kD, w.kqv, kD, wref(p.qkvg, 4 * kD, pt ? pt->qkvgT : nullptr, kD), nullptr, w.qkvg, 4 * kD, 0));
   MAGPO_TRY(retention_fwd(s, T, N, A, kappa, false, w.qkvg, w.qkvg + kD, w.qkvg + 2 * kD, 4 * kD, H0, done, w.ret,
                           Hsave, Hout));
@@ -192,8 +196,12 @@ int sable_train_backward(cudaStream_t s, const GuiderP& p, const GuiderT& pt, co
                           w.Hs_enc, w.tB, w.tQ, w.tQ + kD, w.tQ + 2 * kD, Q));
   MAGPO_TRY(dense_bwd(s, R, kD, Q, w.kqv, kD, w.tQ, Q, pt.qkvgT, p.qkvg, Q, g.qkvg, Q, nullptr, w.tA, kD, 0));  // tA = d(kqv)
   MAGPO_TRY(act_rms_bwd(s, R, w.z0, nullptr, p.ln, ROW_GELU, w.tD, w.tA, nullptr, w.tB, g.ln));   // tB = d(z0)
-  MAGPO_TRY(dense_bwd(s, R, d, kD, w.on, d, w.tB, kD, pt.WobsT, p.Wobs, kD, g.Wobs, kD, nullptr, w.t_d, d, 0));
-  MAGPO_TRY(rms_general_bwd_scale(s, R, d, b.agents_view, w.t_d, g.obs_scale));
+  if (obs_embed_ok(d)) {
+    MAGPO_TRY(obs_embed_bwd(s, R, d, b.agents_view, p.obs_scale, p.Wobs, w.tB, g.Wobs, g.obs_scale));
+  } else {
+    MAGPO_TRY(dense_bwd(s, R, d, kD, w.on, d, w.tB, kD, pt.WobsT, p.Wobs, kD, g.Wobs, kD, nullptr, w.t_d, d, 0));
+    MAGPO_TRY(rms_general_bwd_scale(s, R, d, b.agents_view, w.t_d, g.obs_scale));
+  }
   return MAGPO_OK;
 }
 

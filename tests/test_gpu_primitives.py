@@ -255,3 +255,48 @@ def test_gemm_tensor_core_tn_weight_grad(dev, M, N, K):
     out = dW.cpu().numpy()
     assert rel_err(out[:, :N], ref) < 3e-6 * max(1.0, (M / 1000) ** 0.5)
     assert (out[:, N:] == init[:, N:]).all()
+
+
+@pytest.mark.parametrize("R,K,N", [(1000, 4, 128), (777, 14, 64), (5000, 16, 128), (33, 1, 64), (3000, 10, 128)])
+def test_thin_k_layers(dev, R, K, N):
+    """thin.cu: Y = relu(X W + b) and (dW, db) = (X^T dY, colsum dY) for a thin input side, against fp64 NumPy."""
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((R, K)).astype(np.float32)
+    W = (rng.standard_normal((K, N)) * 0.5).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    dY = rng.standard_normal((R, N)).astype(np.float32)
+    Xd, Wd, bd, dYd = dt(X, dev), dt(W, dev), dt(b, dev), dt(dY, dev)
+    Y = torch.zeros(R, N, device=dev)
+    s = L.stream_ptr()
+    L.call("magpo_test_thin", s, 0, C.c_int64(R), K, N, L.ptr(Xd), L.ptr(Wd), L.ptr(bd), None, L.ptr(Y), None, None, 2)
+    ref = np.maximum(X.astype(np.float64) @ W + b, 0)
+    assert rel_err(Y.cpu().numpy(), ref) < 2e-6
+    dW = torch.full((K, N), 0.5, device=dev)
+    db = torch.full((N,), -0.25, device=dev)
+    L.call("magpo_test_thin", s, 1, C.c_int64(R), K, N, L.ptr(Xd), None, None, L.ptr(dYd), L.ptr(dW), L.ptr(db), None, 0)
+    assert rel_err(dW.cpu().numpy(), X.astype(np.float64).T @ dY + 0.5) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
+    assert rel_err(db.cpu().numpy(), dY.astype(np.float64).sum(0) - 0.25) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
+
+
+@pytest.mark.parametrize("R,N", [(1000, 10), (777, 5), (5000, 16), (33, 1), (2500, 6)])
+def test_thin_n_layers(dev, R, N):
+    """thin.cu: the action head Y = X W + b (K = 128) and its fused backward (dX masked by X > 0, dW, db)."""
+    K = 128
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((R, K)).astype(np.float32)
+    X[X < -0.5] = 0.0  # relu-like activations with exact zeros
+    W = (rng.standard_normal((K, N)) * 0.3).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    dY = rng.standard_normal((R, N)).astype(np.float32)
+    Xd, Wd, bd, dYd = dt(X, dev), dt(W, dev), dt(b, dev), dt(dY, dev)
+    Y = torch.zeros(R, N, device=dev)
+    s = L.stream_ptr()
+    L.call("magpo_test_thin", s, 2, C.c_int64(R), K, N, L.ptr(Xd), L.ptr(Wd), L.ptr(bd), None, L.ptr(Y), None, None, 0)
+    assert rel_err(Y.cpu().numpy(), X.astype(np.float64) @ W + b) < 2e-6
+    dX = torch.zeros(R, K, device=dev)
+    dW = torch.full((K, N), 0.5, device=dev)
+    db = torch.full((N,), -0.25, device=dev)
+    L.call("magpo_test_thin", s, 3, C.c_int64(R), K, N, L.ptr(Xd), L.ptr(Wd), None, L.ptr(dYd), L.ptr(dX), L.ptr(dW), L.ptr(db), 2)
+    assert rel_err(dX.cpu().numpy(), (dY.astype(np.float64) @ W.T) * (X > 0)) < 2e-6
+    assert rel_err(dW.cpu().numpy(), X.astype(np.float64).T @ dY + 0.5) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
+    assert rel_err(db.cpu().numpy(), dY.astype(np.float64).sum(0) - 0.25) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
