@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 SCENARIO = dict(num_agents=3, num_actions=10, time_limit=100, maxval=30)  # CoordSum 3x10-30 (coordsum/__init__.py:26-35)
 METRIC, UNIT = "end_to_end_training_agent_env_steps_per_sec", "agent-steps/s"
 PROF_CATS = ["gemm_nn", "gemm_tn", "colsum", "rowops", "retention_fwd", "retention_bwd", "gru_pointwise", "loss", "pack",
-             "optim", "env_step", "sample", "gae", "misc"]
+             "optim", "env_step", "sample", "gae", "misc", "gemm_rollout"]
 
 
 def parse():
@@ -247,14 +247,32 @@ def main():
             for v in brk.values():
                 v["share"] = round(v["ms"] / total, 4) if total else 0.0
             out["breakdown_ms_per_step"] = brk
+            # dominant kernel class: the tcgen05 3xTF32 GEMMs Y[M,N] = X[M,K] W (forward and dX; M = token rows, K, N in 64..384).
+            # At 16..64 flop/byte (x3 MMAs per product) they sit on the HBM side of the ridge: the roofline is bandwidth.
             g = brk["gemm_nn"]
+            gbytes = C.c_double()
+            lib.magpo_prof_read_bytes(PROF_CATS.index("gemm_nn"), C.byref(gbytes))
+            hb = peaks.get("hbm_gbs", 6650.0)
+            gbs = gbytes.value / (g["ms"] * 1e-3) / 1e9 if g["ms"] else 0.0
             tf = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            out["roofline"] = {"kernel": "gemm_nn_kernel (fp32 SIMT; all forward and dX GEMMs)", "bound": "tensor", "achieved": tf,
-                               "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                               "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                               if peaks else "fallback 1.4 PFLOP/s sustained",
-                               "note": "share of the profiled step: %.2f; work = 2*M*N*K flops per launch, summed" % g["share"]}
+            traffic = None
+            try:  # DRAM bytes per launch of the same kernel from the committed ncu launch list (profiles/)
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r1_minibatch_launches.json")))
+                k = prof["kernels"]["gemm_tc_kernel"]
+                traffic = k["dram_bytes"] / k["launches"]
+            except Exception:
+                pass
+            out["roofline"] = {"kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32 x3, TMA-fed; all forward and dX GEMMs of both networks)",
+                               "bound": "hbm", "achieved": gbs, "peak": hb, "unit": "GB/s", "frac": gbs / hb, "traffic": traffic,
+                               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                               "launches": g["launch_scopes"],
+                               "algorithmic_bytes_per_launch": gbytes.value / max(1, g["launch_scopes"]),
+                               "avg_launch_ms": g["ms"] / max(1, g["launch_scopes"]),
+                               "tensor_side": {"achieved_tflops_fp32_equivalent": tf, "mma_per_product": 3,
+                                               "peak_bf16_tflops_sustained": peaks.get("bf16_tflops_sustained", 1400.0)},
+                               "note": "share of the profiled step: %.2f; bytes = 4*M*(K+N) per launch (+4*M*N when accumulating), "
+                                       "summed over the update's GEMM launches (M = T*N*A rows) and divided by their summed CUDA-event time; "
+                                       "the rollout's launch-latency-bound small GEMMs (M = U*E*A rows) are the gemm_rollout class" % g["share"]}
             hb = peaks.get("hbm_gbs", 6650.0)
             out["roofline_hbm_kernels"] = {
                 k: {"achieved_GBps": round(brk[k]["work"] / (brk[k]["ms"] * 1e-3) / 1e9, 1) if brk[k]["ms"] else None,

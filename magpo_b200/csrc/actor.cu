@@ -193,11 +193,11 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
   MAGPO_TRY(gemm_tn(s, R, 3 * kH, kH, w.e, kH, dgi, 3 * kH, g.Wi, 3 * kH));
   MAGPO_TRY(colsum(s, R, 3 * kH, dgi, 3 * kH, g.bi));
   MAGPO_TRY(gemm_nn(s, R, kH, 3 * kH, dgi, 3 * kH, wref(pt.WiT, kH, p.Wi, 3 * kH), nullptr, w.dA, kH, 0));  // dA = dL/de (pre-relu mask next)
-  relu_bwd_kernel<<<g256(R * kH), 256, 0, s>>>(R * kH, w.e, w.dA);
-  MAGPO_LAUNCH_OK();
-  if (thin_k_ok(d, kH, kH, w.dA, w.dA, kH)) {
-    MAGPO_TRY(thin_k_bwd(s, R, d, kH, agents_view, d, w.dA, kH, g.pre_w, kH, g.pre_b));
+  if (thin_k_ok(d, kH, kH, w.dA, w.dA, kH)) {  // relu mask of the pre torso applied on the fly
+    MAGPO_TRY(thin_k_bwd(s, R, d, kH, agents_view, d, w.dA, kH, w.e, g.pre_w, kH, g.pre_b));
   } else {
+    relu_bwd_kernel<<<g256(R * kH), 256, 0, s>>>(R * kH, w.e, w.dA);
+    MAGPO_LAUNCH_OK();
     MAGPO_TRY(gemm_tn(s, R, kH, d, agents_view, d, w.dA, kH, g.pre_w, kH));
     MAGPO_TRY(colsum(s, R, kH, w.dA, kH, g.pre_b));
   }

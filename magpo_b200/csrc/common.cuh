@@ -31,12 +31,12 @@ void note_launch();
 // roofline numbers and the per-kernel breakdown. Off by default; zero cost when off.
 enum ProfCat {
   PROF_GEMM_NN = 0, PROF_GEMM_TN, PROF_COLSUM, PROF_ROWOPS, PROF_RET_FWD, PROF_RET_BWD, PROF_GRU, PROF_LOSS, PROF_PACK,
-  PROF_OPTIM, PROF_ENV, PROF_SAMPLE, PROF_GAE, PROF_MISC, PROF_NUM
+  PROF_OPTIM, PROF_ENV, PROF_SAMPLE, PROF_GAE, PROF_MISC, PROF_GEMM_SMALL /* M < 64 Ki rows: the rollout */, PROF_NUM
 };
 struct ProfScope {
   int idx;
   cudaStream_t s;
-  ProfScope(int cat, cudaStream_t s, double work);
+  ProfScope(int cat, cudaStream_t s, double work, double bytes = 0.0);  // bytes: algorithmic HBM bytes when `work` is flops
   ~ProfScope();
 };
 

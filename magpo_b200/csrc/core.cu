@@ -19,11 +19,11 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- profiling
 static bool g_prof_on = false;
-struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+struct ProfRec { cudaEvent_t a, b; int cat; double work, bytes; };
 static std::vector<ProfRec> g_recs;
 static size_t g_used = 0;
 
-ProfScope::ProfScope(int cat, cudaStream_t st, double work) : idx(-1), s(st) {
+ProfScope::ProfScope(int cat, cudaStream_t st, double work, double bytes) : idx(-1), s(st) {
   if (!g_prof_on) return;
   if (g_used == g_recs.size()) {
     ProfRec r;
@@ -33,6 +33,7 @@ ProfScope::ProfScope(int cat, cudaStream_t st, double work) : idx(-1), s(st) {
   idx = (int)g_used++;
   g_recs[idx].cat = cat;
   g_recs[idx].work = work;
+  g_recs[idx].bytes = bytes;
   cudaEventRecord(g_recs[idx].a, s);
 }
 ProfScope::~ProfScope() {
@@ -66,6 +67,15 @@ int magpo_prof_read(int cat, double* ms, double* work, int64_t* count) {
     if (cudaEventElapsedTime(&t, g_recs[i].a, g_recs[i].b) != cudaSuccess) continue;
     *ms += t; *work += g_recs[i].work; *count += 1;
   }
+  return MAGPO_OK;
+}
+// Sum of the algorithmic HBM bytes declared by the recorded scopes of category `cat` (GEMM scopes declare flops as work).
+int magpo_prof_read_bytes(int cat, double* bytes) {
+  using namespace magpo;
+  if (!bytes || cat < 0 || cat >= PROF_NUM) return MAGPO_ERR_ARG;
+  *bytes = 0;
+  for (size_t i = 0; i < g_used; ++i)
+    if (g_recs[i].cat == cat) *bytes += g_recs[i].bytes;
   return MAGPO_OK;
 }
 const char* magpo_version(void) { return "magpo_b200 0.1 (sm_100a)"; }

@@ -198,7 +198,7 @@ int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, Wr
   }
   const float* W = Wr.w;
   const int ldw = Wr.ldw;
-  ProfScope ps(PROF_GEMM_NN, s, 2.0 * (double)M * N * K);
+  ProfScope ps(M < 65536 ? PROF_GEMM_SMALL : PROF_GEMM_NN, s, 2.0 * (double)M * N * K, 4.0 * (double)M * (K + N));
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(N, BN));
   gemm_nn_kernel<<<grid, 256, 0, s>>>((int)M, N, K, X, ldx, W, ldw, bias, Y, ldy, flags);
   MAGPO_LAUNCH_OK();
@@ -217,7 +217,7 @@ int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
             int ldw) {
   if (M <= 0 || N <= 0 || K <= 0) return MAGPO_OK;
   if (tc_tn_supported(M, N, K, X, ldx, dY, ldy, dW, ldw)) return gemm_tc_tn(s, M, N, K, X, ldx, dY, ldy, dW, ldw);
-  ProfScope ps(PROF_GEMM_TN, s, 2.0 * (double)M * N * K);
+  ProfScope ps(PROF_GEMM_TN, s, 2.0 * (double)M * N * K, 4.0 * (double)M * (K + N));
   const int nt = (int)ceil_div(N, 64), kt = (int)ceil_div(K, 64);
   const int64_t rows = slab_rows(M, nt * kt);
   dim3 grid((unsigned)ceil_div(M, rows), nt, kt);

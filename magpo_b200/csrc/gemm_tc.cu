@@ -28,7 +28,8 @@ namespace {
 using tcp::TC_BM;
 constexpr int TC_KC = 32;
 constexpr int TC_CHUNK_BYTES = TC_BM * TC_KC * 4;  // 16 KiB
-constexpr int TC_THREADS = 384;
+constexpr int TC_CONV_THREADS = 256;               // warps 8..15
+constexpr int TC_THREADS = 256 + TC_CONV_THREADS;
 constexpr int TC_MAX_STAGES = 6;
 constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
 
@@ -66,7 +67,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_raw[i], 1);
-      mbar_init(&full_conv[i], 128);
+      mbar_init(&full_conv[i], TC_CONV_THREADS);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -182,26 +183,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
     if (et == 0) bulk_wait_all();
   } else if (warp >= 8) {
-    // ===================== converters: fp32 -> (tf32 hi, tf32 lo) =====================
-    const int ct = threadIdx.x - 256;  // 0..127
+    // ===================== converters: lo = x - tf32_trunc(x) =====================
+    // The landed fp32 chunk is itself the hi operand: kind::tf32 reads the top 19 bits of each word, i.e. truncates. Only the
+    // residual is written (exact in fp32; the tensor core truncates it to TF32 in turn: relative error <= 2^-20).
+    const int ct = threadIdx.x - 256;  // 0..TC_CONV_THREADS-1
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_row_tiles; tile += gridDim.x) {
       for (int c = 0; c < p.kchunks; ++c, ++it) {
         const int s = it % p.stages;
         mbar_wait(&full_raw[s], (it / p.stages) & 1);
-        float4* hi = reinterpret_cast<float4*>(sA + (size_t)s * 2 * TC_CHUNK_BYTES);
-        float4* lo = hi + TC_CHUNK_BYTES / 16;
+        const float4* hi = reinterpret_cast<const float4*>(sA + (size_t)s * 2 * TC_CHUNK_BYTES);
+        float4* lo = reinterpret_cast<float4*>(sA + (size_t)s * 2 * TC_CHUNK_BYTES + TC_CHUNK_BYTES);
 #pragma unroll
-        for (int i = 0; i < TC_CHUNK_BYTES / 16 / 128; ++i) {
-          const int idx = ct + i * 128;
-          const float4 x = hi[idx];
-          float4 h, l;
-          split_tf32(x.x, h.x, l.x);
-          split_tf32(x.y, h.y, l.y);
-          split_tf32(x.z, h.z, l.z);
-          split_tf32(x.w, h.w, l.w);
-          hi[idx] = h;
-          lo[idx] = l;
+        for (int i = 0; i < TC_CHUNK_BYTES / 16 / TC_CONV_THREADS; ++i) {
+          const int idx = ct + i * TC_CONV_THREADS;
+          lo[idx] = tf32_residual4(hi[idx]);
         }
         fence_proxy_async();
         mbar_arrive(&full_conv[s]);
@@ -264,7 +260,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_raw[i], 1);
-      mbar_init(&full_conv[i], 128);
+      mbar_init(&full_conv[i], TC_CONV_THREADS);
       mbar_init(&empty[i], 1);
     }
     mbar_init(tmem_full, 1);
@@ -346,23 +342,15 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       if (et == 0) bulk_wait_all();
     } else if (warp >= 8) {
+      // converters: the landed chunks are the hi operands as they are (the tensor core truncates to TF32); write the residuals
       const int ct = threadIdx.x - 256;
       const int nvec = raw_bytes / 16;
       for (int it = 0; it < nchunks; ++it) {
         const int s = it % p.stages;
         mbar_wait(&full_raw[s], (it / p.stages) & 1);
-        float4* hi = reinterpret_cast<float4*>(sStage + (size_t)s * 2 * raw_bytes);
-        float4* lo = hi + nvec;
-        for (int idx = ct; idx < nvec; idx += 128) {
-          const float4 x = hi[idx];
-          float4 h, l;
-          split_tf32(x.x, h.x, l.x);
-          split_tf32(x.y, h.y, l.y);
-          split_tf32(x.z, h.z, l.z);
-          split_tf32(x.w, h.w, l.w);
-          hi[idx] = h;
-          lo[idx] = l;
-        }
+        const float4* hi = reinterpret_cast<const float4*>(sStage + (size_t)s * 2 * raw_bytes);
+        float4* lo = reinterpret_cast<float4*>(sStage + (size_t)s * 2 * raw_bytes + raw_bytes);
+        for (int idx = ct; idx < nvec; idx += TC_CONV_THREADS) lo[idx] = tf32_residual4(hi[idx]);
         fence_proxy_async();
         mbar_arrive(&full_conv[s]);
       }
@@ -520,7 +508,7 @@ int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
   }
   const int n_tiles = N / p.BN;
   dim3 grid((unsigned)std::max(1, std::min(p.num_row_tiles, kNumSMs / n_tiles)), (unsigned)n_tiles);
-  ProfScope ps(PROF_GEMM_NN, s, 2.0 * (double)M * N * K);
+  ProfScope ps(M < 65536 ? PROF_GEMM_SMALL : PROF_GEMM_NN, s, 2.0 * (double)M * N * K, 4.0 * (double)M * (K + N + ((flags & GEMM_ACCUMULATE) ? N : 0)));
   gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmX, tmBh, tmBl, tmY, p);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
@@ -576,7 +564,7 @@ int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx,
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     attr = true;
   }
-  ProfScope ps(PROF_GEMM_TN, s, 2.0 * (double)M * N * K);
+  ProfScope ps(PROF_GEMM_TN, s, 2.0 * (double)M * N * K, 4.0 * (double)M * (K + N));
   gemm_tc_tn_kernel<<<dim3((unsigned)gx, (unsigned)n_tiles), TC_THREADS, smem, s>>>(tmX, tmDY, tmDW, p);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;

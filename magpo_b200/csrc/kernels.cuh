@@ -54,8 +54,8 @@ bool thin_n_ok(int K, int N, const float* X, int ldx);
 bool obs_embed_ok(int d);
 int thin_k_fwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* W, int ldw, const float* bias,
                float* Y, int ldy, int relu);
-int thin_k_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, float* dW, int lddw,
-               float* db);
+int thin_k_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, const float* relu_out,
+               float* dW, int lddw, float* db);
 int thin_n_fwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* W, int ldw, const float* bias,
                float* Y, int ldy);
 int thin_n_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, const float* W, int ldw,

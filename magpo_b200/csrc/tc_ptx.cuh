@@ -107,5 +107,11 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
+// x - trunc_tf32(x): the part of x the tensor core drops when it reads an fp32 word as TF32 (exact in fp32)
+__device__ __forceinline__ float tf32_residual(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 tf32_residual4(float4 x) {
+  return make_float4(tf32_residual(x.x), tf32_residual(x.y), tf32_residual(x.z), tf32_residual(x.w));
+}
+
 }  // namespace tcp
 }  // namespace magpo

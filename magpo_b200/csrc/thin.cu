@@ -4,7 +4,7 @@
 // weights in registers / shared memory, parameter gradients accumulated in registers and flushed once per CTA), with the
 // neighbouring element-wise work fused in:
 //   thin_k_fwd      Y[R,N]   = act(X[R,K] W + b)                       K <= 16, N in {64,128}   (learner pre-torso, torsos.py:36-47)
-//   thin_k_bwd      dW += X^T dY, db += colsum(dY)                     same shapes (X is data: no dX)
+//   thin_k_bwd      dW += X^T dY, db += colsum(dY), dY optionally masked by the layer's relu output   (X is data: no dX)
 //   thin_n_fwd      Y[R,N]   = X[R,128] W + b                          N <= 16                  (DiscreteActionHead, heads.py:32-63)
 //   thin_n_bwd      dX = (dY W^T) * [X > 0], dW += X^T dY, db += colsum(dY)   (head backward fused with the relu of the post torso)
 //   obs_embed_fwd   on = RMSNorm_d(obs); z0 = on Wobs; xin = RMSNorm(gelu(z0)); kqv = xin + PE    (sable_network.py:93-101,121-137)
@@ -75,7 +75,7 @@ thin_k_fwd_kernel(int64_t R, int K, const float* __restrict__ X, int ldx, const 
 template <int NQ, int KMAX>
 __global__ void __launch_bounds__(256)
 thin_k_bwd_kernel(int64_t R, int K, const float* __restrict__ X, int ldx, const float* __restrict__ dY, int lddy,
-                  float* __restrict__ dW, int lddw, float* __restrict__ db) {
+                  const float* __restrict__ relu_out, float* __restrict__ dW, int lddw, float* __restrict__ db) {
   constexpr int ROWS = 256 / NQ;
   constexpr int N = 4 * NQ;
   constexpr int UN = KMAX <= 4 ? 4 : (KMAX <= 8 ? 2 : 1);
@@ -94,6 +94,13 @@ thin_k_bwd_kernel(int64_t R, int K, const float* __restrict__ X, int ldx, const 
       const int64_t row = row0 + u * stride;
       const bool ok = row < R;
       d[u] = ok ? *reinterpret_cast<const float4*>(dY + row * lddy + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (relu_out && ok) {  // dY is the gradient w.r.t. relu(X W + b): mask it with the layer's saved output
+        const float4 o = *reinterpret_cast<const float4*>(relu_out + row * lddy + 4 * c);
+        if (!(o.x > 0.f)) d[u].x = 0.f;
+        if (!(o.y > 0.f)) d[u].y = 0.f;
+        if (!(o.z > 0.f)) d[u].z = 0.f;
+        if (!(o.w > 0.f)) d[u].w = 0.f;
+      }
       load_thin_row<KMAX>(x[u], X, row, ldx, K, ok);
     }
 #pragma unroll
@@ -373,13 +380,13 @@ int thin_k_fwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx,
   return MAGPO_OK;
 }
 
-int thin_k_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, float* dW, int lddw,
-               float* db) {
+int thin_k_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, const float* relu_out,
+               float* dW, int lddw, float* db) {
   if (R <= 0) return MAGPO_OK;
   if (!thin_k_ok(K, N, 4, dY, dY, lddy)) return MAGPO_ERR_UNSUPPORTED;
   ProfScope ps(PROF_ROWOPS, s, 4.0 * R * (K + N));
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(R, 64), (int64_t)kNumSMs * 4));
-#define THIN_K_BWD(NQ, KM) thin_k_bwd_kernel<NQ, KM><<<grid, 256, 0, s>>>(R, K, X, ldx, dY, lddy, dW, lddw, db)
+#define THIN_K_BWD(NQ, KM) thin_k_bwd_kernel<NQ, KM><<<grid, 256, 0, s>>>(R, K, X, ldx, dY, lddy, relu_out, dW, lddw, db)
   if (N == kH) { if (K <= 4) THIN_K_BWD(32, 4); else if (K <= 8) THIN_K_BWD(32, 8); else THIN_K_BWD(32, 16); }
   else { if (K <= 4) THIN_K_BWD(16, 4); else if (K <= 8) THIN_K_BWD(16, 8); else THIN_K_BWD(16, 16); }
 #undef THIN_K_BWD
@@ -448,7 +455,7 @@ extern "C" int magpo_test_thin(magpo_stream_t s_, int kind, int64_t R, int K, in
   cudaStream_t s = as_stream(s_);
   switch (kind) {
     case 0: return thin_k_fwd(s, R, K, N, X, K, W, N, bias, out0, N, flags & 2);
-    case 1: return thin_k_bwd(s, R, K, N, X, K, dY, N, out0, N, out1);
+    case 1: return thin_k_bwd(s, R, K, N, X, K, dY, N, (flags & 2) ? W : nullptr, out0, N, out1);
     case 2: return thin_n_fwd(s, R, K, N, X, K, W, N, bias, out0, N);
     case 3: return thin_n_bwd(s, R, K, N, X, K, dY, N, W, N, flags & 2, out0, K, out1, N, out2);
     default: return MAGPO_ERR_ARG;

@@ -78,6 +78,36 @@ pack_rows_kernel(int T, int B, int A, int d, int a, int n_env, MagpoTrajectory t
   }
 }
 
+// Same gather with one thread per output row, for narrow observations (d <= 16): all 32 lanes issue the per-row scalars and
+// the 4d-byte observation, so consecutive rows (the agents of one env, then the next env of the minibatch) coalesce.
+__global__ void __launch_bounds__(256)
+pack_rows_narrow_kernel(int T, int B, int A, int d, int a, int n_env, MagpoTrajectory tr, const float* __restrict__ adv,
+                        const float* __restrict__ tgt, const int32_t* __restrict__ env_index,
+                        const int32_t* __restrict__ agent_perm, float* __restrict__ o_view, uint8_t* __restrict__ o_mask,
+                        int32_t* __restrict__ o_step, uint8_t* __restrict__ o_done, int32_t* __restrict__ o_action,
+                        float* __restrict__ o_value, float* __restrict__ o_logp, float* __restrict__ o_adv,
+                        float* __restrict__ o_tgt) {
+  const int64_t R = (int64_t)T * n_env * A;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < R; row += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(row % A);
+    const int n = (int)((row / A) % n_env);
+    const int t = (int)(row / ((int64_t)A * n_env));
+    const int b = __ldg(env_index + n), ai = __ldg(agent_perm + i);
+    const int64_t src = ((int64_t)t * B + b) * A + ai;
+    const int32_t st = tr.step_count[src], ac = tr.action[src];
+    const float va = tr.value[src], lp = tr.log_prob[src], ad = adv[src], tg = tgt[src];
+    if ((d & 3) == 0) {
+      for (int c = 0; c < d; c += 4)
+        *reinterpret_cast<float4*>(o_view + row * d + c) = *reinterpret_cast<const float4*>(tr.agents_view + src * d + c);
+    } else {
+      for (int c = 0; c < d; ++c) o_view[row * d + c] = tr.agents_view[src * d + c];
+    }
+    for (int c = 0; c < a; ++c) o_mask[row * a + c] = tr.action_mask[src * a + c];
+    o_step[row] = st; o_action[row] = ac; o_value[row] = va; o_logp[row] = lp; o_adv[row] = ad; o_tgt[row] = tg;
+    if (i == 0) o_done[(int64_t)t * n_env + n] = tr.done[(int64_t)t * B + b];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pack_hidden_kernel(int A, int n_env, const float* __restrict__ policy_h0, const float* __restrict__ h_enc,
                    const float* __restrict__ h_self, const float* __restrict__ h_cross,
@@ -205,7 +235,8 @@ int magpo_pack_minibatch(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoS
   const int A = net->n_agents, T = sys->rollout_length, B = sys->update_batch_size * sys->num_envs;
   const int64_t R = (int64_t)T * n_env * A;
   ProfScope ps(PROF_PACK, s, 2.0 * (double)R * (4.0 * net->obs_dim + net->action_dim + 24.0) + 2.0 * n_env * (3 * 16384.0 + 512.0 * A));
-  pack_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(R, 8), (int64_t)kNumSMs * 16), 256, 0, s>>>(
+  const bool narrow = net->obs_dim <= 16;
+  (narrow ? pack_rows_narrow_kernel : pack_rows_kernel)<<<(unsigned)std::min<int64_t>(ceil_div(R, narrow ? 256 : 8), (int64_t)kNumSMs * 16), 256, 0, s>>>(
       T, B, A, net->obs_dim, net->action_dim, n_env, traj, advantages, targets, env_index, agent_perm,
       const_cast<float*>(out.agents_view), const_cast<uint8_t*>(out.action_mask), const_cast<int32_t*>(out.step_count),
       const_cast<uint8_t*>(out.done), const_cast<int32_t*>(out.action), const_cast<float*>(out.value),

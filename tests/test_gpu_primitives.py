@@ -276,6 +276,13 @@ def test_thin_k_layers(dev, R, K, N):
     L.call("magpo_test_thin", s, 1, C.c_int64(R), K, N, L.ptr(Xd), None, None, L.ptr(dYd), L.ptr(dW), L.ptr(db), None, 0)
     assert rel_err(dW.cpu().numpy(), X.astype(np.float64).T @ dY + 0.5) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
     assert rel_err(db.cpu().numpy(), dY.astype(np.float64).sum(0) - 0.25) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
+    # with the relu mask of the layer's own output (Y from above) applied to dY on the fly
+    dW.fill_(0.0)
+    db.fill_(0.0)
+    L.call("magpo_test_thin", s, 1, C.c_int64(R), K, N, L.ptr(Xd), L.ptr(Y), None, L.ptr(dYd), L.ptr(dW), L.ptr(db), None, 2)
+    dYm = dY.astype(np.float64) * (ref > 0)
+    assert rel_err(dW.cpu().numpy(), X.astype(np.float64).T @ dYm) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
+    assert rel_err(db.cpu().numpy(), dYm.sum(0)) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
 
 
 @pytest.mark.parametrize("R,N", [(1000, 10), (777, 5), (5000, 16), (33, 1), (2500, 6)])

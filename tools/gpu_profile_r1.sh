@@ -1,17 +1,25 @@
 #!/bin/bash
-# Round-1 GPU evidence run: parity tests, the bench line, the ncu launch list and --set full captures of the top kernels.
+# Round-1 GPU evidence run: parity tests, the bench line, ncu launch lists (time + DRAM bytes per launch) of one update
+# minibatch and of a 4-step rollout at the bench size, and --set full captures of the top kernels.
+# Usage (from the repo root, on the GPU box): bash tools/gpu_profile_r1.sh <tag>
 set -u
+TAG=${1:-r1}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider 2>&1 | tail -4
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench6.json 2> gpurun_out/bench6.err
-tail -c 600 gpurun_out/bench6.err
-Q="bench.py --quick --steps 1 --rollout-length 32 --no-cpu-baseline --no-profile"
-python $Q > gpurun_out/plain_r1c.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file gpurun_out/launches_r1c.csv python $Q > gpurun_out/ncu_r1c.log 2>&1
-wc -l gpurun_out/launches_r1c.csv
-for spec in "gemm_tc_kernel:2200" "gemm_tc_tn_kernel:20" "retention_chunk_fwd_kernel:2" "retention_chunk_bwd_kernel:2" "act_rms_fwd_kernel:1500" "gru_gate_bwd_kernel:40"; do
+python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+tail -c 300 gpurun_out/bench_$TAG.err
+M="--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv"
+python tools/profile_update.py > gpurun_out/pu_plain.log 2>&1 && \
+ncu $M --log-file gpurun_out/launches_${TAG}_minibatch.csv python tools/profile_update.py > gpurun_out/pu_ncu.log 2>&1
+python tools/profile_update.py --rollout-steps 4 > gpurun_out/pr_plain.log 2>&1 && \
+ncu $M --log-file gpurun_out/launches_${TAG}_rollout4.csv python tools/profile_update.py --rollout-steps 4 > gpurun_out/pr_ncu.log 2>&1
+for spec in "gemm_tc_kernel:12" "gemm_tc_tn_kernel:3" "retention_chunk_bwd_kernel:0" "retention_chunk_fwd_kernel:1" "gru_scan_bwd_kernel:0" "gru_scan_fwd_kernel:0" "act_rms_bwd_kernel:1"; do
   k=${spec%%:*}; s=${spec##*:}
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$k" -s $s -c 2 -f -o gpurun_out/full_r1c_$k python $Q > gpurun_out/ncu_full_$k.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$k" -s $s -c 1 -f \
+    -o gpurun_out/full_${TAG}_$k python tools/profile_update.py > gpurun_out/ncu_full_$k.log 2>&1
   tail -1 gpurun_out/ncu_full_$k.log
 done
-ls -la gpurun_out/*.ncu-rep
+timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"retention_fwd_kernel" -s 2 -c 1 -f \
+  -o gpurun_out/full_${TAG}_retention_fwd_kernel python tools/profile_update.py --rollout-steps 4 > gpurun_out/ncu_full_retention_fwd.log 2>&1
+tail -1 gpurun_out/ncu_full_retention_fwd.log
+ls -la gpurun_out/full_${TAG}_*.ncu-rep

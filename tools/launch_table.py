@@ -31,6 +31,12 @@ for k in per.values():
     a[2] += k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0)
 tot = sum(a[1] for a in agg.values())
 md = "--md" in sys.argv
+if "--json" in sys.argv:
+    import json
+    out = sys.argv[sys.argv.index("--json") + 1]
+    json.dump({"source": path, "total_ms": tot / 1e6,
+               "kernels": {n.split("<")[0] if n.startswith("gemm") else n: {"launches": a[0], "ms": a[1] / 1e6, "dram_bytes": a[2]}
+                           for n, a in agg.items()}}, open(out, "w"), indent=1)
 print(f"total {tot / 1e6:.3f} ms over {sum(a[0] for a in agg.values())} launches")
 if md:
     print("| kernel | launches | ms | share | DRAM GB | GB/s |\n|---|---|---|---|---|---|")
