@@ -105,9 +105,10 @@ def test_update_step_matches_oracle(dev, chunk):
 
 
 def test_second_rollout_carries_state(dev):
-    """Two consecutive update steps: the carried timestep / hidden states / env state keep matching the oracle."""
+    """Three consecutive update steps (eager rollout, CUDA-graph capture + replay, replay): the carried timestep / hidden
+    states / env state keep matching the oracle."""
     spec, ncfg, osys, state, lrn = build(dev, E=4, U=1, T=110, P=1, M=1)  # T > time_limit: crosses an auto-reset
-    for it in range(2):
+    for it in range(3):
         rec = {}
         olr.update_step(state, spec, ncfg, osys, record=rec)
         lrn.update_step()
