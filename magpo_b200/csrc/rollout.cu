@@ -21,7 +21,15 @@ int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
                           float kappa, const float* pe, const SableActs& w, float* logits, float* Hs_self,
                           float* Hs_cross, float* Hself_out, float* Hcross_out);
 
+// sable_step.cu: the whole get_actions of a step as one kernel (A <= 4, obs_dim <= 16)
+bool sable_step_supported(int A, int d, int a);
+int sable_step(cudaStream_t st, const MagpoNetCfg* net, int B, int gumbel_rows, const GuiderP& p, float kappa, const float* agents_view,
+               const uint8_t* action_mask, const int32_t* step_count, const uint8_t* prev_done, const uint32_t* sample_keys,
+               const float* pe, MagpoSableHState hs, bool dry, int32_t* action, float* log_prob, float* value, float* masked_logits);
+
 namespace {
+
+bool g_force_unfused = false;  // tests / tools: A/B the fused step kernel against the per-layer launch sequence
 
 // keys: [T+1][A][2] sample keys; key advanced in place by T+1 splits.
 __global__ void rollout_keys_kernel(uint32_t* __restrict__ key, int steps, int A, uint32_t* __restrict__ sample_keys) {
@@ -134,6 +142,9 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
                 const uint8_t* prev_done, const uint32_t* sample_keys, MagpoSableHState hs, bool dry,
                 int32_t* action, float* log_prob, float* value, float* masked_logits, const RolloutWs& w) {
   const int A = net->n_agents, d = net->obs_dim, a = net->action_dim, ms = net->max_step_count;
+  if (!g_force_unfused && sable_step_supported(A, d, a))
+    return sable_step(s, net, B, gumbel_rows, gp, kappa, agents_view, action_mask, step_count, prev_done, sample_keys, w.pe, hs, dry,
+                      action, log_prob, value, masked_logits);
   MAGPO_TRY(sable_encoder_forward(s, gp, gt, 1, B, A, d, ms, agents_view, step_count, prev_done, hs.encoder, kappa, w.pe,
                                   w.sa, value, nullptr, dry ? nullptr : hs.encoder));
   if (!action) return MAGPO_OK;
@@ -167,6 +178,11 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
 using namespace magpo;
 
 extern "C" {
+
+int magpo_debug_force_unfused_rollout(int on) {
+  g_force_unfused = on != 0;
+  return MAGPO_OK;
+}
 
 size_t magpo_rollout_workspace_bytes(const MagpoNetCfg* net, int32_t B, int32_t T) {
   if (check_net(net) != MAGPO_OK || B < 0 || T < 0) return 0;

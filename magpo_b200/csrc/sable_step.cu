@@ -1,0 +1,553 @@
+// Fused per-step Sable inference for the rollout: SableNetwork.get_actions (networks/sable_network.py:443-482) for a
+// batch of envs in ONE kernel — recurrent encoder over the A agents (utils/sable/encode.py:58-84, sable_network.py:139-156),
+// the A autoregressive decoder steps (utils/sable/decode.py:111-153, sable_network.py:219-242,321-343), each followed by the
+// distrax gumbel-max sample from the step's threefry key, and the value head. It replaces ~80 short launches per env step.
+//
+// Mapping: the envs of a rollout never interact, and inside one env the decoder is a chain (agent i's input token is agent
+// i-1's sampled action), so one warp runs the whole chain for EPW envs with nothing but warp shuffles between stages:
+//   * a 64-wide activation row lives in one float2 per lane (lane l = columns 2l, 2l+1), the same layout the row kernels use;
+//   * a dense layer y = x W is 64 broadcast-FMA steps: x_k by shuffle, the k-th weight row from shared memory (256 contiguous
+//     bytes per warp, conflict-free). The CTA streams the 5 + 7 A weight matrices of the step (0.4 MB, L2 resident) through two
+//     64 KiB buffers with cp.async, one layer ahead of the arithmetic, so no weight load is ever waited for; EPW envs (x A
+//     tokens in the encoder) share each weight read;
+//   * the 64x64 retention states (3 x 16 KiB per env, the only large HBM stream of the rollout) are read row by row, 256
+//     coalesced bytes per row and warp, 8 rows in flight per env. The decoder states are READ once per agent but WRITTEN once
+//     per step: with H0 the stored state, lam the step's decay and (k_j, v_j) the tokens added so far,
+//         ret_i = q_i (lam H0 + sum_{j<=i} k_j^T v_j) = lam (q_i H0) + sum_{j<=i} (q_i . k_j) v_j,
+//     so agents 0..A-2 only read H0 and the last agent's pass also writes lam H0 + sum_j k_j^T v_j. Per env-step the state
+//     traffic is 32 + 2 (16 A + 16) KiB instead of 32 (1 + 2 A) KiB.
+// All arithmetic is fp32 FMA (no TF32 split on this path). Algorithmic HBM bytes per env-step: state traffic above +
+// A (4 d + a + 4) in + 12 A out.
+#include "kernels.cuh"
+#include "params.cuh"
+#include "prng.cuh"
+
+namespace magpo {
+namespace {
+
+constexpr float kEps = 1e-6f;
+constexpr int EPW = 2;         // envs per warp
+constexpr int SS_WARPS = 14;   // warps per CTA (28 envs; one CTA per SM, the register file is the occupancy limit): 8192 envs = 1.98 waves
+constexpr int SS_THREADS = SS_WARPS * 32;
+constexpr int SS_WBUF = kD * 4 * kD;  // floats of the largest layer [64, 256]
+constexpr uint32_t SS_SMEM = 2 * SS_WBUF * sizeof(float);
+constexpr unsigned kFull = 0xffffffffu;
+
+struct StepArgs {
+  int B, d, a, max_step, gumbel_rows, dry;
+  float kappa;
+  const float* obs;          // [B,A,d]
+  const uint8_t* mask;       // [B,A,a]
+  const int32_t* step;       // [B,A]
+  const uint8_t* prev_done;  // [B] or null
+  const uint32_t* keys;      // [A][2] sample keys of this step
+  const float* pe;           // [max_step+1, 64]
+  float *h_enc, *h_self, *h_cross;  // [B,64,64]
+  int32_t* action;           // [B,A]
+  float *log_prob, *value;   // [B,A]
+  float* masked_logits;      // [B,A,a] or null
+};
+
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float swishf(float x) { return x * sigmoid_precise(x); }
+
+// y[r][j] (+)= x[r] W[:, 64 j + (2l, 2l+1)]   for R rows sharing every weight load; W row-major [64, ldw]
+template <int NB, int R>
+__device__ __forceinline__ void dense(const float* __restrict__ W /*shared*/, int ldw, const float2 (&x)[R], float2 (&y)[R][NB],
+                                      int lane) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) y[r][j] = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int k2 = 0; k2 < 32; ++k2) {
+    float2 w0[NB], w1[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      w0[j] = *reinterpret_cast<const float2*>(W + (2 * k2) * ldw + 64 * j + 2 * lane);
+      w1[j] = *reinterpret_cast<const float2*>(W + (2 * k2 + 1) * ldw + 64 * j + 2 * lane);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float xa = __shfl_sync(kFull, x[r].x, k2), xb = __shfl_sync(kFull, x[r].y, k2);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        y[r][j].x = fmaf(xa, w0[j].x, y[r][j].x); y[r][j].y = fmaf(xa, w0[j].y, y[r][j].y);
+        y[r][j].x = fmaf(xb, w1[j].x, y[r][j].x); y[r][j].y = fmaf(xb, w1[j].y, y[r][j].y);
+      }
+    }
+  }
+}
+template <int R>
+__device__ __forceinline__ void dense1(const float* __restrict__ W, const float2 (&x)[R], float2 (&y)[R], int lane) {
+  float2 t[R][1];
+  dense<1, R>(W, kD, x, t, lane);
+#pragma unroll
+  for (int r = 0; r < R; ++r) y[r] = t[r][0];
+}
+
+// Weight pipeline: every thread copies its 16-byte pieces of the next layer's matrix (global, contiguous) into the idle buffer.
+__device__ __forceinline__ void stage_issue(float* dst /*shared*/, const float* __restrict__ src, int nfloats) {
+  const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+  for (int i = threadIdx.x * 4; i < nfloats; i += SS_THREADS * 4)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i * 4), "l"(src + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// the layer issued last has landed for every thread, and every warp is done with the other buffer
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
+// RMSNorm(p) * scale   (flax nn.RMSNorm, eps 1e-6)
+__device__ __forceinline__ float2 rmsnorm(float2 p, float2 sc) {
+  const float rstd = rsqrtf(warp_sum(p.x * p.x + p.y * p.y) * (1.0f / kD) + kEps);
+  return make_float2(p.x * (rstd * sc.x), p.y * (rstd * sc.y));
+}
+// swish(g) * GroupNorm_1(ret)  (flax fast variance; retention.py:289-295)
+__device__ __forceinline__ float2 gn_gate(float2 g, float2 x, float2 sc, float2 bi) {
+  const float mean = warp_sum(x.x + x.y) * (1.0f / kD);
+  const float m2 = warp_sum(x.x * x.x + x.y * x.y) * (1.0f / kD);
+  const float rstd = rsqrtf(fmaxf(0.0f, m2 - mean * mean) + kEps);
+  return make_float2(swishf(g.x) * ((x.x - mean) * rstd * sc.x + bi.x), swishf(g.y) * ((x.y - mean) * rstd * sc.y + bi.y));
+}
+__device__ __forceinline__ float2 pe_row(const float* __restrict__ pe, int step, int max_step, int lane) {
+  return ldg2(pe + (size_t)min(max(step, 0), max_step) * kD + 2 * lane);
+}
+// component r of a row held as float2 per lane
+__device__ __forceinline__ float row_elem(float2 v, int r) { return __shfl_sync(kFull, (r & 1) ? v.y : v.x, r >> 1); }
+
+// pull one 16 KiB state towards L2 ahead of its row-by-row read (one bulk prefetch instruction)
+__device__ __forceinline__ void prefetch_state(const float* H) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(H), "r"((uint32_t)(kD * kD * sizeof(float))) : "memory");
+}
+
+// state rows r0..r0+7 of env state H (evict-first: streamed once)
+__device__ __forceinline__ void load_rows(float2 (&h)[8], const float* __restrict__ H, int r0, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = __ldcs(reinterpret_cast<const float2*>(H + (size_t)(r0 + j) * kD + 2 * lane));
+}
+
+// Decoder retention of agent i (token-causal): out_e = lam (q_e H0_e) + sum_{j<=i} (q_e . k_ej) v_ej, H0 read-only; the last
+// agent's pass also writes lam H0 + sum_j k_j^T v_j. Both envs' rows are in flight together.
+template <int A>
+__device__ __forceinline__ void decoder_retention(int i, float* __restrict__ Hall, const int (&b)[EPW], const bool (&live)[EPW],
+                                                  const float (&lam)[EPW], const float2 (&q)[EPW], const float2 (&k)[EPW][A],
+                                                  const float2 (&v)[EPW][A], float2 (&out)[EPW], int lane) {
+  float2 acc[EPW];
+#pragma unroll
+  for (int e = 0; e < EPW; ++e) acc[e] = make_float2(0.f, 0.f);
+  for (int r0 = 0; r0 < kD; r0 += 8) {
+    float2 h[EPW][8];
+#pragma unroll
+    for (int e = 0; e < EPW; ++e) load_rows(h[e], Hall + (size_t)b[e] * kD * kD, r0, lane);
+#pragma unroll
+    for (int e = 0; e < EPW; ++e) {
+      float* H = Hall + (size_t)b[e] * kD * kD;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float qr = row_elem(q[e], r0 + j);
+        acc[e].x = fmaf(qr, h[e][j].x, acc[e].x);
+        acc[e].y = fmaf(qr, h[e][j].y, acc[e].y);
+        if (i == A - 1 && live[e]) {
+          float2 hn = make_float2(h[e][j].x * lam[e], h[e][j].y * lam[e]);
+#pragma unroll
+          for (int jj = 0; jj < A; ++jj) {
+            const float kr = row_elem(k[e][jj], r0 + j);
+            hn.x = fmaf(kr, v[e][jj].x, hn.x);
+            hn.y = fmaf(kr, v[e][jj].y, hn.y);
+          }
+          __stcs(reinterpret_cast<float2*>(H + (size_t)(r0 + j) * kD + 2 * lane), hn);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPW; ++e) {
+    acc[e].x *= lam[e]; acc[e].y *= lam[e];
+#pragma unroll
+    for (int jj = 0; jj < A; ++jj)
+      if (jj <= i) {
+        const float qk = warp_sum(q[e].x * k[e][jj].x + q[e].y * k[e][jj].y);
+        acc[e].x = fmaf(qk, v[e][jj].x, acc[e].x);
+        acc[e].y = fmaf(qk, v[e][jj].y, acc[e].y);
+      }
+    out[e] = acc[e];
+  }
+}
+
+template <int A, int KMAX>
+// 14 warps are allocated as 16 (register allocation granularity): 128 registers per thread is the ceiling
+__global__ void __launch_bounds__(512, 1)
+sable_step_kernel(const GuiderP p, const StepArgs s) {
+  extern __shared__ __align__(16) float wbuf[];  // two weight buffers of SS_WBUF floats
+  float* const w_a = wbuf;
+  float* const w_b = wbuf + SS_WBUF;
+  const int lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * SS_WARPS + (threadIdx.x >> 5);  // warps past the batch run dead (no stores)
+  stage_issue(w_a, p.qkvg, kD * 4 * kD);
+  float* cur_w = w_a;  // buffer of the layer about to be computed
+  float* nxt_w = w_b;  // buffer the following layer is prefetched into
+  const bool full = !s.dry && s.action;
+// the current layer's weights are complete and the other buffer is free: start the next layer's copy, then compute
+#define LAYER(next_ptr, next_n)                               \
+  stage_wait();                                               \
+  if ((next_ptr) != nullptr) stage_issue(nxt_w, (next_ptr), (next_n));
+#define LAYER_DONE()                                          \
+  { float* t_ = cur_w; cur_w = nxt_w; nxt_w = t_; }
+  int b[EPW];
+  bool live[EPW];
+  float lam[EPW];
+#pragma unroll
+  for (int e = 0; e < EPW; ++e) {
+    const int64_t be = pair * EPW + e;
+    live[e] = be < s.B;
+    b[e] = live[e] ? (int)be : s.B - 1;  // a dead slot recomputes the last env and writes nothing
+    lam[e] = (s.prev_done && s.prev_done[b[e]]) ? 0.0f : s.kappa;
+  }
+  constexpr int RE = EPW * A;  // encoder rows of this warp: (env, agent)
+  if (lane < EPW) {
+    const int bl = lane == 0 ? b[0] : b[EPW - 1];
+    prefetch_state(s.h_enc + (size_t)bl * kD * kD);
+  }
+
+  // ------------------------------------------------------------------ encoder
+  float2 xin[RE], cur[RE];
+  int stp[RE];
+  {
+    float2 w[KMAX];
+    float sc[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      w[k] = k < s.d ? ldg2(p.Wobs + (size_t)k * kD + 2 * lane) : make_float2(0.f, 0.f);
+      sc[k] = k < s.d ? __ldg(p.obs_scale + k) : 0.f;
+    }
+    const float2 ln = ldg2(p.ln + 2 * lane);
+    const float inv_d = 1.0f / (float)s.d;
+#pragma unroll
+    for (int r = 0; r < RE; ++r) {
+      const int64_t row = (int64_t)b[r / A] * A + (r % A);
+      float x[KMAX], ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        x[k] = k < s.d ? __ldg(s.obs + row * s.d + k) : 0.f;
+        ss = fmaf(x[k], x[k], ss);
+      }
+      const float rstd0 = rsqrtf(ss * inv_d + kEps);
+      float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const float o = x[k] * (rstd0 * sc[k]);
+        z.x = fmaf(o, w[k].x, z.x);
+        z.y = fmaf(o, w[k].y, z.y);
+      }
+      xin[r] = rmsnorm(make_float2(gelu_tanh(z.x), gelu_tanh(z.y)), ln);
+      stp[r] = __ldg(s.step + row);
+      cur[r] = f2add(xin[r], pe_row(s.pe, stp[r], s.max_step, lane));
+    }
+  }
+  float2 ret[RE], gate[RE];
+  {
+    float2 qkvg[RE][4];
+    LAYER(p.wo, kD * kD)
+    dense<4, RE>(cur_w, 4 * kD, cur, qkvg, lane);
+    LAYER_DONE()
+    // retention: H <- lam H + sum_i k_i^T v_i ; ret_i = q_i H   (all A tokens are added before any output)
+#pragma unroll
+    for (int r = 0; r < RE; ++r) ret[r] = make_float2(0.f, 0.f);
+    for (int r0 = 0; r0 < kD; r0 += 8) {
+      float2 h[EPW][8];
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) load_rows(h[e], s.h_enc + (size_t)b[e] * kD * kD, r0, lane);
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) {
+        float* H = s.h_enc + (size_t)b[e] * kD * kD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = r0 + j;
+          float2 hh = make_float2(h[e][j].x * lam[e], h[e][j].y * lam[e]);
+#pragma unroll
+          for (int i = 0; i < A; ++i) {
+            const float kr = row_elem(qkvg[e * A + i][1], r);
+            hh.x = fmaf(kr, qkvg[e * A + i][2].x, hh.x);
+            hh.y = fmaf(kr, qkvg[e * A + i][2].y, hh.y);
+          }
+          if (!s.dry && live[e]) __stcs(reinterpret_cast<float2*>(H + (size_t)r * kD + 2 * lane), hh);
+#pragma unroll
+          for (int i = 0; i < A; ++i) {
+            const float qr = row_elem(qkvg[e * A + i][0], r);
+            ret[e * A + i].x = fmaf(qr, hh.x, ret[e * A + i].x);
+            ret[e * A + i].y = fmaf(qr, hh.y, ret[e * A + i].y);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RE; ++r) gate[r] = qkvg[r][3];
+    if (full && lane < EPW) {  // the decoder states are needed ~10 layers from now
+      const int bl = lane == 0 ? b[0] : b[EPW - 1];
+      prefetch_state(s.h_self + (size_t)bl * kD * kD);
+      prefetch_state(s.h_cross + (size_t)bl * kD * kD);
+    }
+  }
+  float2 x[RE], xpe[RE];
+  {
+    const float2 gs = ldg2(p.gn_s + 2 * lane), gb = ldg2(p.gn_b + 2 * lane);
+#pragma unroll
+    for (int r = 0; r < RE; ++r) cur[r] = gn_gate(gate[r], ret[r], gs, gb);
+    float2 o[RE];
+    LAYER(p.ffn_gl, kD * 2 * kD)
+    dense1<RE>(cur_w, cur, o, lane);
+    LAYER_DONE()
+    const float2 ln1 = ldg2(p.ln1 + 2 * lane);
+#pragma unroll
+    for (int r = 0; r < RE; ++r) xin[r] = rmsnorm(f2add(o[r], xin[r]), ln1);  // x1
+    float2 gl[RE][2];
+    LAYER(p.ffn_out, kD * kD)
+    dense<2, RE>(cur_w, 2 * kD, xin, gl, lane);
+    LAYER_DONE()
+#pragma unroll
+    for (int r = 0; r < RE; ++r) cur[r] = make_float2(swishf(gl[r][0].x) * gl[r][1].x, swishf(gl[r][0].y) * gl[r][1].y);
+    LAYER(p.h0_w, kD * kD)
+    dense1<RE>(cur_w, cur, o, lane);
+    LAYER_DONE()
+    const float2 ln2 = ldg2(p.ln2 + 2 * lane);
+#pragma unroll
+    for (int r = 0; r < RE; ++r) {
+      x[r] = rmsnorm(f2add(o[r], xin[r]), ln2);
+      xpe[r] = f2add(x[r], pe_row(s.pe, stp[r], s.max_step, lane));
+    }
+    // value head: Dense(64) -> gelu -> RMSNorm -> Dense(1)
+    LAYER(full ? p.qkvg1 : nullptr, kD * 4 * kD)
+    dense1<RE>(cur_w, x, o, lane);
+    LAYER_DONE()
+    const float2 hb = ldg2(p.h0_b + 2 * lane), hs = ldg2(p.h2_s + 2 * lane), hw = ldg2(p.h3_w + 2 * lane);
+    const float hb3 = __ldg(p.h3_b);
+#pragma unroll
+    for (int r = 0; r < RE; ++r) {
+      const float2 hn = rmsnorm(make_float2(gelu_tanh(o[r].x + hb.x), gelu_tanh(o[r].y + hb.y)), hs);
+      const float v = warp_sum(hn.x * hw.x + hn.y * hw.y) + hb3;
+      if (lane == 0 && live[r / A]) s.value[(int64_t)b[r / A] * A + (r % A)] = v;
+    }
+  }
+  if (!full) return;
+
+  // ------------------------------------------------------------------ decoder: A autoregressive steps
+  float2 k1[EPW][A], v1[EPW][A], k2[EPW][A], v2[EPW][A];  // tokens added to the self / cross states so far
+#pragma unroll
+  for (int e = 0; e < EPW; ++e)
+#pragma unroll
+    for (int jj = 0; jj < A; ++jj) k1[e][jj] = v1[e][jj] = k2[e][jj] = v2[e][jj] = make_float2(0.f, 0.f);
+  int prev_act[EPW];
+#pragma unroll
+  for (int e = 0; e < EPW; ++e) prev_act[e] = 0;
+  // a real loop (the body is ~2k instructions: unrolling it A times overflows the instruction cache); the per-agent k/v
+  // history stays in registers through compile-time indices under runtime predicates
+#pragma unroll 1
+  for (int i = 0; i < A; ++i) {
+    float2 xD[EPW], in[EPW];
+    int st[EPW];
+    {
+      const float2 dln = ldg2(p.dln + 2 * lane);
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) {
+        const int tok = i == 0 ? 0 : 1 + prev_act[e];  // start-of-timestep token, else one-hot(previous action)
+        const float2 z = ldg2(p.Wa + (size_t)tok * kD + 2 * lane);
+        xD[e] = rmsnorm(make_float2(gelu_tanh(z.x), gelu_tanh(z.y)), dln);
+        st[e] = 0;
+#pragma unroll
+        for (int jj = 0; jj < A; ++jj)
+          if (jj == i) st[e] = stp[e * A + jj];
+        in[e] = f2add(xD[e], pe_row(s.pe, st[e], s.max_step, lane));
+      }
+    }
+    // ---- self retention
+    float2 r1[EPW], g1[EPW];
+    {
+      float2 qkvg[EPW][4];
+      LAYER(p.wo1, kD * kD)
+      dense<4, EPW>(cur_w, 4 * kD, in, qkvg, lane);
+      LAYER_DONE()
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) {
+#pragma unroll
+        for (int jj = 0; jj < A; ++jj)
+          if (jj == i) { k1[e][jj] = qkvg[e][1]; v1[e][jj] = qkvg[e][2]; }
+        g1[e] = qkvg[e][3];
+      }
+      float2 q1[EPW];
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) q1[e] = qkvg[e][0];
+      decoder_retention<A>(i, s.h_self, b, live, lam, q1, k1, v1, r1, lane);
+    }
+    float2 rpe[EPW];
+    {
+      const float2 gs = ldg2(p.gn1_s + 2 * lane), gb = ldg2(p.gn1_b + 2 * lane), dln1 = ldg2(p.dln1 + 2 * lane);
+      float2 t[EPW], o[EPW];
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) t[e] = gn_gate(g1[e], r1[e], gs, gb);
+      LAYER(p.qkvg2, kD * 4 * kD)
+      dense1<EPW>(cur_w, t, o, lane);
+      LAYER_DONE()
+#pragma unroll
+      for (int e = 0; e < EPW; ++e)
+        rpe[e] = f2add(rmsnorm(f2add(o[e], xD[e]), dln1), pe_row(s.pe, st[e], s.max_step, lane));
+    }
+    // ---- cross retention: key = value = r (+PE), query = obs_rep (+PE)
+    float2 yv[EPW];
+    {
+      float2 q2[EPW], qin[EPW], kvg[EPW][3];
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) {
+        qin[e] = xpe[e * A];
+#pragma unroll
+        for (int jj = 1; jj < A; ++jj)
+          if (jj == i) qin[e] = xpe[e * A + jj];
+      }
+      {
+        float2 t[EPW][1];
+        LAYER(p.wo2, kD * kD)
+        dense<1, EPW>(cur_w, 4 * kD, qin, t, lane);
+#pragma unroll
+        for (int e = 0; e < EPW; ++e) q2[e] = t[e][0];
+      }
+      dense<3, EPW>(cur_w + kD, 4 * kD, rpe, kvg, lane);
+      LAYER_DONE()
+      float2 r2[EPW];
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) {
+#pragma unroll
+        for (int jj = 0; jj < A; ++jj)
+          if (jj == i) { k2[e][jj] = kvg[e][0]; v2[e][jj] = kvg[e][1]; }
+      }
+      decoder_retention<A>(i, s.h_cross, b, live, lam, q2, k2, v2, r2, lane);
+      const float2 gs = ldg2(p.gn2_s + 2 * lane), gb = ldg2(p.gn2_b + 2 * lane), dln2 = ldg2(p.dln2 + 2 * lane);
+      float2 t[EPW], o[EPW];
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) t[e] = gn_gate(kvg[e][2], r2[e], gs, gb);
+      LAYER(p.dffn_gl, kD * 2 * kD)
+      dense1<EPW>(cur_w, t, o, lane);
+      LAYER_DONE()
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) {
+        float2 xr = x[e * A];
+#pragma unroll
+        for (int jj = 1; jj < A; ++jj)
+          if (jj == i) xr = x[e * A + jj];
+        yv[e] = rmsnorm(f2add(o[e], xr), dln2);
+      }
+    }
+    // ---- SwiGLU FFN, head, sample
+    {
+      float2 gl[EPW][2], t[EPW], o[EPW];
+      LAYER(p.dffn_out, kD * kD)
+      dense<2, EPW>(cur_w, 2 * kD, yv, gl, lane);
+      LAYER_DONE()
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) t[e] = make_float2(swishf(gl[e][0].x) * gl[e][1].x, swishf(gl[e][0].y) * gl[e][1].y);
+      LAYER(p.dh0_w, kD * kD)
+      dense1<EPW>(cur_w, t, o, lane);
+      LAYER_DONE()
+      const float2 dln3 = ldg2(p.dln3 + 2 * lane);
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) t[e] = rmsnorm(f2add(o[e], yv[e]), dln3);  // xd
+      LAYER(i + 1 < A ? p.qkvg1 : nullptr, kD * 4 * kD)
+      dense1<EPW>(cur_w, t, o, lane);
+      LAYER_DONE()
+      const float2 hb = ldg2(p.dh0_b + 2 * lane), hs = ldg2(p.dh2_s + 2 * lane);
+      float2 hn[EPW];
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) hn[e] = rmsnorm(make_float2(gelu_tanh(o[e].x + hb.x), gelu_tanh(o[e].y + hb.y)), hs);
+      // logits: lane j < a owns action j
+      float lg[EPW];
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) lg[e] = lane < s.a ? __ldg(p.dh3_b + lane) : 0.f;
+      const int jc = lane < s.a ? lane : 0;
+#pragma unroll 4
+      for (int k2i = 0; k2i < 32; ++k2i) {
+        const float wa = __ldg(p.dh3_w + (size_t)(2 * k2i) * s.a + jc), wb = __ldg(p.dh3_w + (size_t)(2 * k2i + 1) * s.a + jc);
+#pragma unroll
+        for (int e = 0; e < EPW; ++e) {
+          lg[e] = fmaf(__shfl_sync(kFull, hn[e].x, k2i), wa, lg[e]);
+          lg[e] = fmaf(__shfl_sync(kFull, hn[e].y, k2i), wb, lg[e]);
+        }
+      }
+      // distrax.Categorical(logits=masked).sample_and_log_prob(seed=sample_key)  (decode.py:135-142): noise shape (1,E,1,a)
+      const uint32_t key0 = __ldg(s.keys + 2 * i), key1 = __ldg(s.keys + 2 * i + 1);
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) {
+        const int64_t row = (int64_t)b[e] * A + i;
+        const bool mine = lane < s.a;
+        const bool legal = mine && s.mask[row * s.a + jc];
+        const float ml = legal ? lg[e] : kF32Min;
+        const float mx = warp_max(mine ? ml : kF32Min);
+        const float se = warp_sum(mine ? expf(ml - mx) : 0.f);
+        const float lp = ml - (mx + logf(se));
+        const uint64_t ctr = (uint64_t)(b[e] % s.gumbel_rows) * (uint64_t)s.a + (uint64_t)jc;
+        float sc = mine ? prng_gumbel_from_bits(prng_bits_i(key0, key1, ctr)) + lp : -INFINITY;
+        int idx = mine ? lane : 0x7fffffff;
+        // argmax, first index on ties (jnp.argmax)
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+          const float os = __shfl_xor_sync(kFull, sc, o2);
+          const int oi = __shfl_xor_sync(kFull, idx, o2);
+          if (os > sc || (os == sc && oi < idx)) { sc = os; idx = oi; }
+        }
+        const float best_lp = __shfl_sync(kFull, lp, idx);
+        prev_act[e] = idx;
+        if (live[e]) {
+          if (lane == 0) { s.action[row] = idx; s.log_prob[row] = best_lp; }
+          if (s.masked_logits && mine) s.masked_logits[row * s.a + lane] = ml;
+        }
+      }
+    }
+  }
+}
+
+template <int A>
+int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
+  const unsigned grid = (unsigned)ceil_div(ceil_div(s.B, EPW), SS_WARPS);
+  static bool attr = false;
+  if (!attr) {
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
+    attr = true;
+  }
+  if (s.d <= 4) sable_step_kernel<A, 4><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
+  else if (s.d <= 8) sable_step_kernel<A, 8><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
+  else sable_step_kernel<A, 16><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+}  // namespace
+
+bool sable_step_supported(int A, int d, int a) { return A >= 1 && A <= 4 && d >= 1 && d <= 16 && a >= 1 && a <= 32; }
+
+// One SableNetwork.get_actions for B envs. action == nullptr (bootstrap): encoder + value only, states untouched.
+int sable_step(cudaStream_t st, const MagpoNetCfg* net, int B, int gumbel_rows, const GuiderP& p, float kappa, const float* agents_view,
+               const uint8_t* action_mask, const int32_t* step_count, const uint8_t* prev_done, const uint32_t* sample_keys,
+               const float* pe, MagpoSableHState hs, bool dry, int32_t* action, float* log_prob, float* value, float* masked_logits) {
+  if (B <= 0) return MAGPO_OK;
+  const int A = net->n_agents;
+  if (!sable_step_supported(A, net->obs_dim, net->action_dim)) return MAGPO_ERR_UNSUPPORTED;
+  StepArgs s;
+  s.B = B; s.d = net->obs_dim; s.a = net->action_dim; s.max_step = net->max_step_count; s.gumbel_rows = gumbel_rows;
+  s.dry = (dry || !action) ? 1 : 0;
+  s.kappa = kappa;
+  s.obs = agents_view; s.mask = action_mask; s.step = step_count; s.prev_done = prev_done; s.keys = sample_keys; s.pe = pe;
+  s.h_enc = hs.encoder; s.h_self = hs.decoder_self; s.h_cross = hs.decoder_cross;
+  s.action = action; s.log_prob = log_prob; s.value = value; s.masked_logits = masked_logits;
+  const double state_bytes = s.dry ? 16384.0 : (32768.0 + 2.0 * (16384.0 * A + 16384.0));
+  ProfScope ps(PROF_SAMPLE, st, (double)B * (state_bytes + A * (4.0 * s.d + s.a + 4.0) + 12.0 * A));
+  switch (A) {
+    case 1: return launch_a<1>(st, p, s);
+    case 2: return launch_a<2>(st, p, s);
+    case 3: return launch_a<3>(st, p, s);
+    default: return launch_a<4>(st, p, s);
+  }
+}
+
+}  // namespace magpo

@@ -13,13 +13,13 @@ python tools/profile_update.py > gpurun_out/pu_plain.log 2>&1 && \
 ncu $M --log-file gpurun_out/launches_${TAG}_minibatch.csv python tools/profile_update.py > gpurun_out/pu_ncu.log 2>&1
 python tools/profile_update.py --rollout-steps 4 > gpurun_out/pr_plain.log 2>&1 && \
 ncu $M --log-file gpurun_out/launches_${TAG}_rollout4.csv python tools/profile_update.py --rollout-steps 4 > gpurun_out/pr_ncu.log 2>&1
-for spec in "gemm_tc_kernel:12" "gemm_tc_tn_kernel:3" "retention_chunk_bwd_kernel:0" "retention_chunk_fwd_kernel:1" "gru_scan_bwd_kernel:0" "gru_scan_fwd_kernel:0" "act_rms_bwd_kernel:1"; do
+for spec in "gemm_tc_kernel:12" "gemm_tc_tn_kernel:3" "retention_chunk_bwd_kernel:0" "retention_chunk_fwd_kernel:1" "gru_scan_bwd_kernel:0" "gru_scan_fwd_kernel:0" "act_rms_bwd_kernel:1" "thin_n_bwd_kernel:0"; do
   k=${spec%%:*}; s=${spec##*:}
   timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$k" -s $s -c 1 -f \
     -o gpurun_out/full_${TAG}_$k python tools/profile_update.py > gpurun_out/ncu_full_$k.log 2>&1
   tail -1 gpurun_out/ncu_full_$k.log
 done
-timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"retention_fwd_kernel" -s 2 -c 1 -f \
-  -o gpurun_out/full_${TAG}_retention_fwd_kernel python tools/profile_update.py --rollout-steps 4 > gpurun_out/ncu_full_retention_fwd.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"sable_step_kernel" -s 1 -c 1 -f \
+  -o gpurun_out/full_${TAG}_sable_step_kernel python tools/profile_update.py --rollout-steps 4 > gpurun_out/ncu_full_retention_fwd.log 2>&1
 tail -1 gpurun_out/ncu_full_retention_fwd.log
 ls -la gpurun_out/full_${TAG}_*.ncu-rep
