@@ -1,0 +1,316 @@
+"""System entry of the B200 path, with the calling convention of `mava/systems/gpo/anakin/rec_magpo.py`:
+
+    learn, actor_network, learner_state = learner_setup(env, (key, actor_net_key, net_key), config)
+    out = learn(learner_state)        # ExperimentOutput(learner_state, episode_metrics, train_metrics)
+
+`learner_setup` follows rec_magpo.py:533-685 (network / optimiser / env-state / key construction), `get_learner_fn`
+rec_magpo.py:91-104,501-530 (`num_updates_per_eval` consecutive `_update_step`s per call). One process drives one GPU: the
+reference's device axis Nd is the process group, so every leaf of the learner state carries the leading `[1, U, ...]` of this
+rank's device (Appendix B of SURVEY.md lists the pytree). The leaves are views of the learner's device buffers; `learn`
+adopts whatever state it is given (copying leaves that are not its own views), runs on the GPU through libmagpo_b200.so and
+returns views again. There is no CPU fallback: without a CUDA device `learner_setup` raises.
+
+    python -m magpo_b200.rec_magpo env=coordsum arch.num_envs=1024 system.num_updates=8 arch.num_evaluation=2
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+import time
+from typing import Any, Callable, Dict, NamedTuple, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import init as minit
+from .config import Config, check_total_timesteps, compose
+from .learner import CoordSumVec, MagpoLearner, SystemConfig, param_views
+
+
+# ----------------------------------------------------------------------------- types (systems/gpo/types.py:25-83, mava/types.py:199-207)
+class Params(NamedTuple):
+    guider_params: Dict[str, torch.Tensor]
+    actor_params: Dict[str, torch.Tensor]
+
+
+class AdamState(NamedTuple):  # optax ScaleByAdamState
+    count: torch.Tensor
+    mu: Dict[str, torch.Tensor]
+    nu: Dict[str, torch.Tensor]
+
+
+class OptStates(NamedTuple):
+    guider_opt_state: AdamState
+    actor_opt_state: AdamState
+
+
+class SableHiddenStates(NamedTuple):
+    encoder: torch.Tensor
+    decoder_self_retn: torch.Tensor
+    decoder_cross_retn: torch.Tensor
+
+
+class HiddenStates(NamedTuple):
+    sable_hidden_state: SableHiddenStates
+    policy_hidden_state: torch.Tensor
+
+
+class Observation(NamedTuple):
+    agents_view: torch.Tensor
+    action_mask: torch.Tensor
+    step_count: torch.Tensor
+
+
+class TimeStep(NamedTuple):
+    observation: Observation
+    reward: torch.Tensor
+    discount: torch.Tensor
+    step_type: torch.Tensor
+
+
+class GPOLearnerState(NamedTuple):
+    params: Params
+    opt_states: OptStates
+    key: torch.Tensor
+    env_state: Dict[str, torch.Tensor]
+    timestep: TimeStep
+    dones: torch.Tensor
+    hstates: HiddenStates
+
+
+class ExperimentOutput(NamedTuple):
+    learner_state: GPOLearnerState
+    episode_metrics: Dict[str, torch.Tensor]
+    train_metrics: Dict[str, torch.Tensor]
+
+
+LearnerFn = Callable[[GPOLearnerState], ExperimentOutput]
+
+
+# jumanji registrations of the CoordSum scenarios (mava/coordsum/__init__.py:6-45): task_name -> constructor kwargs
+COORDSUM_REGISTRY = {
+    "5x20-80-v0": dict(num_agents=5, num_actions=20, time_limit=100, maxval=80),
+    "3x30-50-v0": dict(num_agents=3, num_actions=30, time_limit=100, maxval=50),
+    "3x10-30-v0": dict(num_agents=3, num_actions=10, time_limit=100, maxval=30),
+    "8x15-100-v0": dict(num_agents=8, num_actions=15, time_limit=100, maxval=100),
+}
+
+
+def make_env(config: Config) -> CoordSumVec:
+    """mava/utils/make_env.py:90-104 for the env whose dynamics live in the tree (CoordSum); the training wrapper stack
+    RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(CoordSumWrapper))) is part of the env-step kernel."""
+    if config.env.env_name != "CoordSum":
+        raise NotImplementedError(f"{config.env.env_name}: only CoordSum dynamics are built (Jumanji is not vendored)")
+    kw = dict(COORDSUM_REGISTRY.get(config.env.scenario.task_name, {}))
+    kw.update(config.env.scenario.get("task_config", {}))
+    kw.update(config.env.get("kwargs", {}))
+    return CoordSumVec(num_agents=kw["num_agents"], num_actions=kw["num_actions"], time_limit=kw.get("time_limit", 100),
+                       maxval=kw.get("maxval"))
+
+
+def _system_config(config: Config) -> SystemConfig:
+    s = config.system
+    if s.get("decay_learning_rates", False):
+        raise NotImplementedError("decay_learning_rates: only the constant schedule is built (utils/training.py:48-64)")
+    return SystemConfig(num_envs=int(config.arch.num_envs), update_batch_size=int(s.update_batch_size),
+                        rollout_length=int(s.rollout_length), ppo_epochs=int(s.ppo_epochs),
+                        num_minibatches=int(s.num_minibatches), gamma=float(s.gamma), gae_lambda=float(s.gae_lambda),
+                        clip_eps=float(s.clip_eps), ent_coef=float(s.ent_coef), vf_coef=float(s.vf_coef),
+                        max_grad_norm=float(s.max_grad_norm), clip_gpo=float(s.clip_gpo), alpha=float(s.alpha),
+                        actor_lr=float(s.actor_lr), chunk_envs=int(config.arch.get("chunk_envs", 0)))
+
+
+class ActorNetwork:
+    """`actor_network.apply(params, hstate, (observation, done)) -> (hstate, logits)` of RecurrentActor
+    (networks/base.py:161-184) for the evaluator hook (rec_magpo.py:709): masked logits [T, N, A, a]."""
+
+    def __init__(self, lrn: MagpoLearner):
+        self.lrn = lrn
+
+    def apply(self, actor_flat: torch.Tensor, hstate: torch.Tensor, observation: Observation, done: torch.Tensor):
+        """observation leaves [T, N, A, ...], done [T, N], hstate [N, A, 128]. Returns (carry, logits [T, N, A, a] with
+        illegal actions at finfo.min). The carry is returned for T == 1 (the evaluator's per-step call); else None."""
+        lrn = self.lrn
+        T, N, A = observation.agents_view.shape[:3]
+        a, dev = lrn.net.action_dim, lrn.dev
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        mb = dict(agents_view=observation.agents_view.to(torch.float32).contiguous(),
+                  action_mask=observation.action_mask.to(torch.uint8).contiguous(),
+                  step_count=observation.step_count.to(torch.int32).contiguous(), done=done.to(torch.uint8).contiguous(),
+                  action=z(T, N, A, dt=torch.int32), value=z(T, N, A), log_prob=z(T, N, A), advantages=z(T, N, A),
+                  targets=z(T, N, A), policy_h0=hstate.to(torch.float32).contiguous())
+        s = L.struct_of(L.Minibatch, **mb)
+        s.sable_h0 = L.struct_of(L.SableHState, **{k: z(N, 64, 64) for k in ("encoder", "decoder_self", "decoder_cross")})
+        s.T, s.N = T, N
+        lib = L.lib()
+        lib.magpo_update_workspace_bytes.restype = C.c_size_t
+        lib.magpo_rollout_workspace_bytes.restype = C.c_size_t
+        nbytes = max(int(lib.magpo_update_workspace_bytes(C.byref(lrn.c_net), T, N)),
+                     int(lib.magpo_rollout_workspace_bytes(C.byref(lrn.c_net), N, 0)))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        logits = z(T, N, A, a)
+        L.call("magpo_actor_forward", L.stream_ptr(), C.byref(lrn.c_net), L.ptr(actor_flat), s, L.ptr(logits), L.ptr(ws),
+               C.c_size_t(nbytes))
+        carry = None
+        if T == 1:
+            carry = mb["policy_h0"].clone()
+            L.call("magpo_actor_step", L.stream_ptr(), C.byref(lrn.c_net), N, L.ptr(actor_flat), L.ptr(mb["agents_view"]),
+                   L.ptr(mb["done"]), L.ptr(carry), L.ptr(ws), C.c_size_t(nbytes))
+        torch.cuda.current_stream().synchronize()  # the temporaries above must outlive the launches
+        return carry, logits
+
+    def initialize_carry(self, n_envs: int) -> torch.Tensor:
+        """ScannedRNN.initialize_carry (networks/base.py:144-149)."""
+        return torch.zeros(n_envs, self.lrn.net.n_agents, self.lrn.net.hidden, device=self.lrn.dev)
+
+
+def _state_views(lrn: MagpoLearner) -> GPOLearnerState:
+    """The learner's device buffers as the reference's pytree, every leaf with the leading [1, U, ...] of this device."""
+    U, E, A = lrn.sys.update_batch_size, lrn.sys.num_envs, lrn.net.n_agents
+    T = lrn.sys.rollout_length
+    lead = lambda t: t.reshape(1, U, E, *t.shape[1:])          # per-env leaves [U*E, ...] -> [1, U, E, ...]
+    rep = lambda t: t.reshape(1, 1, *t.shape).expand(1, U, *t.shape)  # replicated leaves (params, optimiser, key)
+    tree = lambda flat, table: {k: rep(v) for k, v in param_views(flat, table).items()}
+    params = Params(tree(lrn.guider, lrn.g_table), tree(lrn.actor, lrn.a_table))
+    opt = OptStates(AdamState(rep(lrn.g_count[0]), tree(lrn.g_mu, lrn.g_table), tree(lrn.g_nu, lrn.g_table)),
+                    AdamState(rep(lrn.a_count[0]), tree(lrn.a_mu, lrn.a_table), tree(lrn.a_nu, lrn.a_table)))
+    obs = Observation(lead(lrn.traj["agents_view"][T if not lrn.first_rollout else 0]),
+                      lead(lrn.traj["action_mask"][T if not lrn.first_rollout else 0]),
+                      lead(lrn.traj["step_count"][T if not lrn.first_rollout else 0]))
+    ts = TimeStep(obs, lead(lrn.ts["reward"]), lead(lrn.ts["discount"]), lead(lrn.ts["step_type"]))
+    done_env = lrn.traj["done"][T if not lrn.first_rollout else 0]
+    sable = lrn.sable_hidden_state() if not lrn.first_rollout else lrn.hs
+    hs = HiddenStates(SableHiddenStates(*(lead(sable[k]).reshape(1, U, E, 1, 1, 64, 64)
+                                          for k in ("encoder", "decoder_self", "decoder_cross"))), lead(lrn.policy_h))
+    return GPOLearnerState(params, opt, rep(lrn.key), {k: lead(v) for k, v in lrn.env_state.items()}, ts,
+                           lead(done_env)[..., None].expand(1, U, E, A).bool(), hs)
+
+
+def _flatten(x, prefix=""):
+    if isinstance(x, torch.Tensor):
+        yield prefix, x
+    elif isinstance(x, dict):
+        for k in x:
+            yield from _flatten(x[k], f"{prefix}/{k}")
+    elif isinstance(x, tuple):
+        names = getattr(x, "_fields", range(len(x)))
+        for n, v in zip(names, x):
+            yield from _flatten(v, f"{prefix}/{n}")
+
+
+def _adopt(lrn: MagpoLearner, state: GPOLearnerState) -> None:
+    """Copy the writable leaves (params, optimiser state, key) of a foreign state into the learner's buffers. Leaves that are
+    views of those buffers already (the state `learn` returned) cost nothing."""
+    mine = dict(_flatten((_state_views(lrn).params, _state_views(lrn).opt_states, _state_views(lrn).key)))
+    theirs = dict(_flatten((state.params, state.opt_states, state.key)))
+    for name, dst in mine.items():
+        src = theirs[name]
+        if src.data_ptr() != dst.data_ptr():
+            # replicated leaves: slot 0 of the foreign state is the value (identical across U, rec_magpo.py:660-673)
+            dst[0, 0].copy_(src[0, 0].to(dst.dtype))
+
+
+def get_learner_fn(lrn: MagpoLearner, config: Config) -> LearnerFn:
+    """rec_magpo.py:91-104,501-530: `learn` = num_updates_per_eval x `_update_step`, metrics stacked like scan∘vmap∘scan."""
+    n_upd = int(config.system.num_updates_per_eval)
+    U, E = lrn.sys.update_batch_size, lrn.sys.num_envs
+
+    def learn(learner_state: GPOLearnerState) -> ExperimentOutput:
+        _adopt(lrn, learner_state)
+        ep = {k: [] for k in ("episode_return", "episode_length", "is_terminal_step")}
+        tr = []
+        for _ in range(n_upd):
+            metrics, losses = lrn.update_step()
+            for k in ep:  # [T, U*E] -> [U, T, E]
+                ep[k].append(metrics[k].reshape(-1, U, E).permute(1, 0, 2).clone())
+            tr.append(losses.clone())
+        episode_metrics = {k: torch.stack(v)[None] for k, v in ep.items()}            # [1, updates, U, T, E]
+        episode_metrics["is_terminal_step"] = episode_metrics["is_terminal_step"].bool()
+        info = MagpoLearner.loss_info(torch.stack(tr), lrn.sys)                        # [updates, P, M]
+        train_metrics = {k: v[None, :, None].expand(1, n_upd, U, *v.shape[1:]) for k, v in info.items()}
+        return ExperimentOutput(_state_views(lrn), episode_metrics, train_metrics)
+
+    return learn
+
+
+def shard_env_keys(all_keys: np.ndarray, world_size: int, rank: int, U: int, E: int) -> np.ndarray:
+    """The reference reshapes the Nd*U*E reset keys to (Nd, U, E) (rec_magpo.py:648-653): global env index -> (device, slot,
+    env). Returns this rank's [U*E, 2] block, slot-major."""
+    all_keys = np.asarray(all_keys, np.uint32)
+    assert all_keys.shape == (world_size * U * E, 2), all_keys.shape
+    return all_keys.reshape(world_size, U * E, 2)[rank]
+
+
+def mean_over_devices(flat: torch.Tensor, world_size: int) -> torch.Tensor:
+    """`jax.lax.pmean(..., "device")` of the flat (guider grads | learner grads | loss sums) buffer (rec_magpo.py:399-409):
+    one sum all-reduce; the 1/Nd factor is applied where the buffer is consumed (magpo_clip_adam's grad_scale, the loss read-out).
+    This helper is the host-side statement of that contract (used by the CPU tests with the gloo backend)."""
+    import torch.distributed as dist
+
+    if world_size > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat * (1.0 / world_size)
+
+
+def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, device=None, allreduce=None, rank: int = 0,
+                  world_size: int = 1) -> Tuple[LearnerFn, ActorNetwork, GPOLearnerState]:
+    """rec_magpo.py:533-685. keys = (key, actor_net_key, net_key) as raw uint32[2] arrays (jax.random.PRNGKey layout)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("magpo_b200 runs on CUDA devices only (no CPU fallback)")
+    device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+    key, actor_net_key, net_key = keys
+    config.system.num_agents = env.num_agents  # rec_magpo.py:541-543
+    config.system.num_actions = env.action_dim
+    lrn = MagpoLearner(env, _system_config(config), device=device, allreduce=allreduce, world_size=world_size)
+    # parameters: flax's orthogonal/normal initialisers cannot be reproduced bit-for-bit without jax; same shapes, same
+    # gains, NumPy generator seeded from the net keys
+    lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, int(np.asarray(net_key)[-1])),
+                   minit.init_actor(env.obs_dim, env.action_dim, int(np.asarray(actor_net_key)[-1])))
+    U, E = lrn.sys.update_batch_size, lrn.sys.num_envs
+    # key, *env_keys = split(key, Nd*U*E + 1); reset_key = split(key)[1] is the step key of every device and slot (:642-673)
+    allk = minit.split(np.asarray(key, np.uint32), world_size * U * E + 1, device)
+    step_key = minit.split(allk[0], 2, device)[1]
+    lrn.reset(shard_env_keys(allk[1:], world_size, rank, U, E), step_key)
+    return get_learner_fn(lrn, config), ActorNetwork(lrn), _state_views(lrn)
+
+
+def run_experiment(config: Config, device=None, log=print) -> float:
+    """rec_magpo.py:688-831 without the evaluator / logger / checkpointer backends: `num_evaluation` calls of `learn`, each
+    `num_updates_per_eval` updates, reporting steps per second and the mean return of the episodes that ended."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    config = check_total_timesteps(config, world)
+    config.system.num_updates_per_eval = config.system.num_updates // config.arch.num_evaluation
+    env = make_env(config)
+    key, key_e, actor_net_key, net_key = minit.split(minit.prng_key(int(config.system.seed)), 4, device or "cuda:0")
+    allreduce = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
+    learn, _, state = learner_setup(env, (key, actor_net_key, net_key), config, device=device, allreduce=allreduce, rank=rank,
+                                    world_size=world)
+    steps_per_rollout = (world * config.system.num_updates_per_eval * config.system.rollout_length *
+                         config.system.update_batch_size * config.arch.num_envs)
+    last = float("nan")
+    for ev in range(int(config.arch.num_evaluation)):
+        t0 = time.perf_counter()
+        out = learn(state)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        state = out.learner_state
+        term = out.episode_metrics["is_terminal_step"]
+        if bool(term.any()):
+            last = float(out.episode_metrics["episode_return"][term].mean())
+        if rank == 0:
+            log(f"eval {ev}: steps_per_second={steps_per_rollout / dt:.0f} timestep={steps_per_rollout * (ev + 1)} "
+                f"episode_return={last:.4f} total_loss={float(out.train_metrics['total_loss'].mean()):.5f} "
+                f"value_loss={float(out.train_metrics['value_loss'].mean()):.5f} entropy={float(out.train_metrics['entropy'].mean()):.4f}")
+    return last
+
+
+def main(argv=None) -> float:
+    return run_experiment(compose("default/rec_magpo", list(sys.argv[1:] if argv is None else argv)))
+
+
+if __name__ == "__main__":
+    main()

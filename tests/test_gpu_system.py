@@ -1,0 +1,75 @@
+"""-m gpu: the system entry (`learner_setup` / `learn`, rec_magpo.py:533-685,501-530) and the evaluator hook
+(`actor_network.apply`) on the GPU: pytree shapes of Appendix B, metric shapes of scan∘vmap∘scan, state adoption."""
+import numpy as np
+import pytest
+import torch
+
+from magpo_b200 import init as minit
+from magpo_b200 import rec_magpo as rm
+from magpo_b200.config import compose
+from oracle import nets as onets
+from oracle import learner as olr
+
+from gpu_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(dev, extra=()):
+    cfg = compose("default/rec_magpo", ["arch.num_envs=6", "system.rollout_length=10", "system.ppo_epochs=2", "system.num_updates=4",
+                                        "arch.num_evaluation=2", "system.total_timesteps=~", *extra])
+    cfg.system.num_updates_per_eval = 2
+    env = rm.make_env(cfg)
+    key, _, ak, nk = minit.split(minit.prng_key(42), 4, dev)
+    return cfg, env, rm.learner_setup(env, (key, ak, nk), cfg, device=dev)
+
+
+def test_learn_shapes_and_state_contract(dev):
+    cfg, env, (learn, actor_network, state) = _setup(dev)
+    U, E, A, T, P, M = 2, 6, 3, 10, 2, 2
+    assert state.key.shape == (1, U, 2) and state.dones.shape == (1, U, E, A)
+    assert state.timestep.observation.agents_view.shape == (1, U, E, A, env.obs_dim)
+    assert state.hstates.sable_hidden_state.encoder.shape == (1, U, E, 1, 1, 64, 64)
+    assert state.hstates.policy_hidden_state.shape == (1, U, E, A, 128)
+    assert state.env_state["record"].shape == (1, U, E, env.num_actions, env.time_limit)
+    assert state.params.guider_params["encoder/encoder_block_0/retn/w_o"].shape == (1, U, 64, 64)
+    p0 = state.params.actor_params["action_head/Dense_0/kernel"][0, 0].clone()
+    out = learn(state)
+    assert set(out.train_metrics) == {"total_loss", "value_loss", "actor_loss", "guider_loss", "kl_loss", "entropy"}
+    for v in out.train_metrics.values():
+        assert v.shape == (1, 2, U, P, M)
+    for k in ("episode_return", "episode_length", "is_terminal_step"):
+        assert out.episode_metrics[k].shape == (1, 2, U, T, E)
+    assert int(out.learner_state.opt_states.guider_opt_state.count[0, 0]) == 2 * P * M
+    assert not torch.equal(out.learner_state.params.actor_params["action_head/Dense_0/kernel"][0, 0], p0)
+    assert torch.isfinite(out.train_metrics["total_loss"]).all()
+    # a foreign state (e.g. restored from a checkpoint) is adopted: zeroed parameters reach the device buffers
+    foreign = out.learner_state._replace(params=rm.Params(
+        {k: torch.zeros_like(v) for k, v in out.learner_state.params.guider_params.items()}, out.learner_state.params.actor_params))
+    out2 = learn(foreign)
+    # the update moved the parameters away from zero by at most a few Adam steps of size lr
+    w = out2.learner_state.params.guider_params["encoder/encoder_block_0/retn/w_o"][0, 0]
+    assert float(w.abs().max()) <= 2 * P * M * 2.5e-4 * 1.01
+
+
+def test_actor_network_apply_matches_oracle(dev):
+    cfg, env, (learn, actor_network, state) = _setup(dev)
+    lrn = actor_network.lrn
+    rng = np.random.default_rng(0)
+    N, A, d, a = 7, env.num_agents, env.obs_dim, env.action_dim
+    obs = rng.integers(0, 5, (1, N, A, d)).astype(np.float32)
+    mask = rng.random((1, N, A, a)) < 0.8
+    mask[..., 0] = True
+    done = rng.random((1, N)) < 0.3
+    h = (rng.standard_normal((N, A, 128)) * 0.3).astype(np.float32)
+    t = lambda x: torch.as_tensor(x).to(dev)
+    carry, logits = actor_network.apply(lrn.actor, t(h), rm.Observation(t(obs), t(mask), t(np.zeros((1, N, A), np.int32))), t(done))
+    _, ap = lrn.get_params()
+    ncfg = onets.NetCfg(A, d, a)
+    p = onets.to_torch({k: v.cpu().numpy() for k, v in ap.items()})
+    h_ref, l_ref = onets.actor_apply(p, ncfg, torch.tensor(h), torch.tensor(obs), torch.tensor(np.repeat(done[..., None], A, -1)),
+                                     torch.tensor(mask))
+    got = logits.cpu().numpy()
+    assert rel_err(got[mask], l_ref.numpy()[mask]) < 1e-4
+    assert (got[~mask] == np.finfo(np.float32).min).all()
+    assert rel_err(carry.cpu().numpy(), h_ref.numpy()) < 1e-4

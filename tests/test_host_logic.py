@@ -1,0 +1,86 @@
+"""CPU tests of the host-side mirror of the reference's system entry (magpo_b200/rec_magpo.py, config.py): config composition,
+the env registry, env-key sharding across ranks and the gradient mean over a 2-process gloo group (the N>1 path's host logic)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from magpo_b200 import rec_magpo as rm
+from magpo_b200.config import check_total_timesteps, compose
+from oracle import coordsum as ocs
+from oracle import prng as oprng
+
+
+def test_config_composition_and_overrides():
+    c = compose("default/rec_magpo", ["env/scenario=5x20-80", "arch.num_envs=64", "system.rollout_length=32", "system.num_updates=8",
+                                      "arch.num_evaluation=2", "system.total_timesteps=~"])
+    assert c.env.scenario.task_name == "5x20-80-v0" and c.arch.num_envs == 64 and c.system.rollout_length == 32
+    c = check_total_timesteps(c, 2)
+    assert c.system.total_timesteps == 2 * 32 * c.system.update_batch_size * 64 * 8
+    sysc = rm._system_config(c)
+    assert (sysc.num_envs, sysc.rollout_length, sysc.ppo_epochs, sysc.num_minibatches) == (64, 32, 4, 2)
+    assert sysc.clip_gpo == 1.5 and sysc.alpha == 1.0 and abs(sysc.actor_lr - 2.5e-4) < 1e-12
+
+
+def test_env_registry_matches_reference_registrations():
+    assert rm.COORDSUM_REGISTRY == ocs.SCENARIOS
+    for name in ("3x10-30", "3x30-50", "5x20-80", "8x15-100"):
+        c = compose("default/rec_magpo", [f"env/scenario={name}"])
+        env = rm.make_env(c)
+        kw = ocs.SCENARIOS[c.env.scenario.task_name]
+        assert (env.num_agents, env.num_actions, env.time_limit, env.maxval) == (kw["num_agents"], kw["num_actions"], 100, kw["maxval"])
+        assert env.obs_dim == env.num_agents + 1 and env.action_dim == env.num_actions
+
+
+def test_env_key_sharding_is_the_reference_reshape():
+    U, E, world = 2, 5, 4
+    allk = oprng.split(oprng.prng_key(7), world * U * E + 1)[1:]
+    parts = [rm.shard_env_keys(allk, world, r, U, E) for r in range(world)]
+    assert (np.concatenate(parts) == allk).all()
+    # (device, slot, env) order: env e of slot u on device r is global index (r*U + u)*E + e
+    assert (parts[3].reshape(U, E, 2)[1, 2] == allk[(3 * U + 1) * E + 2]).all()
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        U, E = 2, 3
+        # every rank derives the same key chain (replicated step key) and takes its own block of reset keys
+        allk = oprng.split(oprng.prng_key(42), world * U * E + 1)
+        step_key = oprng.split(allk[0])[1]
+        mine = rm.shard_env_keys(allk[1:], world, rank, U, E)
+        gathered = [torch.zeros(U * E, 2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gathered, torch.as_tensor(mine.astype(np.int64)))
+        keys = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(keys, torch.as_tensor(step_key.astype(np.int64)))
+        # per-rank gradients: the device mean is one sum all-reduce + a 1/Nd scale
+        g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        m = rm.mean_over_devices(g.clone(), world)
+        if rank == 0:
+            out.put(dict(all=torch.cat(gathered).numpy().astype(np.uint32), ref=allk[1:], keys=[k.numpy() for k in keys],
+                         mean=m.numpy(), expect=(torch.arange(10, dtype=torch.float32) * (1 + 2) / 2).numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_process_gloo_sharding_and_gradient_mean():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (res["all"] == res["ref"]).all()          # the ranks' blocks tile the global key array in order
+    assert (res["keys"][0] == res["keys"][1]).all()  # identical step key on every device
+    assert np.allclose(res["mean"], res["expect"])
