@@ -9,7 +9,7 @@
 // and the backward, with G = dL/dHn carried in reverse, W = D * (dO V^T):
 //   dQ = W K + diag(c) dO Hp^T      dK = W^T Q + diag(e) V G^T      dV = P^T dO + diag(e) K G      dHp = c_L G + (diag(c) Q)^T dO
 // Only the state entering each chunk is saved for the backward (T/Lc x 16 KiB per env instead of T x 16 KiB).
-// All products run as warp-level m16n8k8 TF32 MMAs with the 3xTF32 split (x = hi + lo, hi*hi + hi*lo + lo*hi, fp32
+// All products run as warp-level m16n8k8 TF32 MMAs with the 3xTF32 split (x = hi + lo by truncation, hi*hi + hi*lo + lo*hi, fp32
 // accumulate), operands staged once per chunk in shared memory; the running state (H forward, G backward) lives in
 // accumulator fragments for the whole sequence. Tiles are 32x64x64 at most, far below what a tcgen05 instruction (M >= 64,
 // operands through descriptors, accumulator in TMEM) is built for, so the warp-level instruction is the right size here.
@@ -32,12 +32,11 @@ struct FragB {
   uint32_t h[2], l[2];
 };
 
-// x = hi + lo with hi, lo exactly representable in TF32 (round-to-nearest on the bit pattern)
+// x = hi + lo: hi = x truncated to TF32 (what the tensor core reads of the fp32 word anyway), lo = x - hi exact in fp32 and
+// truncated to TF32 by the tensor core in turn (relative error of the 3-term product <= 2^-20). Two ALU ops per element.
 __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
-  const uint32_t u = __float_as_uint(x);
-  hi = (u + 0x1000u) & 0xFFFFE000u;
-  const float r = x - __uint_as_float(hi);
-  lo = (__float_as_uint(r) + 0x1000u) & 0xFFFFE000u;
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 __device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
