@@ -159,16 +159,16 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
   const int64_t Rs = (int64_t)N * A, R = Rs * T;
   // head + post torso
   if (thin_n_ok(kH, a, w.post, kH)) {  // dW, db, dX and the relu mask of the post torso in one pass
-    MAGPO_TRY(thin_n_bwd(s, R, kH, a, w.post, kH, dlogits, a, p.head_w, a, 1, w.dA, kH, g.head_w, a, g.head_b));
+    MAGPO_TRY(thin_n_bwd(s, R, kH, a, w.post, kH, dlogits, a, p.head_w, a, 1, w.dA, kH, g.head_w, a, g.head_b, g.post_b));
   } else {
     MAGPO_TRY(gemm_tn(s, R, a, kH, w.post, kH, dlogits, a, g.head_w, a));
     MAGPO_TRY(colsum(s, R, a, dlogits, a, g.head_b));
     MAGPO_TRY(gemm_nn(s, R, kH, a, dlogits, a, wref(pt.headT, kH), nullptr, w.dA, kH, 0));
     relu_bwd_kernel<<<g256(R * kH), 256, 0, s>>>(R * kH, w.post, w.dA);
     MAGPO_LAUNCH_OK();
+    MAGPO_TRY(colsum(s, R, kH, w.dA, kH, g.post_b));
   }
   MAGPO_TRY(gemm_tn(s, R, kH, kH, w.Y, kH, w.dA, kH, g.post_w, kH));
-  MAGPO_TRY(colsum(s, R, kH, w.dA, kH, g.post_b));
   MAGPO_TRY(gemm_nn(s, R, kH, kH, w.dA, kH, wref(pt.postT, kH, p.post_w, kH), nullptr, w.dB, kH, 0));  // dB = dL/dY
   // reverse scan; dgi reuses the gi buffer (dead after the forward)
   float* dgi = w.gi;

@@ -58,8 +58,9 @@ int thin_k_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx,
                float* dW, int lddw, float* db);
 int thin_n_fwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* W, int ldw, const float* bias,
                float* Y, int ldy);
+// dbx (optional): column sums of the (masked) dX, i.e. the bias gradient of the relu layer that produced X
 int thin_n_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, const float* W, int ldw,
-               int relu_mask, float* dX, int lddx, float* dW, int lddw, float* db);
+               int relu_mask, float* dX, int lddx, float* dW, int lddw, float* db, float* dbx);
 int obs_embed_fwd(cudaStream_t s, int64_t R, int d, const float* obs, const float* obs_scale, const float* Wobs,
                   const float* ln_scale, const float* pe, const int32_t* step, int max_step, float* on, float* z0, float* xin,
                   float* kqv);
@@ -90,8 +91,9 @@ int swiglu_bwd(cudaStream_t s, int64_t R, const float* gl, const float* dh, floa
 // out[r, :nout] = RMSNorm(gelu(zh)) * scale @ W3[64,nout] + b3     (head layers 1..3, sable_network.py:102-109,274-283)
 int head_fwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, const float* b3,
              int nout, float* out);
+// dbz (optional): column sums of dzh, i.e. the bias gradient of the Dense(64) that produced zh
 int head_bwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, int nout,
-             const float* dout, float* dzh, float* dscale, float* dW3, float* db3);
+             const float* dout, float* dzh, float* dscale, float* dW3, float* db3, float* dbz);
 // decoder input: x = RMSNorm(gelu(Wa[token])) * scale, token = start (0) for the first agent of a timestep else
 // 1 + action of the previous token (decode.py:86-108); xpe = x + pe
 int embed_fwd(cudaStream_t s, int64_t R, int A, const int32_t* action, const float* Wa, const float* scale,

@@ -278,7 +278,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(int64_t R, const float* __restrict__ zh, const float* __restrict__ scale,
                 const float* __restrict__ W3, int nout, const float* __restrict__ dout, float* __restrict__ dzh,
-                float* __restrict__ dscale, float* __restrict__ dW3, float* __restrict__ db3) {
+                float* __restrict__ dscale, float* __restrict__ dW3, float* __restrict__ db3, float* __restrict__ dbz) {
   __shared__ float dWs[kD * NV];
   __shared__ float sm[kWarps * 64];
   __shared__ float dbs[NV];
@@ -294,7 +294,7 @@ head_bwd_kernel(int64_t R, const float* __restrict__ zh, const float* __restrict
     dwx[j] = 0.f; dwy[j] = 0.f;
   }
   const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * lane_);
-  float2 ds = make_float2(0.f, 0.f);
+  float2 ds = make_float2(0.f, 0.f), dz = make_float2(0.f, 0.f);
   float dbl = 0.f;
   constexpr int UN = NV <= 8 ? 4 : 2;  // rows in flight per warp
   const int lane = lane_;
@@ -336,7 +336,9 @@ head_bwd_kernel(int64_t R, const float* __restrict__ zh, const float* __restrict
       const float2 u2 = make_float2(dhn.x * sc.x, dhn.y * sc.y);
       const float dot = warp_sum(p.x * u2.x + p.y * u2.y) * (1.0f / kD);
       const float r3 = rstd * rstd * rstd;
-      st2(dzh, row, kD, lane, make_float2((rstd * u2.x - p.x * r3 * dot) * gp.x, (rstd * u2.y - p.y * r3 * dot) * gp.y));
+      const float2 dzv = make_float2((rstd * u2.x - p.x * r3 * dot) * gp.x, (rstd * u2.y - p.y * r3 * dot) * gp.y);
+      dz.x += dzv.x; dz.y += dzv.y;  // column sums of dzh = bias gradient of the Dense that produced zh
+      st2(dzh, row, kD, lane, dzv);
     }
   }
 #pragma unroll
@@ -351,6 +353,7 @@ head_bwd_kernel(int64_t R, const float* __restrict__ zh, const float* __restrict
   for (int i = threadIdx.x; i < kD * nout; i += blockDim.x) atomicAdd(dW3 + i, dWs[i]);
   if (threadIdx.x < nout) atomicAdd(db3 + threadIdx.x, dbs[threadIdx.x]);
   flush_cols(ds, dscale, sm);
+  if (dbz) flush_cols(dz, dbz, sm);
 }
 
 // ------------------------------------------------------------------ decoder action embedding
@@ -513,14 +516,14 @@ int head_fwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, con
   return MAGPO_OK;
 }
 int head_bwd(cudaStream_t s, int64_t R, const float* zh, const float* scale, const float* W3, int nout,
-             const float* dout, float* dzh, float* dscale, float* dW3, float* db3) {
+             const float* dout, float* dzh, float* dscale, float* dW3, float* db3, float* dbz) {
   if (R <= 0) return MAGPO_OK;
   ProfScope ps(PROF_ROWOPS, s, (512.0 + 4.0 * nout) * R);
   if (nout < 1 || nout > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
-  if (nout == 1) head_bwd_kernel<1><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
-  else if (nout <= 8) head_bwd_kernel<8><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
-  else if (nout <= 16) head_bwd_kernel<16><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
-  else head_bwd_kernel<32><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3);
+  if (nout == 1) head_bwd_kernel<1><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3, dbz);
+  else if (nout <= 8) head_bwd_kernel<8><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3, dbz);
+  else if (nout <= 16) head_bwd_kernel<16><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3, dbz);
+  else head_bwd_kernel<32><<<row_grid(R), 256, 0, s>>>(R, zh, scale, W3, nout, dout, dzh, dscale, dW3, db3, dbz);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }

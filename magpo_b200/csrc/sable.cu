@@ -158,8 +158,8 @@ int sable_train_backward(cudaStream_t s, const GuiderP& p, const GuiderT& pt, co
   const int64_t R = (int64_t)T * N * A;
   const int Q = 4 * kD;
   // ---- decoder
-  MAGPO_TRY(head_bwd(s, R, w.zhD, p.dh2_s, p.dh3_w, a, dlogits, w.tA, g.dh2_s, g.dh3_w, g.dh3_b));
-  MAGPO_TRY(dense_bwd(s, R, kD, kD, w.xd, kD, w.tA, kD, pt.dh0T, p.dh0_w, kD, g.dh0_w, kD, g.dh0_b, w.tB, kD, 0));
+  MAGPO_TRY(head_bwd(s, R, w.zhD, p.dh2_s, p.dh3_w, a, dlogits, w.tA, g.dh2_s, g.dh3_w, g.dh3_b, g.dh0_b));
+  MAGPO_TRY(dense_bwd(s, R, kD, kD, w.xd, kD, w.tA, kD, pt.dh0T, p.dh0_w, kD, g.dh0_w, kD, nullptr, w.tB, kD, 0));
   MAGPO_TRY(act_rms_bwd(s, R, w.fD, w.y, p.dln3, 0, w.tB, nullptr, nullptr, w.tA, g.dln3));       // tA = d(fD) = d(y) residual
   MAGPO_TRY(dense_bwd(s, R, kD, kD, w.hmidD, kD, w.tA, kD, pt.dffn_outT, p.dffn_out, kD, g.dffn_out, kD, nullptr, w.tB, kD, 0));
   MAGPO_TRY(swiglu_bwd(s, R, w.glD, w.tB, w.tG));
@@ -183,8 +183,8 @@ int sable_train_backward(cudaStream_t s, const GuiderP& p, const GuiderT& pt, co
   MAGPO_TRY(dense_bwd(s, R, kD, Q, w.xpeD, kD, w.tQ, Q, pt.qkvg1T, p.qkvg1, Q, g.qkvg1, Q, nullptr, w.tA, kD, 0));  // tA = d(xpeD)
   MAGPO_TRY(embed_bwd(s, R, A, a, b.action, p.Wa, p.dln, w.tB, w.tA, g.Wa, g.dln));
   // ---- encoder: d(obs_rep) = head path + tD + tE
-  MAGPO_TRY(head_bwd(s, R, w.zh, p.h2_s, p.h3_w, 1, dvalue, w.tA, g.h2_s, g.h3_w, g.h3_b));
-  MAGPO_TRY(dense_bwd(s, R, kD, kD, w.x, kD, w.tA, kD, pt.h0T, p.h0_w, kD, g.h0_w, kD, g.h0_b, w.tB, kD, 0));
+  MAGPO_TRY(head_bwd(s, R, w.zh, p.h2_s, p.h3_w, 1, dvalue, w.tA, g.h2_s, g.h3_w, g.h3_b, g.h0_b));
+  MAGPO_TRY(dense_bwd(s, R, kD, kD, w.x, kD, w.tA, kD, pt.h0T, p.h0_w, kD, g.h0_w, kD, nullptr, w.tB, kD, 0));
   MAGPO_TRY(act_rms_bwd(s, R, w.f, w.x1, p.ln2, 0, w.tB, w.tD, w.tE, w.tA, g.ln2));               // tA = d(f) = d(x1) residual
   MAGPO_TRY(dense_bwd(s, R, kD, kD, w.hmid, kD, w.tA, kD, pt.ffn_outT, p.ffn_out, kD, g.ffn_out, kD, nullptr, w.tB, kD, 0));
   MAGPO_TRY(swiglu_bwd(s, R, w.gl, w.tB, w.tG));

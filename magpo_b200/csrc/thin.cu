@@ -174,7 +174,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 thin_n_bwd_kernel(int64_t R, int N, const float* __restrict__ X, int ldx, const float* __restrict__ dY, int lddy,
                   const float* __restrict__ W, int ldw, int relu_mask, float* __restrict__ dX, int lddx,
-                  float* __restrict__ dW, int lddw, float* __restrict__ db) {
+                  float* __restrict__ dW, int lddw, float* __restrict__ db, float* __restrict__ dbx) {
   constexpr int UN = 4;
   __shared__ __align__(16) float Wt[NV * kH];
   __shared__ float red[NV * kH + NV];
@@ -189,6 +189,7 @@ thin_n_bwd_kernel(int64_t R, int N, const float* __restrict__ X, int ldx, const 
 #pragma unroll
   for (int n = 0; n < NV; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   float bs = 0.f;  // lane n: column sum of dY[:, n]
+  float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of the masked dX
   const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), stride = (int64_t)gridDim.x * 8;
   for (int64_t row0 = w0; row0 < R; row0 += UN * stride) {
     float4 x[UN];
@@ -219,7 +220,10 @@ thin_n_bwd_kernel(int64_t R, int N, const float* __restrict__ X, int ldx, const 
         if (!(x[u].z > 0.f)) dx.z = 0.f;
         if (!(x[u].w > 0.f)) dx.w = 0.f;
       }
-      if (dX && row < R) *reinterpret_cast<float4*>(dX + row * lddx + 4 * lane) = dx;
+      if (row < R) {
+        xs.x += dx.x; xs.y += dx.y; xs.z += dx.z; xs.w += dx.w;
+        if (dX) *reinterpret_cast<float4*>(dX + row * lddx + 4 * lane) = dx;
+      }
     }
   }
 #pragma unroll
@@ -232,6 +236,15 @@ thin_n_bwd_kernel(int64_t R, int N, const float* __restrict__ X, int ldx, const 
   __syncthreads();
   for (int i = threadIdx.x; i < N * kH; i += 256) atomicAdd(dW + (size_t)(i % kH) * lddw + i / kH, red[i]);
   if (db && threadIdx.x < N) atomicAdd(db + threadIdx.x, red[NV * kH + threadIdx.x]);
+  if (dbx) {  // second use of the reduction buffer (first kH floats)
+    __syncthreads();
+    if (threadIdx.x < kH) red[threadIdx.x] = 0.f;
+    __syncthreads();
+    atomicAdd(&red[4 * lane + 0], xs.x); atomicAdd(&red[4 * lane + 1], xs.y);
+    atomicAdd(&red[4 * lane + 2], xs.z); atomicAdd(&red[4 * lane + 3], xs.w);
+    __syncthreads();
+    if (threadIdx.x < kH) atomicAdd(dbx + threadIdx.x, red[threadIdx.x]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- Sable obs embedding
@@ -406,13 +419,13 @@ int thin_n_fwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx,
 }
 
 int thin_n_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx, const float* dY, int lddy, const float* W, int ldw,
-               int relu_mask, float* dX, int lddx, float* dW, int lddw, float* db) {
+               int relu_mask, float* dX, int lddx, float* dW, int lddw, float* db, float* dbx) {
   if (R <= 0) return MAGPO_OK;
   if (!thin_n_ok(K, N, X, ldx) || (dX && ((lddx & 3) || (reinterpret_cast<uintptr_t>(dX) & 15)))) return MAGPO_ERR_UNSUPPORTED;
   ProfScope ps(PROF_ROWOPS, s, 4.0 * R * (2 * K + N));
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(R, 64), (int64_t)kNumSMs * 4));
-  if (N <= 8) thin_n_bwd_kernel<8><<<grid, 256, 0, s>>>(R, N, X, ldx, dY, lddy, W, ldw, relu_mask, dX, lddx, dW, lddw, db);
-  else thin_n_bwd_kernel<16><<<grid, 256, 0, s>>>(R, N, X, ldx, dY, lddy, W, ldw, relu_mask, dX, lddx, dW, lddw, db);
+  if (N <= 8) thin_n_bwd_kernel<8><<<grid, 256, 0, s>>>(R, N, X, ldx, dY, lddy, W, ldw, relu_mask, dX, lddx, dW, lddw, db, dbx);
+  else thin_n_bwd_kernel<16><<<grid, 256, 0, s>>>(R, N, X, ldx, dY, lddy, W, ldw, relu_mask, dX, lddx, dW, lddw, db, dbx);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
@@ -457,7 +470,7 @@ extern "C" int magpo_test_thin(magpo_stream_t s_, int kind, int64_t R, int K, in
     case 0: return thin_k_fwd(s, R, K, N, X, K, W, N, bias, out0, N, flags & 2);
     case 1: return thin_k_bwd(s, R, K, N, X, K, dY, N, (flags & 2) ? W : nullptr, out0, N, out1);
     case 2: return thin_n_fwd(s, R, K, N, X, K, W, N, bias, out0, N);
-    case 3: return thin_n_bwd(s, R, K, N, X, K, dY, N, W, N, flags & 2, out0, K, out1, N, out2);
+    case 3: return thin_n_bwd(s, R, K, N, X, K, dY, N, W, N, flags & 2, out0, K, out1, N, out2, (flags & 4) ? const_cast<float*>(bias) : nullptr);
     default: return MAGPO_ERR_ARG;
   }
 }

@@ -116,3 +116,26 @@ def test_second_rollout_carries_state(dev):
         assert (lrn.traj["action"].cpu().numpy() == rec["traj"][0]["action"]).all(), it
         assert (lrn.traj["reward"].cpu().numpy() == rec["traj"][0]["reward"]).all(), it
         assert rel_err(lrn.traj["value"].cpu().numpy(), rec["traj"][0]["value"]) < 2e-4, it
+
+
+@pytest.mark.parametrize("scenario,E,T", [("5x20-80-v0", 4, 9), ("8x15-100-v0", 3, 6), ("3x30-50-v0", 5, 12)])
+def test_other_scenarios_match_oracle(dev, scenario, E, T):
+    """The other registered CoordSum scenarios (coordsum/__init__.py:6-45): A = 5 and 8 take the per-layer rollout path
+    (the fused step kernel covers A <= 4), a = 20 / 30 the general GEMM path instead of the thin action-head kernels."""
+    spec, ncfg, osys, state, lrn = build(dev, E=E, U=1, T=T, P=1, M=1, scenario=scenario)
+    rec = {}
+    _, infos = olr.update_step(state, spec, ncfg, osys, record=rec)
+    _, losses = lrn.update_step()
+    sync()
+    assert (lrn.traj["action"].cpu().numpy() == rec["traj"][0]["action"]).all(), "sampled actions differ"
+    assert (lrn.traj["reward"].cpu().numpy() == rec["traj"][0]["reward"]).all()
+    assert rel_err(lrn.traj["value"].cpu().numpy(), rec["traj"][0]["value"]) < 1e-4
+    assert rel_err(lrn.traj["log_prob"].cpu().numpy(), rec["traj"][0]["log_prob"]) < 1e-4
+    li = MagpoLearner.loss_info(losses.cpu(), lrn.sys)
+    for name in ("value_loss", "actor_loss", "guider_loss", "kl_loss", "entropy"):
+        ref, got = infos[0][name], float(li[name][0, 0])
+        assert abs(got - ref) <= 2e-4 * max(1.0, abs(ref)), (name, got, ref)
+    gp, ap = lrn.get_params()
+    for new, ref in ((gp, state["guider_params"]), (ap, state["actor_params"])):
+        for name, r in ref.items():
+            assert np.abs(new[name].cpu().numpy() - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-3), name

@@ -303,7 +303,9 @@ def test_thin_n_layers(dev, R, N):
     dX = torch.zeros(R, K, device=dev)
     dW = torch.full((K, N), 0.5, device=dev)
     db = torch.full((N,), -0.25, device=dev)
-    L.call("magpo_test_thin", s, 3, C.c_int64(R), K, N, L.ptr(Xd), L.ptr(Wd), None, L.ptr(dYd), L.ptr(dX), L.ptr(dW), L.ptr(db), 2)
+    dbx = torch.full((K,), 0.125, device=dev)
+    L.call("magpo_test_thin", s, 3, C.c_int64(R), K, N, L.ptr(Xd), L.ptr(Wd), L.ptr(dbx), L.ptr(dYd), L.ptr(dX), L.ptr(dW), L.ptr(db), 2 | 4)
     assert rel_err(dX.cpu().numpy(), (dY.astype(np.float64) @ W.T) * (X > 0)) < 2e-6
+    assert rel_err(dbx.cpu().numpy(), ((dY.astype(np.float64) @ W.T) * (X > 0)).sum(0) + 0.125) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
     assert rel_err(dW.cpu().numpy(), X.astype(np.float64).T @ dY + 0.5) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
     assert rel_err(db.cpu().numpy(), dY.astype(np.float64).sum(0) - 0.25) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
