@@ -51,6 +51,8 @@ struct StepArgs {
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float swishf(float x) { return x * sigmoid_precise(x); }
+// acc + s * v on both halves with one packed instruction (FFMA2, sm_100: two IEEE fp32 FMAs per lane and issue slot)
+__device__ __forceinline__ float2 fma2(float s_, float2 v, float2 acc) { return __ffma2_rn(make_float2(s_, s_), v, acc); }
 
 // y[r][j] (+)= x[r] W[:, 64 j + (2l, 2l+1)]   for R rows sharing every weight load; W row-major [64, ldw]
 template <int NB, int R>
@@ -72,10 +74,7 @@ __device__ __forceinline__ void dense(const float* __restrict__ W /*shared*/, in
     for (int r = 0; r < R; ++r) {
       const float xa = __shfl_sync(kFull, x[r].x, k2), xb = __shfl_sync(kFull, x[r].y, k2);
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        y[r][j].x = fmaf(xa, w0[j].x, y[r][j].x); y[r][j].y = fmaf(xa, w0[j].y, y[r][j].y);
-        y[r][j].x = fmaf(xb, w1[j].x, y[r][j].x); y[r][j].y = fmaf(xb, w1[j].y, y[r][j].y);
-      }
+      for (int j = 0; j < NB; ++j) y[r][j] = fma2(xb, w1[j], fma2(xa, w0[j], y[r][j]));
     }
   }
 }
@@ -147,16 +146,12 @@ __device__ __forceinline__ void decoder_retention(int i, float* __restrict__ Hal
       float* H = Hall + (size_t)b[e] * kD * kD;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float qr = row_elem(q[e], r0 + j);
-        acc[e].x = fmaf(qr, h[e][j].x, acc[e].x);
-        acc[e].y = fmaf(qr, h[e][j].y, acc[e].y);
+        acc[e] = fma2(row_elem(q[e], r0 + j), h[e][j], acc[e]);
         if (i == A - 1 && live[e]) {
           float2 hn = make_float2(h[e][j].x * lam[e], h[e][j].y * lam[e]);
 #pragma unroll
           for (int jj = 0; jj < A; ++jj) {
-            const float kr = row_elem(k[e][jj], r0 + j);
-            hn.x = fmaf(kr, v[e][jj].x, hn.x);
-            hn.y = fmaf(kr, v[e][jj].y, hn.y);
+            hn = fma2(row_elem(k[e][jj], r0 + j), v[e][jj], hn);
           }
           __stcs(reinterpret_cast<float2*>(H + (size_t)(r0 + j) * kD + 2 * lane), hn);
         }
@@ -170,8 +165,7 @@ __device__ __forceinline__ void decoder_retention(int i, float* __restrict__ Hal
     for (int jj = 0; jj < A; ++jj)
       if (jj <= i) {
         const float qk = warp_sum(q[e].x * k[e][jj].x + q[e].y * k[e][jj].y);
-        acc[e].x = fmaf(qk, v[e][jj].x, acc[e].x);
-        acc[e].y = fmaf(qk, v[e][jj].y, acc[e].y);
+        acc[e] = fma2(qk, v[e][jj], acc[e]);
       }
     out[e] = acc[e];
   }
@@ -269,16 +263,12 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
           float2 hh = make_float2(h[e][j].x * lam[e], h[e][j].y * lam[e]);
 #pragma unroll
           for (int i = 0; i < A; ++i) {
-            const float kr = row_elem(qkvg[e * A + i][1], r);
-            hh.x = fmaf(kr, qkvg[e * A + i][2].x, hh.x);
-            hh.y = fmaf(kr, qkvg[e * A + i][2].y, hh.y);
+            hh = fma2(row_elem(qkvg[e * A + i][1], r), qkvg[e * A + i][2], hh);
           }
           if (!s.dry && live[e]) __stcs(reinterpret_cast<float2*>(H + (size_t)r * kD + 2 * lane), hh);
 #pragma unroll
           for (int i = 0; i < A; ++i) {
-            const float qr = row_elem(qkvg[e * A + i][0], r);
-            ret[e * A + i].x = fmaf(qr, hh.x, ret[e * A + i].x);
-            ret[e * A + i].y = fmaf(qr, hh.y, ret[e * A + i].y);
+            ret[e * A + i] = fma2(row_elem(qkvg[e * A + i][0], r), hh, ret[e * A + i]);
           }
         }
       }
