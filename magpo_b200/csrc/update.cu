@@ -258,6 +258,30 @@ size_t magpo_update_workspace_bytes(const MagpoNetCfg* net, int32_t T, int32_t N
   return ar.off;
 }
 
+namespace {
+// The guider and the learner are independent until the losses (which need both logits) and again after them. The learner's
+// persistent GRU scans are latency chains on <= 96 of the 148 SMs, so its forward / backward run on a forked stream and the
+// guider's streaming kernels fill the idle SMs and HBM bandwidth meanwhile.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int init() {
+    if (s) return MAGPO_OK;
+    MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    return MAGPO_OK;
+  }
+};
+SideStream g_side;
+bool g_overlap_nets = true;
+}  // namespace
+
+int magpo_debug_set_overlap(int on) {
+  g_overlap_nets = on != 0;
+  return MAGPO_OK;
+}
+
 int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* sys, const float* guider,
                           const float* actor, MagpoMinibatch mb, const int32_t* env_slot, const float* adv_stats_,
                           float inv_tokens, float* grads, void* workspace, size_t workspace_bytes) {
@@ -287,13 +311,33 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
   }
   const SableBatch b = make_batch(net, mb, w.pe);
   const int skip = g_debug_skip;
+  const bool overlap = g_overlap_nets && !skip;
+  cudaStream_t s2 = s;
+  if (overlap) {
+    MAGPO_TRY(g_side.init());
+    s2 = g_side.s;
+    MAGPO_CUDA_OK(cudaEventRecord(g_side.fork, s));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_side.fork, 0));
+  }
+  if (!(skip & 2)) MAGPO_TRY(actor_forward(s2, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
   if (!(skip & 1)) MAGPO_TRY(sable_train_forward(s, gp, &w.gt, b, w.sa, w.value, w.lg, true));
-  if (!(skip & 2)) MAGPO_TRY(actor_forward(s, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
+  if (overlap) {
+    MAGPO_CUDA_OK(cudaEventRecord(g_side.join, s2));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_side.join, 0));
+  }
   MAGPO_TRY(magpo_losses(s, R, N, A, a, sys, inv_tokens, w.lg, w.ll, mb.action_mask, mb.action, mb.log_prob,
                          mb.advantages, w.value, mb.value, mb.targets, env_slot, adv_stats_, w.dlg, w.dll, w.dvalue,
                          loss_sums));
+  if (overlap) {
+    MAGPO_CUDA_OK(cudaEventRecord(g_side.fork, s));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_side.fork, 0));
+  }
+  if (!(skip & 10)) MAGPO_TRY(actor_backward(s2, ap, w.at, T, N, A, d, a, mb.agents_view, mb.done, w.aa, w.dll, ag));
   if (!(skip & 5)) MAGPO_TRY(sable_train_backward(s, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
-  if (!(skip & 10)) MAGPO_TRY(actor_backward(s, ap, w.at, T, N, A, d, a, mb.agents_view, mb.done, w.aa, w.dll, ag));
+  if (overlap) {
+    MAGPO_CUDA_OK(cudaEventRecord(g_side.join, s2));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_side.join, 0));
+  }
   return MAGPO_OK;
 }
 
