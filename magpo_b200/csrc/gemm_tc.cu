@@ -67,12 +67,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_raw[i], 1);
-      mbar_init(&full_conv[i], TC_CONV_THREADS);
+      mbar_init(&full_conv[i], TC_CONV_THREADS / 32);  // one arrival per converter warp
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
     }
     mbar_init(b_ready, 1);
     fence_barrier_init();
@@ -154,9 +154,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int sl = 0; sl < nslab; ++sl, ++slab_it) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.BN + sl * 32), v);
-        if (sl == nslab - 1) {  // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
+        if (sl == nslab - 1) {  // accumulator fully read: hand it back to the MMA warp (one arrival per warp: hundreds of
+          tc_fence_before();    // arrivals on one mbarrier serialise in shared memory and cost a large part of a microsecond)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         uint8_t* buf = sOut + (size_t)(slab_it & 1) * TC_CHUNK_BYTES;
         if (et == 0) bulk_wait_read<1>();  // the store that last used this buffer has finished reading it
@@ -200,7 +201,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           lo[idx] = tf32_residual4(hi[idx]);
         }
         fence_proxy_async();
-        mbar_arrive(&full_conv[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_conv[s]);
       }
     }
   }
@@ -260,7 +262,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_raw[i], 1);
-      mbar_init(&full_conv[i], TC_CONV_THREADS);
+      mbar_init(&full_conv[i], TC_CONV_THREADS / 32);  // one arrival per converter warp
       mbar_init(&empty[i], 1);
     }
     mbar_init(tmem_full, 1);
@@ -352,7 +354,8 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         float4* lo = reinterpret_cast<float4*>(sStage + (size_t)s * 2 * raw_bytes + raw_bytes);
         for (int idx = ct; idx < nvec; idx += TC_CONV_THREADS) lo[idx] = tf32_residual4(hi[idx]);
         fence_proxy_async();
-        mbar_arrive(&full_conv[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_conv[s]);
       }
     }
   }
