@@ -233,8 +233,10 @@ def main():
         # one more step with per-category CUDA events on the launching stream (bench-only instrumentation)
         lib.magpo_prof_enable(1 if rank == 0 else 0)
         lrn.graph_rollout = False  # the per-category events are recorded by eager launches, not by a graph replay
+        lib.magpo_debug_set_overlap(0)  # ... and kernel by kernel: no guider/learner stream overlap inside this step
         lrn.update_step()
         torch.cuda.synchronize()
+        lib.magpo_debug_set_overlap(1)
         lrn.graph_rollout = True
         lib.magpo_prof_enable(0)
         if rank == 0:
