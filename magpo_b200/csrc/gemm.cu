@@ -184,7 +184,7 @@ int gemm_nn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, Wr
             int ldy, int flags) {
   if (M <= 0 || N <= 0) return MAGPO_OK;
   if (K <= 0) return MAGPO_ERR_ARG;
-  if (Wr.wt && K > 256 && K % 128 == 0 && !bias && !(flags & GEMM_RELU) && tc_supported(M, N, 128, X, ldx, Y, ldy, Wr.ldwt)) {
+  if (Wr.wt && K >= 256 && K % 128 == 0 && !bias && !(flags & GEMM_RELU) && tc_supported(M, N, 128, X, ldx, Y, ldy, Wr.ldwt)) {
     // a [K > 256, N] weight (hi + lo images) does not fit in shared memory beside the pipeline: run K in slices of 128 that
     // accumulate into Y (TMA reduce-add) instead of falling back to 32-column tiles that re-read X four times
     for (int k0 = 0; k0 < K; k0 += 128)
