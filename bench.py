@@ -279,7 +279,10 @@ def main():
             out["roofline_hbm_kernels"] = {
                 k: {"achieved_GBps": round(brk[k]["work"] / (brk[k]["ms"] * 1e-3) / 1e9, 1) if brk[k]["ms"] else None,
                     "frac_of_measured_hbm": round(brk[k]["work"] / (brk[k]["ms"] * 1e-3) / 1e9 / hb, 4) if brk[k]["ms"] else None}
-                for k in ("gae", "env_step", "rowops", "loss", "optim", "pack")}
+                for k in ("gae", "env_step", "rowops", "loss", "optim", "pack", "sample")}
+            # "sample" is the rollout's fused per-step Sable kernel (encoder + decoder + sampling): its bytes are the retention
+            # state stream (160 KiB per env-step at A = 3) plus observations / actions
+            out["roofline_hbm_kernels"]["sable_step"] = out["roofline_hbm_kernels"].pop("sample")
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt, cores, sample = run_reference(args, as_baseline=True)

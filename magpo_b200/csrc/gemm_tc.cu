@@ -464,8 +464,13 @@ bool tc_lookup(const float* w, const float** hi, const float** lo) {
 static bool tc_plan(int64_t M, int N, int K, TcParams* p, uint32_t* smem_bytes) {
   if (K % TC_KC || K < TC_KC || N % 32 || M < 1) return false;
   const int cands[] = {256, 192, 128, 96, 64, 32};
+  static int max_bn = -1;
+  if (max_bn < 0) {
+    const char* e = getenv("MAGPO_TC_MAX_BN");  // experiments: cap the N tile of the forward GEMM
+    max_bn = e ? atoi(e) : 256;
+  }
   for (int bn : cands) {
-    if (N % bn) continue;
+    if (N % bn || bn > max_bn) continue;
     const uint32_t b_bytes = (uint32_t)K * bn * 8;
     const uint32_t fixed = b_bytes + 2 * TC_CHUNK_BYTES + 256 * 4 + 256 + 1024 /*alignment slack*/;
     if (fixed + 2 * 2 * TC_CHUNK_BYTES > TC_SMEM_LIMIT) continue;

@@ -382,34 +382,54 @@ embed_fwd_kernel(int64_t R, int A, const int32_t* __restrict__ action, const flo
   }
 }
 
+// The map dy -> dWa[token] is linear in dy for a fixed token (the RMSNorm / gelu Jacobian depends on Wa[token] only), so
+// the rows are first summed per token (a streaming pass: one or two 256-byte loads and two shared-memory adds per row,
+// four rows in flight per warp) and the Jacobian is applied once per token and block.
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(int64_t R, int A, int a, const int32_t* __restrict__ action, const float* __restrict__ Wa,
                  const float* __restrict__ scale, const float* __restrict__ dy1, const float* __restrict__ dy2,
                  float* __restrict__ dWa, float* __restrict__ dscale) {
-  __shared__ float dWs[(kMaxActions + 1) * kD];
+  __shared__ float D[(kMaxActions + 1) * kD];
   __shared__ float sm[kWarps * 64];
-  for (int i = threadIdx.x; i < (a + 1) * kD; i += blockDim.x) dWs[i] = 0.f;
+  for (int i = threadIdx.x; i < (a + 1) * kD; i += blockDim.x) D[i] = 0.f;
   __syncthreads();
-  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * (threadIdx.x & 31));
-  float2 ds = make_float2(0.f, 0.f);
-  ROW_LOOP() {
-    const int tok = shifted_token(action, row, A);
-    const float2 zz = ld2(Wa, tok, kD, lane);
-    const float2 p = make_float2(gelu_tanh(zz.x), gelu_tanh(zz.y));
-    const float ss = warp_sum(p.x * p.x + p.y * p.y);
-    const float rstd = rsqrtf(ss * (1.0f / kD) + kEps);
-    float2 d = ld2(dy1, row, kD, lane);
-    if (dy2) { const float2 t = ld2(dy2, row, kD, lane); d.x += t.x; d.y += t.y; }
-    ds.x += d.x * p.x * rstd;
-    ds.y += d.y * p.y * rstd;
-    const float2 u = make_float2(d.x * sc.x, d.y * sc.y);
-    const float dot = warp_sum(p.x * u.x + p.y * u.y) * (1.0f / kD);
-    const float r3 = rstd * rstd * rstd;
-    atomicAdd(&dWs[tok * kD + 2 * lane], (rstd * u.x - p.x * r3 * dot) * gelu_tanh_grad(zz.x));
-    atomicAdd(&dWs[tok * kD + 2 * lane + 1], (rstd * u.y - p.y * r3 * dot) * gelu_tanh_grad(zz.y));
+  constexpr int UN = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wg = (int64_t)blockIdx.x * kWarps + warp, wstride = (int64_t)gridDim.x * kWarps;
+  for (int64_t row0 = wg; row0 < R; row0 += UN * wstride) {
+    float2 d[UN];
+    int tok[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t row = row0 + u * wstride;
+      const bool ok = row < R;
+      tok[u] = ok ? shifted_token(action, row, A) : 0;
+      d[u] = ok ? ld2(dy1, row, kD, lane) : make_float2(0.f, 0.f);
+      if (ok && dy2) { const float2 t = ld2(dy2, row, kD, lane); d[u].x += t.x; d[u].y += t.y; }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      if (row0 + u * wstride < R) {
+        atomicAdd(&D[tok[u] * kD + 2 * lane], d[u].x);
+        atomicAdd(&D[tok[u] * kD + 2 * lane + 1], d[u].y);
+      }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < (a + 1) * kD; i += blockDim.x) atomicAdd(dWa + i, dWs[i]);
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * lane);
+  float2 ds = make_float2(0.f, 0.f);
+  for (int t = warp; t <= a; t += kWarps) {
+    const float2 zz = ld2(Wa, t, kD, lane);
+    const float2 p = make_float2(gelu_tanh(zz.x), gelu_tanh(zz.y));
+    const float rstd = rsqrtf(warp_sum(p.x * p.x + p.y * p.y) * (1.0f / kD) + kEps);
+    const float2 dd = *reinterpret_cast<const float2*>(&D[t * kD + 2 * lane]);
+    ds.x += dd.x * p.x * rstd;
+    ds.y += dd.y * p.y * rstd;
+    const float2 u = make_float2(dd.x * sc.x, dd.y * sc.y);
+    const float dot = warp_sum(p.x * u.x + p.y * u.y) * (1.0f / kD);
+    const float r3 = rstd * rstd * rstd;
+    atomicAdd(dWa + t * kD + 2 * lane, (rstd * u.x - p.x * r3 * dot) * gelu_tanh_grad(zz.x));
+    atomicAdd(dWa + t * kD + 2 * lane + 1, (rstd * u.y - p.y * r3 * dot) * gelu_tanh_grad(zz.y));
+  }
   flush_cols(ds, dscale, sm);
 }
 
