@@ -30,7 +30,8 @@ constexpr int EPW = 2;         // envs per warp
 constexpr int SS_WARPS = 14;   // warps per CTA (28 envs; one CTA per SM, the register file is the occupancy limit): 8192 envs = 1.98 waves
 constexpr int SS_THREADS = SS_WARPS * 32;
 constexpr int SS_WBUF = kD * 4 * kD;  // floats of the largest layer [64, 256]
-constexpr uint32_t SS_SMEM = 2 * SS_WBUF * sizeof(float);
+constexpr int SS_XROWS = 8;  // rows of the per-warp activation scratch (EPW x A <= 8)
+constexpr uint32_t SS_SMEM = (2 * SS_WBUF + SS_WARPS * SS_XROWS * kD) * sizeof(float);
 constexpr unsigned kFull = 0xffffffffu;
 
 struct StepArgs {
@@ -55,33 +56,43 @@ __device__ __forceinline__ float swishf(float x) { return x * sigmoid_precise(x)
 __device__ __forceinline__ float2 fma2(float s_, float2 v, float2 acc) { return __ffma2_rn(make_float2(s_, s_), v, acc); }
 
 // y[r][j] (+)= x[r] W[:, 64 j + (2l, 2l+1)]   for R rows sharing every weight load; W row-major [64, ldw]
+// The R input rows are parked in the warp's shared scratch `xs` [R][64] and read back four k at a time as broadcast LDS.128
+// (one shared-memory instruction per row and 4 k instead of four shuffles).
 template <int NB, int R>
 __device__ __forceinline__ void dense(const float* __restrict__ W /*shared*/, int ldw, const float2 (&x)[R], float2 (&y)[R][NB],
-                                      int lane) {
+                                      float* __restrict__ xs, int lane) {
 #pragma unroll
-  for (int r = 0; r < R; ++r)
+  for (int r = 0; r < R; ++r) {
+    *reinterpret_cast<float2*>(xs + r * kD + 2 * lane) = x[r];
 #pragma unroll
     for (int j = 0; j < NB; ++j) y[r][j] = make_float2(0.f, 0.f);
-#pragma unroll 4
-  for (int k2 = 0; k2 < 32; ++k2) {
-    float2 w0[NB], w1[NB];
+  }
+  __syncwarp();
+#pragma unroll 2
+  for (int k4 = 0; k4 < 16; ++k4) {
+    float4 xv[R];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      w0[j] = *reinterpret_cast<const float2*>(W + (2 * k2) * ldw + 64 * j + 2 * lane);
-      w1[j] = *reinterpret_cast<const float2*>(W + (2 * k2 + 1) * ldw + 64 * j + 2 * lane);
-    }
+    for (int r = 0; r < R; ++r) xv[r] = *reinterpret_cast<const float4*>(xs + r * kD + 4 * k4);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float xa = __shfl_sync(kFull, x[r].x, k2), xb = __shfl_sync(kFull, x[r].y, k2);
+    for (int kk = 0; kk < 4; ++kk) {
+      float2 w[NB];
 #pragma unroll
-      for (int j = 0; j < NB; ++j) y[r][j] = fma2(xb, w1[j], fma2(xa, w0[j], y[r][j]));
+      for (int j = 0; j < NB; ++j) w[j] = *reinterpret_cast<const float2*>(W + (4 * k4 + kk) * ldw + 64 * j + 2 * lane);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float xk = kk == 0 ? xv[r].x : (kk == 1 ? xv[r].y : (kk == 2 ? xv[r].z : xv[r].w));
+#pragma unroll
+        for (int j = 0; j < NB; ++j) y[r][j] = fma2(xk, w[j], y[r][j]);
+      }
     }
   }
+  __syncwarp();  // the scratch is rewritten by the next layer
 }
 template <int R>
-__device__ __forceinline__ void dense1(const float* __restrict__ W, const float2 (&x)[R], float2 (&y)[R], int lane) {
+__device__ __forceinline__ void dense1(const float* __restrict__ W, const float2 (&x)[R], float2 (&y)[R], float* __restrict__ xs,
+                                       int lane) {
   float2 t[R][1];
-  dense<1, R>(W, kD, x, t, lane);
+  dense<1, R>(W, kD, x, t, xs, lane);
 #pragma unroll
   for (int r = 0; r < R; ++r) y[r] = t[r][0];
 }
@@ -178,6 +189,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
   extern __shared__ __align__(16) float wbuf[];  // two weight buffers of SS_WBUF floats
   float* const w_a = wbuf;
   float* const w_b = wbuf + SS_WBUF;
+  float* const xs = wbuf + 2 * SS_WBUF + (threadIdx.x >> 5) * SS_XROWS * kD;  // this warp's activation scratch
   const int lane = threadIdx.x & 31;
   const int64_t pair = (int64_t)blockIdx.x * SS_WARPS + (threadIdx.x >> 5);  // warps past the batch run dead (no stores)
   stage_issue(w_a, p.qkvg, kD * 4 * kD);
@@ -245,7 +257,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
   {
     float2 qkvg[RE][4];
     LAYER(p.wo, kD * kD)
-    dense<4, RE>(cur_w, 4 * kD, cur, qkvg, lane);
+    dense<4, RE>(cur_w, 4 * kD, cur, qkvg, xs, lane);
     LAYER_DONE()
     // retention: H <- lam H + sum_i k_i^T v_i ; ret_i = q_i H   (all A tokens are added before any output)
 #pragma unroll
@@ -288,19 +300,19 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
     for (int r = 0; r < RE; ++r) cur[r] = gn_gate(gate[r], ret[r], gs, gb);
     float2 o[RE];
     LAYER(p.ffn_gl, kD * 2 * kD)
-    dense1<RE>(cur_w, cur, o, lane);
+    dense1<RE>(cur_w, cur, o, xs, lane);
     LAYER_DONE()
     const float2 ln1 = ldg2(p.ln1 + 2 * lane);
 #pragma unroll
     for (int r = 0; r < RE; ++r) xin[r] = rmsnorm(f2add(o[r], xin[r]), ln1);  // x1
     float2 gl[RE][2];
     LAYER(p.ffn_out, kD * kD)
-    dense<2, RE>(cur_w, 2 * kD, xin, gl, lane);
+    dense<2, RE>(cur_w, 2 * kD, xin, gl, xs, lane);
     LAYER_DONE()
 #pragma unroll
     for (int r = 0; r < RE; ++r) cur[r] = make_float2(swishf(gl[r][0].x) * gl[r][1].x, swishf(gl[r][0].y) * gl[r][1].y);
     LAYER(p.h0_w, kD * kD)
-    dense1<RE>(cur_w, cur, o, lane);
+    dense1<RE>(cur_w, cur, o, xs, lane);
     LAYER_DONE()
     const float2 ln2 = ldg2(p.ln2 + 2 * lane);
 #pragma unroll
@@ -310,7 +322,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
     }
     // value head: Dense(64) -> gelu -> RMSNorm -> Dense(1)
     LAYER(full ? p.qkvg1 : nullptr, kD * 4 * kD)
-    dense1<RE>(cur_w, x, o, lane);
+    dense1<RE>(cur_w, x, o, xs, lane);
     LAYER_DONE()
     const float2 hb = ldg2(p.h0_b + 2 * lane), hs = ldg2(p.h2_s + 2 * lane), hw = ldg2(p.h3_w + 2 * lane);
     const float hb3 = __ldg(p.h3_b);
@@ -357,7 +369,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
     {
       float2 qkvg[EPW][4];
       LAYER(p.wo1, kD * kD)
-      dense<4, EPW>(cur_w, 4 * kD, in, qkvg, lane);
+      dense<4, EPW>(cur_w, 4 * kD, in, qkvg, xs, lane);
       LAYER_DONE()
 #pragma unroll
       for (int e = 0; e < EPW; ++e) {
@@ -378,7 +390,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = gn_gate(g1[e], r1[e], gs, gb);
       LAYER(p.qkvg2, kD * 4 * kD)
-      dense1<EPW>(cur_w, t, o, lane);
+      dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
 #pragma unroll
       for (int e = 0; e < EPW; ++e)
@@ -398,11 +410,11 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
       {
         float2 t[EPW][1];
         LAYER(p.wo2, kD * kD)
-        dense<1, EPW>(cur_w, 4 * kD, qin, t, lane);
+        dense<1, EPW>(cur_w, 4 * kD, qin, t, xs, lane);
 #pragma unroll
         for (int e = 0; e < EPW; ++e) q2[e] = t[e][0];
       }
-      dense<3, EPW>(cur_w + kD, 4 * kD, rpe, kvg, lane);
+      dense<3, EPW>(cur_w + kD, 4 * kD, rpe, kvg, xs, lane);
       LAYER_DONE()
       float2 r2[EPW];
 #pragma unroll
@@ -417,7 +429,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = gn_gate(kvg[e][2], r2[e], gs, gb);
       LAYER(p.dffn_gl, kD * 2 * kD)
-      dense1<EPW>(cur_w, t, o, lane);
+      dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
 #pragma unroll
       for (int e = 0; e < EPW; ++e) {
@@ -432,18 +444,18 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
     {
       float2 gl[EPW][2], t[EPW], o[EPW];
       LAYER(p.dffn_out, kD * kD)
-      dense<2, EPW>(cur_w, 2 * kD, yv, gl, lane);
+      dense<2, EPW>(cur_w, 2 * kD, yv, gl, xs, lane);
       LAYER_DONE()
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = make_float2(swishf(gl[e][0].x) * gl[e][1].x, swishf(gl[e][0].y) * gl[e][1].y);
       LAYER(p.dh0_w, kD * kD)
-      dense1<EPW>(cur_w, t, o, lane);
+      dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
       const float2 dln3 = ldg2(p.dln3 + 2 * lane);
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = rmsnorm(f2add(o[e], yv[e]), dln3);  // xd
       LAYER(i + 1 < A ? p.qkvg1 : nullptr, kD * 4 * kD)
-      dense1<EPW>(cur_w, t, o, lane);
+      dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
       const float2 hb = ldg2(p.dh0_b + 2 * lane), hs = ldg2(p.dh2_s + 2 * lane);
       float2 hn[EPW];
