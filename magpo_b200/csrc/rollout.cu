@@ -23,9 +23,12 @@ int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
 
 // sable_step.cu: the whole get_actions of a step as one kernel (A <= 4, obs_dim <= 16)
 bool sable_step_supported(int A, int d, int a);
+size_t sable_step_table_floats(const MagpoNetCfg* net);
+int sable_step_tables(cudaStream_t st, const MagpoNetCfg* net, const GuiderP& p, const float* pe, float* tab);
 int sable_step(cudaStream_t st, const MagpoNetCfg* net, int B, int gumbel_rows, const GuiderP& p, float kappa, const float* agents_view,
                const uint8_t* action_mask, const int32_t* step_count, const uint8_t* prev_done, const uint32_t* sample_keys,
-               const float* pe, MagpoSableHState hs, bool dry, int32_t* action, float* log_prob, float* value, float* masked_logits);
+               const float* pe, const float* dec_tab, MagpoSableHState hs, bool dry, int32_t* action, float* log_prob, float* value,
+               float* masked_logits);
 
 namespace {
 
@@ -117,7 +120,7 @@ struct RolloutWs {
   ActorActs aa;
   GuiderT gt;  // transposed weights + TF32 hi/lo images: the rollout GEMMs run on the tensor cores as well
   ActorT at;
-  float *pe, *xrep_i, *xrep_pe_i, *logits_i;
+  float *pe, *dec_tab, *xrep_i, *xrep_pe_i, *logits_i;
   int32_t *step_i, *prev_action;
   uint32_t* sample_keys;
   void plan(Arena& ar, const MagpoNetCfg* net, int B, int T) {
@@ -127,6 +130,7 @@ struct RolloutWs {
     gt.plan(ar, net->obs_dim);
     at.plan(ar, net->action_dim);
     pe = ar.get<float>((size_t)(net->max_step_count + 1) * kD);
+    dec_tab = ar.get<float>(sable_step_table_floats(net));
     xrep_i = ar.get<float>((size_t)B * kD);
     xrep_pe_i = ar.get<float>((size_t)B * kD);
     logits_i = ar.get<float>((size_t)B * net->action_dim);
@@ -143,8 +147,8 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
                 int32_t* action, float* log_prob, float* value, float* masked_logits, const RolloutWs& w) {
   const int A = net->n_agents, d = net->obs_dim, a = net->action_dim, ms = net->max_step_count;
   if (!g_force_unfused && sable_step_supported(A, d, a))
-    return sable_step(s, net, B, gumbel_rows, gp, kappa, agents_view, action_mask, step_count, prev_done, sample_keys, w.pe, hs, dry,
-                      action, log_prob, value, masked_logits);
+    return sable_step(s, net, B, gumbel_rows, gp, kappa, agents_view, action_mask, step_count, prev_done, sample_keys, w.pe, w.dec_tab,
+                      hs, dry, action, log_prob, value, masked_logits);
   MAGPO_TRY(sable_encoder_forward(s, gp, gt, 1, B, A, d, ms, agents_view, step_count, prev_done, hs.encoder, kappa, w.pe,
                                   w.sa, value, nullptr, dry ? nullptr : hs.encoder));
   if (!action) return MAGPO_OK;
@@ -206,6 +210,8 @@ int magpo_sable_get_actions(magpo_stream_t s_, const MagpoNetCfg* net, int32_t B
   w.plan(ar, net, B, 0);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
   MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
+  if (!g_force_unfused && sable_step_supported(net->n_agents, net->obs_dim, net->action_dim))
+    MAGPO_TRY(sable_step_tables(s, net, GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim), w.pe, w.dec_tab));
   const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim);
   return get_actions(s, net, B, gumbel_rows, gp, nullptr, net_kappa(net), agents_view, action_mask, step_count, prev_done,
                      sample_keys, hs, false, action, log_prob, value, logits, w);
@@ -248,6 +254,8 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
   MagpoCoordSumState* cst = static_cast<MagpoCoordSumState*>(env_state);
 
   MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
+  if (!g_force_unfused && sable_step_supported(net->n_agents, net->obs_dim, net->action_dim))
+    MAGPO_TRY(sable_step_tables(s, net, GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim), w.pe, w.dec_tab));
   const GuiderT* gtp = nullptr;
   const ActorT* atp = nullptr;
   if (tc_enabled()) {  // parameters are constant during the rollout: one transpose + TF32 split up front

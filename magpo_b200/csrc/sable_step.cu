@@ -43,6 +43,7 @@ struct StepArgs {
   const uint8_t* prev_done;  // [B] or null
   const uint32_t* keys;      // [A][2] sample keys of this step
   const float* pe;           // [max_step+1, 64]
+  const float* dec_tab;      // [(a+1) + (max_step+1), 256]: token rows then step rows of the decoder's first projection
   float *h_enc, *h_self, *h_cross;  // [B,64,64]
   int32_t* action;           // [B,A]
   float *log_prob, *value;   // [B,A]
@@ -321,7 +322,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
       xpe[r] = f2add(x[r], pe_row(s.pe, stp[r], s.max_step, lane));
     }
     // value head: Dense(64) -> gelu -> RMSNorm -> Dense(1)
-    LAYER(full ? p.qkvg1 : nullptr, kD * 4 * kD)
+    LAYER(full ? p.wo1 : nullptr, kD * kD)
     dense1<RE>(cur_w, x, o, xs, lane);
     LAYER_DONE()
     const float2 hb = ldg2(p.h0_b + 2 * lane), hs = ldg2(p.h2_s + 2 * lane), hw = ldg2(p.h3_w + 2 * lane);
@@ -348,29 +349,35 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
   // history stays in registers through compile-time indices under runtime predicates
 #pragma unroll 1
   for (int i = 0; i < A; ++i) {
-    float2 xD[EPW], in[EPW];
-    int st[EPW];
+    float2 xD[EPW];
+    int st[EPW], tokv[EPW];
     {
       const float2 dln = ldg2(p.dln + 2 * lane);
 #pragma unroll
       for (int e = 0; e < EPW; ++e) {
         const int tok = i == 0 ? 0 : 1 + prev_act[e];  // start-of-timestep token, else one-hot(previous action)
+        tokv[e] = tok;
         const float2 z = ldg2(p.Wa + (size_t)tok * kD + 2 * lane);
         xD[e] = rmsnorm(make_float2(gelu_tanh(z.x), gelu_tanh(z.y)), dln);
         st[e] = 0;
 #pragma unroll
         for (int jj = 0; jj < A; ++jj)
           if (jj == i) st[e] = stp[e * A + jj];
-        in[e] = f2add(xD[e], pe_row(s.pe, st[e], s.max_step, lane));
       }
     }
     // ---- self retention
     float2 r1[EPW], g1[EPW];
     {
+      // (xD + pe[step]) W_qkvg1 = xD W + pe[step] W, and xD only depends on the input token (a + 1 values): both terms come
+      // from the tables sable_step_tables() builds once per rollout instead of a 64 x 256 layer per agent
       float2 qkvg[EPW][4];
-      LAYER(p.wo1, kD * kD)
-      dense<4, EPW>(cur_w, 4 * kD, in, qkvg, xs, lane);
-      LAYER_DONE()
+#pragma unroll
+      for (int e = 0; e < EPW; ++e) {
+        const float* ut = s.dec_tab + (size_t)tokv[e] * 4 * kD;
+        const float* pt = s.dec_tab + (size_t)(s.a + 1 + min(max(st[e], 0), s.max_step)) * 4 * kD;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) qkvg[e][j] = f2add(ldg2(ut + 64 * j + 2 * lane), ldg2(pt + 64 * j + 2 * lane));
+      }
 #pragma unroll
       for (int e = 0; e < EPW; ++e) {
 #pragma unroll
@@ -454,7 +461,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
       const float2 dln3 = ldg2(p.dln3 + 2 * lane);
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = rmsnorm(f2add(o[e], yv[e]), dln3);  // xd
-      LAYER(i + 1 < A ? p.qkvg1 : nullptr, kD * 4 * kD)
+      LAYER(i + 1 < A ? p.wo1 : nullptr, kD * kD)
       dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
       const float2 hb = ldg2(p.dh0_b + 2 * lane), hs = ldg2(p.dh2_s + 2 * lane);
@@ -507,6 +514,29 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
   }
 }
 
+// Row r < a + 1: (RMSNorm(gelu(Wa[r])) * dln) W_qkvg1 (the decoder input token r); row a + 1 + t: pe[t] W_qkvg1.
+__global__ void __launch_bounds__(256)
+decoder_tables_kernel(const GuiderP p, int a, int max_step, const float* __restrict__ pe, float* __restrict__ tab) {
+  __shared__ float x[kD];
+  const int r = blockIdx.x, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    float2 v;
+    if (r <= a) {
+      const float2 z = ldg2(p.Wa + (size_t)r * kD + 2 * lane);
+      v = rmsnorm(make_float2(gelu_tanh(z.x), gelu_tanh(z.y)), ldg2(p.dln + 2 * lane));
+    } else {
+      v = ldg2(pe + (size_t)(r - a - 1) * kD + 2 * lane);
+    }
+    x[2 * lane] = v.x;
+    x[2 * lane + 1] = v.y;
+  }
+  __syncthreads();
+  float acc = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < kD; ++k) acc = fmaf(x[k], __ldg(p.qkvg1 + (size_t)k * 4 * kD + threadIdx.x), acc);
+  tab[(size_t)r * 4 * kD + threadIdx.x] = acc;
+}
+
 template <int A>
 int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
   const unsigned grid = (unsigned)ceil_div(ceil_div(s.B, EPW), SS_WARPS);
@@ -528,10 +558,20 @@ int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
 
 bool sable_step_supported(int A, int d, int a) { return A >= 1 && A <= 4 && d >= 1 && d <= 16 && a >= 1 && a <= 32; }
 
+size_t sable_step_table_floats(const MagpoNetCfg* net) { return (size_t)(net->action_dim + 1 + net->max_step_count + 1) * 4 * kD; }
+
+// Once per parameter set (the rollout: once per call): the decoder's first-projection tables read by sable_step().
+int sable_step_tables(cudaStream_t st, const MagpoNetCfg* net, const GuiderP& p, const float* pe, float* tab) {
+  decoder_tables_kernel<<<net->action_dim + 1 + net->max_step_count + 1, 256, 0, st>>>(p, net->action_dim, net->max_step_count, pe, tab);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
 // One SableNetwork.get_actions for B envs. action == nullptr (bootstrap): encoder + value only, states untouched.
 int sable_step(cudaStream_t st, const MagpoNetCfg* net, int B, int gumbel_rows, const GuiderP& p, float kappa, const float* agents_view,
                const uint8_t* action_mask, const int32_t* step_count, const uint8_t* prev_done, const uint32_t* sample_keys,
-               const float* pe, MagpoSableHState hs, bool dry, int32_t* action, float* log_prob, float* value, float* masked_logits) {
+               const float* pe, const float* dec_tab, MagpoSableHState hs, bool dry, int32_t* action, float* log_prob, float* value,
+               float* masked_logits) {
   if (B <= 0) return MAGPO_OK;
   const int A = net->n_agents;
   if (!sable_step_supported(A, net->obs_dim, net->action_dim)) return MAGPO_ERR_UNSUPPORTED;
@@ -540,6 +580,7 @@ int sable_step(cudaStream_t st, const MagpoNetCfg* net, int B, int gumbel_rows, 
   s.dry = (dry || !action) ? 1 : 0;
   s.kappa = kappa;
   s.obs = agents_view; s.mask = action_mask; s.step = step_count; s.prev_done = prev_done; s.keys = sample_keys; s.pe = pe;
+  s.dec_tab = dec_tab;
   s.h_enc = hs.encoder; s.h_self = hs.decoder_self; s.h_cross = hs.decoder_cross;
   s.action = action; s.log_prob = log_prob; s.value = value; s.masked_logits = masked_logits;
   const double state_bytes = s.dry ? 16384.0 : (32768.0 + 2.0 * (16384.0 * A + 16384.0));
