@@ -12,18 +12,21 @@ __global__ void __launch_bounds__(256)
 gru_gate_fwd_kernel(int64_t rows, int A, const float* __restrict__ gi, const float* __restrict__ gh,
                     const float* __restrict__ bhn, const float* __restrict__ hu, const uint8_t* __restrict__ done_next,
                     float* __restrict__ rzn, float* __restrict__ ghn_out, float* __restrict__ y,
-                    float* __restrict__ hu_next) {
+                    float* __restrict__ hu_next, const uint8_t* __restrict__ done_cur) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * kH) return;
   const int64_t row = idx / kH;
   const int j = (int)(idx % kH);
   const float* gir = gi + row * 3 * kH;
   const float* ghr = gh + row * 3 * kH;
-  const float r = sigmoid_precise(gir[j] + ghr[j]);
-  const float z = sigmoid_precise(gir[kH + j] + ghr[kH + j]);
-  const float ghn = ghr[2 * kH + j] + bhn[j];
+  // done_cur: `hu` / `gh` come from the un-masked carry; a row mask commutes with the right-multiplication by W_h, so
+  // resetting the carry (base.py:136-139) is zeroing the row's gh and h here
+  const float keep = (done_cur && done_cur[row / A]) ? 0.0f : 1.0f;
+  const float r = sigmoid_precise(gir[j] + keep * ghr[j]);
+  const float z = sigmoid_precise(gir[kH + j] + keep * ghr[kH + j]);
+  const float ghn = keep * ghr[2 * kH + j] + bhn[j];
   const float n = tanhf(gir[2 * kH + j] + r * ghn);
-  const float hprev = hu[idx];
+  const float hprev = keep * hu[idx];
   const float h = (1.0f - z) * n + z * hprev;
   if (rzn) {
     float* o = rzn + row * 3 * kH;
@@ -127,19 +130,24 @@ int actor_forward(cudaStream_t s, const ActorP& p, const ActorT* pt, int T, int 
   if (thin_k_ok(d, kH, kH, p.pre_w, w.e, kH)) MAGPO_TRY(thin_k_fwd(s, R, d, kH, agents_view, d, p.pre_w, kH, p.pre_b, w.e, kH, 1));
   else MAGPO_TRY(gemm_nn(s, R, kH, d, agents_view, d, wref(p.pre_w, kH), p.pre_b, w.e, kH, GEMM_RELU));
   MAGPO_TRY(gemm_nn(s, R, 3 * kH, kH, w.e, kH, wref(p.Wi, 3 * kH, pt ? pt->WiT : nullptr, kH), p.bi, w.gi, 3 * kH, 0));
-  mask_rows_kernel<<<g256(Rs * kH), 256, 0, s>>>(Rs, A, h0, done, w.HU);
-  MAGPO_LAUNCH_OK();
+  // inference (no backward buffers, T = 1: the rollout's state push): the reset mask is applied inside the gate kernel
+  const bool mask_in_gate = !w.rzn && T == 1;
+  if (!mask_in_gate) {
+    mask_rows_kernel<<<g256(Rs * kH), 256, 0, s>>>(Rs, A, h0, done, w.HU);
+    MAGPO_LAUNCH_OK();
+  }
   const float *wh_hi = nullptr, *wh_lo = nullptr;
   const bool scan = T > 1 && w.rzn && pt && tc_enabled() && !g_force_stepwise && tc_lookup(pt->WhT, &wh_hi, &wh_lo);
   if (scan) MAGPO_TRY(gru_scan_fwd(s, T, N, A, w.gi, wh_hi, wh_lo, p.bhn, done, w.rzn, w.ghn, w.Y, w.HU));
   for (int t = 0; t < T && !scan; ++t) {
-    const float* hu = w.HU + (size_t)t * Rs * kH;
+    const float* hu = mask_in_gate ? h0 : w.HU + (size_t)t * Rs * kH;
     MAGPO_TRY(gemm_nn(s, Rs, 3 * kH, kH, hu, kH, wref(p.Wh, 3 * kH, pt ? pt->WhT : nullptr, kH), nullptr, w.gh, 3 * kH, 0));
     const uint8_t* dn = (t + 1 < T) ? done + (size_t)(t + 1) * N : nullptr;
     ProfScope ps(PROF_GRU, s, 4.0 * kH * 13 * (double)Rs);
     gru_gate_fwd_kernel<<<g256(Rs * kH), 256, 0, s>>>(
         Rs, A, w.gi + (size_t)t * Rs * 3 * kH, w.gh, p.bhn, hu, dn, w.rzn ? w.rzn + (size_t)t * Rs * 3 * kH : nullptr,
-        w.ghn ? w.ghn + (size_t)t * Rs * kH : nullptr, w.Y + (size_t)t * Rs * kH, w.HU + (size_t)(t + 1) * Rs * kH);
+        w.ghn ? w.ghn + (size_t)t * Rs * kH : nullptr, w.Y + (size_t)t * Rs * kH, w.HU + (size_t)(t + 1) * Rs * kH,
+        mask_in_gate ? done : nullptr);
     MAGPO_LAUNCH_OK();
   }
   if (h_out) MAGPO_CUDA_OK(cudaMemcpyAsync(h_out, w.Y + (size_t)(T - 1) * Rs * kH, (size_t)Rs * kH * sizeof(float),
