@@ -110,6 +110,22 @@ def run_reference(args, as_baseline=False):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): everything else that native libraries print there (e.g. NCCL's version
+    # banner) is routed to stderr while the benchmark runs
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(line, flush=True)
+
+
+def run():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -118,12 +134,11 @@ def main():
         if rank != 0:
             return
         val, dt, cores, sample = run_reference(args)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        return json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
     import numpy as np
     import torch
@@ -287,11 +302,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt, cores, sample = run_reference(args, as_baseline=True)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    if rank == 0:
-        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return json.dumps(out) if rank == 0 else None
 
 
 if __name__ == "__main__":
