@@ -22,7 +22,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENARIO = dict(num_agents=3, num_actions=10, time_limit=100, maxval=30)  # CoordSum 3x10-30 (coordsum/__init__.py:26-35)
+# BASELINE.json configs[1]: `rec_magpo.py env=lbf` default scenario (configs/env/lbf.yaml:4 -> 2s-8x8-2p-2f-coop), num_envs=4096 on
+# one B200. `--env coordsum` selects the configs[4] sweep point (CoordSum 3x10-30, coordsum/__init__.py:26-35).
+WORKLOADS = {
+    "lbf": dict(kw=dict(grid_size=8, fov=2, num_agents=2, num_food=2, max_agent_level=2, force_coop=True, time_limit=100),
+                label="LevelBasedForaging 2s-8x8-2p-2f-coop (A=2, a=6, d=14; BASELINE configs[1]; dynamics restated from jumanji "
+                      "1.1.0, see oracle/lbf.py)"),
+    "coordsum": dict(kw=dict(num_agents=3, num_actions=10, time_limit=100, maxval=30),
+                     label="CoordSum 3x10-30 (A=3, a=10, d=4; BASELINE configs[4] sweep point)"),
+}
 METRIC, UNIT = "end_to_end_training_agent_env_steps_per_sec", "agent-steps/s"
 PROF_CATS = ["gemm_nn", "gemm_tn", "colsum", "rowops", "retention_fwd", "retention_bwd", "gru_pointwise", "loss", "pack",
              "optim", "env_step", "sample", "gae", "misc", "gemm_rollout"]
@@ -34,6 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--env", default="lbf", choices=sorted(WORKLOADS))
     ap.add_argument("--num-envs", type=int, default=4096, help="arch.num_envs per GPU per update-batch slot")
     ap.add_argument("--update-batch-size", type=int, default=2)
     ap.add_argument("--rollout-length", type=int, default=128)
@@ -45,11 +54,10 @@ def parse():
 
 
 def workload_config(args, n_gpus):
-    return {"workload": f"rec_magpo CoordSum 3x10-30 (A=3, a=10, d=4), num_envs={args.num_envs}/GPU/slot, "
+    return {"workload": f"rec_magpo {WORKLOADS[args.env]['label']}, num_envs={args.num_envs}/GPU/slot, "
                         f"update_batch_size={args.update_batch_size}, rollout_length={args.rollout_length}, ppo_epochs=4, "
-                        f"num_minibatches=2, Sable D=64 + GRU H=128 (configs[4] sweep point at configs[1]'s num_envs; LBF/RWARE "
-                        f"dynamics live in un-vendored jumanji, see DESIGN.md)",
-            "num_envs": args.num_envs, "update_batch_size": args.update_batch_size, "rollout_length": args.rollout_length,
+                        f"num_minibatches=2, Sable D=64 + GRU H=128",
+            "env": args.env, "num_envs": args.num_envs, "update_batch_size": args.update_batch_size, "rollout_length": args.rollout_length,
             "ppo_epochs": 4, "num_minibatches": 2, "parallelism": f"dp{n_gpus}",
             "l2": "working set per step (>10 GB of activations + 400 MB of Sable state) exceeds the 126 MB L2"}
 
@@ -86,12 +94,12 @@ def run_reference(args, as_baseline=False):
     """The CPU restatement (oracle/) of the same step on the host cores: the reference itself is JAX-only and
     cannot be installed here (no jax/flax/optax/jumanji wheels), so kind = "port"."""
     import torch
-    from oracle import coordsum as ocs, learner as olr, nets as onets
+    from oracle import coordsum as ocs, lbf as olbf, learner as olr, nets as onets
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     E = 16  # bounded sample of the workload: 16 of the envs per slot, everything else as configured
-    spec = ocs.CoordSumSpec(**SCENARIO)
+    spec = (olbf.LbfSpec if args.env == "lbf" else ocs.CoordSumSpec)(**WORKLOADS[args.env]["kw"])
     ncfg = onets.NetCfg(spec.num_agents, spec.obs_dim, spec.action_dim)
     osys = olr.SysCfg(num_envs=E, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length)
     state = olr.learner_setup(spec, ncfg, osys, seed=42)
@@ -146,7 +154,7 @@ def run():
 
     from magpo_b200 import _lib as L
     from magpo_b200 import init as minit
-    from magpo_b200.learner import CoordSumVec, MagpoLearner, SystemConfig
+    from magpo_b200.learner import CoordSumVec, LbfVec, MagpoLearner, SystemConfig
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -157,7 +165,7 @@ def run():
         dist.init_process_group("nccl", device_id=dev)
         allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
-    env = CoordSumVec(**SCENARIO)
+    env = (LbfVec if args.env == "lbf" else CoordSumVec)(**WORKLOADS[args.env]["kw"])
     sysc = SystemConfig(num_envs=args.num_envs, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length,
                         chunk_envs=args.chunk_envs)
     lrn = MagpoLearner(env, sysc, device=dev, allreduce=allreduce, world_size=world)

@@ -133,6 +133,38 @@ int magpo_coordsum_reset(magpo_stream_t s, const MagpoCoordSumCfg* cfg, int32_t 
 int magpo_coordsum_step(magpo_stream_t s, const MagpoCoordSumCfg* cfg, int32_t B,
                         const int32_t* action, MagpoCoordSumState st, MagpoTimeStep ts);
 
+/* LevelBasedForaging (jumanji 1.1.0 @ 9ced6b8 `environments/routing/lbf`, un-vendored third-party dependency, restated — see
+ * oracle/lbf.py; built by mava/utils/make_env.py:107-135 from configs/env/scenario/{2s-8x8-2p-2f-coop,...}.yaml task_config) under
+ * RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(LbfWrapper(env)))) — mava/wrappers/jumanji.py:171-208.
+ * obs_dim d = num_agents + 3*(num_food+num_agents), action_dim 6. Limits: grid_size <= 16, num_agents <= 8, num_food <= 8. */
+typedef struct MagpoLbfCfg {
+  int32_t grid_size, fov, num_agents, num_food, max_agent_level, force_coop, time_limit;
+  int32_t agent_mask_rows; /* 1: generator's agent mask clears whole rows (`mask.at[food_positions]`), 0: food cells only */
+} MagpoLbfCfg;
+
+/* RecordEpisodeMetricsState(env_state = lbf State(agents, food_items, step_count, key)). Positions are (row, col). */
+typedef struct MagpoLbfState {
+  int32_t* agent_pos;       /* [B,A,2] */
+  int32_t* agent_level;     /* [B,A] */
+  uint8_t* agent_loading;   /* [B,A] */
+  int32_t* food_pos;        /* [B,F,2] */
+  int32_t* food_level;      /* [B,F] */
+  uint8_t* food_eaten;      /* [B,F] */
+  int32_t* step_count;      /* [B] */
+  uint32_t* key;            /* [B,2]  lbf State.key */
+  uint32_t* metrics_key;    /* [B,2]  RecordEpisodeMetricsState.key */
+  float* running_return;    /* [B] */
+  int32_t* running_length;  /* [B] */
+  float* episode_return;    /* [B] */
+  int32_t* episode_length;  /* [B] */
+} MagpoLbfState;
+
+/* vmap(env.reset)(keys) / vmap(env.step)(state, action) for the LBF stack; same contract as the CoordSum pair. */
+int magpo_lbf_reset(magpo_stream_t s, const MagpoLbfCfg* cfg, int32_t B, const uint32_t* keys,
+                    MagpoLbfState st, MagpoTimeStep ts);
+int magpo_lbf_step(magpo_stream_t s, const MagpoLbfCfg* cfg, int32_t B, const int32_t* action,
+                   MagpoLbfState st, MagpoTimeStep ts);
+
 /* ------------------------------------------------------------------ GAE
  * calculate_gae — mava/utils/multistep.py:24-68. Layout [T,B,A] (time-major), `done` is per env
  * [T,B] (Transition.done is constant over agents, rec_magpo.py:172), last_done [B]. */

@@ -54,6 +54,17 @@ class CoordSumState(C.Structure):
                                   "running_length", "episode_return", "episode_length")]
 
 
+class LbfCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("grid_size", "fov", "num_agents", "num_food", "max_agent_level", "force_coop",
+                                         "time_limit", "agent_mask_rows")]
+
+
+class LbfState(C.Structure):
+    _fields_ = [(n, vp) for n in ("agent_pos", "agent_level", "agent_loading", "food_pos", "food_level", "food_eaten",
+                                  "step_count", "key", "metrics_key", "running_return", "running_length", "episode_return",
+                                  "episode_length")]
+
+
 class SableHState(C.Structure):
     _fields_ = [(n, vp) for n in ("encoder", "decoder_self", "decoder_cross")]
 

@@ -237,7 +237,7 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
                   void* workspace, size_t workspace_bytes) {
   MAGPO_TRY(check_net(net));
   if (!sys || !env_cfg || !env_state || !guider || !actor || !key || !policy_h || !workspace) return MAGPO_ERR_ARG;
-  if (env_kind != MAGPO_ENV_COORDSUM) return MAGPO_ERR_UNSUPPORTED;
+  if (env_kind != MAGPO_ENV_COORDSUM && env_kind != MAGPO_ENV_LBF) return MAGPO_ERR_UNSUPPORTED;  // RWARE: not built
   cudaStream_t s = as_stream(s_);
   const int A = net->n_agents, d = net->obs_dim, a = net->action_dim;
   const int T = sys->rollout_length, E = sys->num_envs;
@@ -250,8 +250,6 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
   const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), d, a);
   const ActorP ap = ActorP::bind(const_cast<float*>(actor), d, a);
   const float kappa = net_kappa(net);
-  const MagpoCoordSumCfg* ccfg = static_cast<const MagpoCoordSumCfg*>(env_cfg);
-  MagpoCoordSumState* cst = static_cast<MagpoCoordSumState*>(env_state);
 
   MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
   if (!g_force_unfused && sable_step_supported(net->n_agents, net->obs_dim, net->action_dim))
@@ -302,7 +300,12 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
     o.episode_return = traj.episode_return + (size_t)t * B;
     o.episode_length = traj.episode_length + (size_t)t * B;
     o.is_terminal_step = traj.is_terminal_step + (size_t)t * B;
-    MAGPO_TRY(coordsum_step_launch(s, ccfg, B, act, *cst, o, traj.done + (size_t)(t + 1) * B));
+    uint8_t* done_next = traj.done + (size_t)(t + 1) * B;
+    if (env_kind == MAGPO_ENV_LBF)
+      MAGPO_TRY(lbf_step_launch(s, static_cast<const MagpoLbfCfg*>(env_cfg), B, act, *static_cast<MagpoLbfState*>(env_state), o, done_next));
+    else
+      MAGPO_TRY(coordsum_step_launch(s, static_cast<const MagpoCoordSumCfg*>(env_cfg), B, act,
+                                     *static_cast<MagpoCoordSumState*>(env_state), o, done_next));
   }
   // bootstrap value (rec_magpo.py:202-208): a full get_actions of which only the value is kept
   MAGPO_TRY(get_actions(s, net, B, E, gp, gtp, kappa, traj.agents_view + (size_t)T * BA * d, nullptr,

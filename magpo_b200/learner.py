@@ -103,6 +103,7 @@ class CoordSumVec:
     (mava/coordsum/env.py, mava/utils/make_env.py:90-104,202-218) as device arrays."""
 
     kind = L.ENV_COORDSUM
+    reset_fn, step_fn = "magpo_coordsum_reset", "magpo_coordsum_step"
 
     def __init__(self, num_agents: int, num_actions: int, time_limit: int = 100, maxval: int | None = None):
         self.num_agents, self.num_actions, self.time_limit = num_agents, num_actions, time_limit
@@ -128,6 +129,41 @@ class CoordSumVec:
 
     def state_struct(self, st: dict) -> L.CoordSumState:
         return L.struct_of(L.CoordSumState, **st)
+
+
+class LbfVec:
+    """B LevelBasedForaging envs (jumanji 1.1.0 `RandomGenerator(**task_config)`, `time_limit` from env.kwargs) under
+    RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(LbfWrapper(.)))) (mava/utils/make_env.py:90-135, wrappers/jumanji.py:171-208)
+    as device arrays. The dynamics are restated from the un-vendored dependency; see oracle/lbf.py."""
+
+    kind = L.ENV_LBF
+    reset_fn, step_fn = "magpo_lbf_reset", "magpo_lbf_step"
+
+    def __init__(self, grid_size: int = 8, fov: int = 2, num_agents: int = 2, num_food: int = 2, max_agent_level: int = 2,
+                 force_coop: bool = True, time_limit: int = 100, agent_mask_rows: bool = True):
+        self.grid_size, self.fov, self.num_agents, self.num_food = grid_size, fov, num_agents, num_food
+        self.max_agent_level, self.force_coop, self.time_limit = max_agent_level, bool(force_coop), time_limit
+        self.cfg = L.LbfCfg(grid_size, fov, num_agents, num_food, max_agent_level, int(bool(force_coop)), time_limit,
+                            int(bool(agent_mask_rows)))
+
+    @property
+    def obs_dim(self):
+        return self.num_agents + 3 * (self.num_food + self.num_agents)
+
+    @property
+    def action_dim(self):
+        return 6
+
+    def alloc_state(self, B: int, dev) -> dict:
+        i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+        A, F = self.num_agents, self.num_food
+        z = lambda *s, dt=i32: torch.zeros(*s, dtype=dt, device=dev)
+        return dict(agent_pos=z(B, A, 2), agent_level=z(B, A), agent_loading=z(B, A, dt=u8), food_pos=z(B, F, 2),
+                    food_level=z(B, F), food_eaten=z(B, F, dt=u8), step_count=z(B), key=z(B, 2), metrics_key=z(B, 2),
+                    running_return=z(B, dt=f32), running_length=z(B), episode_return=z(B, dt=f32), episode_length=z(B))
+
+    def state_struct(self, st: dict) -> L.LbfState:
+        return L.struct_of(L.LbfState, **st)
 
 
 def alloc_timestep(B, A, d, a, dev) -> dict:
@@ -234,7 +270,7 @@ class MagpoLearner:
         ts = dict(self.ts)
         ts.update(agents_view=self.traj["agents_view"][0], action_mask=self.traj["action_mask"][0],
                   step_count=self.traj["step_count"][0])
-        L.call("magpo_coordsum_reset", L.stream_ptr(), C.byref(self.env.cfg), B, L.ptr(keys),
+        L.call(self.env.reset_fn, L.stream_ptr(), C.byref(self.env.cfg), B, L.ptr(keys),
                self.env.state_struct(self.env_state), L.struct_of(L.TimeStep, **ts))
         self.traj["done"][0].zero_()
         for h in self.hs.values():

@@ -25,7 +25,7 @@ import torch
 from . import _lib as L
 from . import init as minit
 from .config import Config, check_total_timesteps, compose
-from .learner import CoordSumVec, MagpoLearner, SystemConfig, param_views
+from .learner import CoordSumVec, LbfVec, MagpoLearner, SystemConfig, param_views
 
 
 # ----------------------------------------------------------------------------- types (systems/gpo/types.py:25-83, mava/types.py:199-207)
@@ -97,16 +97,25 @@ COORDSUM_REGISTRY = {
 }
 
 
-def make_env(config: Config) -> CoordSumVec:
-    """mava/utils/make_env.py:90-104 for the env whose dynamics live in the tree (CoordSum); the training wrapper stack
-    RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(CoordSumWrapper))) is part of the env-step kernel."""
-    if config.env.env_name != "CoordSum":
-        raise NotImplementedError(f"{config.env.env_name}: only CoordSum dynamics are built (Jumanji is not vendored)")
-    kw = dict(COORDSUM_REGISTRY.get(config.env.scenario.task_name, {}))
-    kw.update(config.env.scenario.get("task_config", {}))
-    kw.update(config.env.get("kwargs", {}))
-    return CoordSumVec(num_agents=kw["num_agents"], num_actions=kw["num_actions"], time_limit=kw.get("time_limit", 100),
-                       maxval=kw.get("maxval"))
+def make_env(config: Config):
+    """mava/utils/make_env.py:90-135,202-218: CoordSum (dynamics in the reference tree) and LevelBasedForaging (jumanji 1.1.0
+    `RandomGenerator(**scenario.task_config)` + `{**env.kwargs, **scenario.env_kwargs}`). The training wrapper stack
+    RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(<Env>Wrapper))) is part of the env-step kernel."""
+    name = config.env.env_name
+    if name == "CoordSum":
+        kw = dict(COORDSUM_REGISTRY.get(config.env.scenario.task_name, {}))
+        kw.update(config.env.scenario.get("task_config", {}))
+        kw.update(config.env.get("kwargs", {}))
+        return CoordSumVec(num_agents=kw["num_agents"], num_actions=kw["num_actions"], time_limit=kw.get("time_limit", 100),
+                           maxval=kw.get("maxval"))
+    if name == "LevelBasedForaging":
+        kw = dict(config.env.scenario.task_config)
+        env_kw = {**dict(config.env.get("kwargs", {})), **dict(config.env.scenario.get("env_kwargs", {}) or {})}
+        unknown = set(env_kw) - {"time_limit"}
+        if unknown:
+            raise NotImplementedError(f"LevelBasedForaging kwargs {sorted(unknown)}: only the VectorObserver defaults are built")
+        return LbfVec(**kw, time_limit=int(env_kw.get("time_limit", 100)))
+    raise NotImplementedError(f"{name}: only CoordSum and LevelBasedForaging dynamics are built (RobotWarehouse: not yet)")
 
 
 def _system_config(config: Config) -> SystemConfig:

@@ -22,6 +22,17 @@ import torch
 from . import coordsum, nets, prng
 
 
+def env_module(spec):
+    """The env restatement matching `spec` (make_env.py:202-218 picks the maker by env name)."""
+    if isinstance(spec, coordsum.CoordSumSpec):
+        return coordsum
+    from . import lbf
+
+    if isinstance(spec, lbf.LbfSpec):
+        return lbf
+    raise TypeError(f"no env restatement for {type(spec).__name__}")
+
+
 @dataclass
 class SysCfg:
     num_envs: int = 16
@@ -218,7 +229,7 @@ def rollout(spec, ncfg: nets.NetCfg, sys: SysCfg, gp_np, ap_np, slot):
                 ap, ncfg, torch.tensor(slot["hstates"]["policy"]), obs_f[None], torch.tensor(last_done)[None], torch.tensor(ob["action_mask"])[None]
             )
             prev_done = np.repeat((ts["step_type"] == coordsum.STEP_LAST)[:, None], A, axis=1)
-            env_state, new_ts = coordsum.step(spec, slot["env_state"], action)
+            env_state, new_ts = env_module(spec).step(spec, slot["env_state"], action)
             done = new_ts["step_type"] == coordsum.STEP_LAST
             sable = tuple(np.where(done[:, None, None, None, None], 0.0, h.numpy()).astype(np.float32) for h in new_hs)
             traj["done"].append(prev_done)
@@ -291,7 +302,7 @@ def learner_setup(spec, ncfg: nets.NetCfg, sys: SysCfg, seed: int = 42, n_device
     ap = nets.init_actor_params(ncfg, param_seed + 1)
     slots = []
     for u in range(U):
-        env_state, ts = coordsum.reset(spec, env_keys[device, u])
+        env_state, ts = env_module(spec).reset(spec, env_keys[device, u])
         slots.append(dict(key=step_key.copy(), env_state=env_state, timestep=ts,
                           dones=np.zeros((E, ncfg.n_agents), bool), hstates=init_hstates(ncfg, E)))
     return dict(guider_params=gp, actor_params=ap, guider_opt=init_opt(gp), actor_opt=init_opt(ap), slots=slots)

@@ -73,3 +73,28 @@ def test_actor_network_apply_matches_oracle(dev):
     assert rel_err(got[mask], l_ref.numpy()[mask]) < 1e-4
     assert (got[~mask] == np.finfo(np.float32).min).all()
     assert rel_err(carry.cpu().numpy(), h_ref.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("greedy", [True, False])
+def test_evaluator_matches_oracle(dev, greedy):
+    """evaluator.py:82-163,188-208 on the GPU against the CPU restatement: same keys -> same per-episode returns / lengths."""
+    from magpo_b200 import evaluator as mev
+    from oracle import coordsum as ocs
+    from oracle import evaluator as oev
+    from oracle import prng as oprng
+
+    cfg, env, (learn, actor_network, state) = _setup(dev, extra=[f"arch.evaluation_greedy={greedy}"])
+    learn(state)  # move the policy off its initialisation
+    lrn = actor_network.lrn
+    n, loops = 5, 2
+    key = oprng.split(oprng.prng_key(3))[1]
+    eval_fn = mev.get_eval_fn(env, actor_network, cfg, absolute_metric=False, n_envs=n, episode_loops=loops)
+    got = eval_fn(lrn.actor, key)
+    _, ap = lrn.get_params()
+    spec = ocs.CoordSumSpec(**rm.COORDSUM_REGISTRY[cfg.env.scenario.task_name])
+    ncfg = onets.NetCfg(env.num_agents, env.obs_dim, env.action_dim)
+    ref = oev.eval_fn(spec, ncfg, {k: v.cpu().numpy() for k, v in ap.items()}, key, n, loops, greedy=greedy)
+    assert got["episode_length"].shape == (n * loops,)
+    assert (got["episode_length"].cpu().numpy() == ref["episode_length"]).all()
+    assert np.allclose(got["episode_return"].cpu().numpy(), ref["episode_return"], rtol=0, atol=1e-5)
+    assert got["steps_per_second"] > 0
