@@ -282,7 +282,8 @@ def run():
             tf = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
             traffic = None
             try:  # DRAM bytes per launch of the same kernel from the committed ncu launch list (profiles/)
-                prof = json.load(open(os.path.join(ROOT, "profiles", "r1_minibatch_launches.json")))
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r1_lbf_minibatch_launches.json" if args.env == "lbf" else
+                                                  "r1_minibatch_launches.json")))
                 k = prof["kernels"]["gemm_tc_kernel"]
                 traffic = k["dram_bytes"] / k["launches"]
             except Exception:

@@ -165,6 +165,43 @@ int magpo_lbf_reset(magpo_stream_t s, const MagpoLbfCfg* cfg, int32_t B, const u
 int magpo_lbf_step(magpo_stream_t s, const MagpoLbfCfg* cfg, int32_t B, const int32_t* action,
                    MagpoLbfState st, MagpoTimeStep ts);
 
+/* RobotWarehouse (jumanji 1.1.0 @ 9ced6b8 `environments/routing/robot_warehouse`, un-vendored third-party dependency, restated — see
+ * oracle/rware.py; built by mava/utils/make_env.py:107-135 from configs/env/scenario/{tiny-4ag,small-4ag,...}.yaml task_config) under
+ * RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(RwareWrapper(env)))) — mava/wrappers/jumanji.py:137-168.
+ * H = (column_height+1)*shelf_rows+2, W = 3*shelf_columns+1, S = number of non-highway cells, obs_dim d = num_agents + 8 +
+ * 7*(2*sensor_range+1)^2, action_dim 5. Limits: H*W <= 1024, num_agents <= 8, request_queue_size <= 16, sensor_range <= 2. */
+typedef struct MagpoRwareCfg {
+  int32_t column_height, shelf_rows, shelf_columns, num_agents, sensor_range, request_queue_size, time_limit;
+} MagpoRwareCfg;
+
+/* RecordEpisodeMetricsState(env_state = robot_warehouse State(grid, agents, shelves, request_queue, step_count, action_mask, key)).
+ * Positions are (x, y) = (row, col). */
+typedef struct MagpoRwareState {
+  int32_t* grid;            /* [B,2,H,W]  channel 0: shelf id + 1, channel 1: agent id + 1 */
+  int32_t* agent_pos;       /* [B,A,2] */
+  int32_t* agent_dir;       /* [B,A]     UP 0, RIGHT 1, DOWN 2, LEFT 3 */
+  uint8_t* agent_carry;     /* [B,A] */
+  int32_t* shelf_pos;       /* [B,S,2] */
+  uint8_t* shelf_req;       /* [B,S] */
+  int32_t* request_queue;   /* [B,Q] */
+  int32_t* step_count;      /* [B] */
+  uint8_t* action_mask;     /* [B,A,5] */
+  uint32_t* key;            /* [B,2] */
+  uint32_t* metrics_key;    /* [B,2]  RecordEpisodeMetricsState.key */
+  float* running_return;    /* [B] */
+  int32_t* running_length;  /* [B] */
+  float* episode_return;    /* [B] */
+  int32_t* episode_length;  /* [B] */
+} MagpoRwareState;
+
+/* Number of shelves S of a layout (for sizing shelf_pos / shelf_req); negative error code on a bad config. */
+int32_t magpo_rware_num_shelves(const MagpoRwareCfg* cfg);
+/* vmap(env.reset)(keys) / vmap(env.step)(state, action) for the RWARE stack; same contract as the CoordSum pair. */
+int magpo_rware_reset(magpo_stream_t s, const MagpoRwareCfg* cfg, int32_t B, const uint32_t* keys,
+                      MagpoRwareState st, MagpoTimeStep ts);
+int magpo_rware_step(magpo_stream_t s, const MagpoRwareCfg* cfg, int32_t B, const int32_t* action,
+                     MagpoRwareState st, MagpoTimeStep ts);
+
 /* ------------------------------------------------------------------ GAE
  * calculate_gae — mava/utils/multistep.py:24-68. Layout [T,B,A] (time-major), `done` is per env
  * [T,B] (Transition.done is constant over agents, rec_magpo.py:172), last_done [B]. */

@@ -65,6 +65,17 @@ class LbfState(C.Structure):
                                   "episode_length")]
 
 
+class RwareCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("column_height", "shelf_rows", "shelf_columns", "num_agents", "sensor_range",
+                                         "request_queue_size", "time_limit")]
+
+
+class RwareState(C.Structure):
+    _fields_ = [(n, vp) for n in ("grid", "agent_pos", "agent_dir", "agent_carry", "shelf_pos", "shelf_req", "request_queue",
+                                  "step_count", "action_mask", "key", "metrics_key", "running_return", "running_length",
+                                  "episode_return", "episode_length")]
+
+
 class SableHState(C.Structure):
     _fields_ = [(n, vp) for n in ("encoder", "decoder_self", "decoder_cross")]
 

@@ -11,4 +11,8 @@ int coordsum_step_launch(cudaStream_t s, const MagpoCoordSumCfg* cfg, int B, con
 int lbf_step_launch(cudaStream_t s, const MagpoLbfCfg* cfg, int B, const int32_t* action, MagpoLbfState st,
                     MagpoTimeStep ts, uint8_t* done_out);
 
+// vmap(env.step) for RobotWarehouse.
+int rware_step_launch(cudaStream_t s, const MagpoRwareCfg* cfg, int B, const int32_t* action, MagpoRwareState st,
+                      MagpoTimeStep ts, uint8_t* done_out);
+
 }  // namespace magpo

@@ -237,7 +237,7 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
                   void* workspace, size_t workspace_bytes) {
   MAGPO_TRY(check_net(net));
   if (!sys || !env_cfg || !env_state || !guider || !actor || !key || !policy_h || !workspace) return MAGPO_ERR_ARG;
-  if (env_kind != MAGPO_ENV_COORDSUM && env_kind != MAGPO_ENV_LBF) return MAGPO_ERR_UNSUPPORTED;  // RWARE: not built
+  if (env_kind != MAGPO_ENV_COORDSUM && env_kind != MAGPO_ENV_LBF && env_kind != MAGPO_ENV_RWARE) return MAGPO_ERR_UNSUPPORTED;
   cudaStream_t s = as_stream(s_);
   const int A = net->n_agents, d = net->obs_dim, a = net->action_dim;
   const int T = sys->rollout_length, E = sys->num_envs;
@@ -301,7 +301,10 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
     o.episode_length = traj.episode_length + (size_t)t * B;
     o.is_terminal_step = traj.is_terminal_step + (size_t)t * B;
     uint8_t* done_next = traj.done + (size_t)(t + 1) * B;
-    if (env_kind == MAGPO_ENV_LBF)
+    if (env_kind == MAGPO_ENV_RWARE)
+      MAGPO_TRY(rware_step_launch(s, static_cast<const MagpoRwareCfg*>(env_cfg), B, act, *static_cast<MagpoRwareState*>(env_state), o,
+                                  done_next));
+    else if (env_kind == MAGPO_ENV_LBF)
       MAGPO_TRY(lbf_step_launch(s, static_cast<const MagpoLbfCfg*>(env_cfg), B, act, *static_cast<MagpoLbfState*>(env_state), o, done_next));
     else
       MAGPO_TRY(coordsum_step_launch(s, static_cast<const MagpoCoordSumCfg*>(env_cfg), B, act,

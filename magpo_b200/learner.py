@@ -166,6 +166,44 @@ class LbfVec:
         return L.struct_of(L.LbfState, **st)
 
 
+class RwareVec:
+    """B RobotWarehouse envs (jumanji 1.1.0 `RandomGenerator(**task_config)`, `time_limit` from env.kwargs) under
+    RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(RwareWrapper(.)))) (mava/utils/make_env.py:90-135, wrappers/jumanji.py:137-168)
+    as device arrays. The dynamics are restated from the un-vendored dependency; see oracle/rware.py."""
+
+    kind = L.ENV_RWARE
+    reset_fn, step_fn = "magpo_rware_reset", "magpo_rware_step"
+
+    def __init__(self, column_height: int = 8, shelf_rows: int = 1, shelf_columns: int = 3, num_agents: int = 4,
+                 sensor_range: int = 1, request_queue_size: int = 4, time_limit: int = 500):
+        self.num_agents, self.sensor_range, self.request_queue_size, self.time_limit = num_agents, sensor_range, request_queue_size, time_limit
+        self.grid_size = ((column_height + 1) * shelf_rows + 2, 3 * shelf_columns + 1)
+        self.cfg = L.RwareCfg(column_height, shelf_rows, shelf_columns, num_agents, sensor_range, request_queue_size, time_limit)
+        self.num_shelves = int(L.lib().magpo_rware_num_shelves(C.byref(self.cfg)))
+        L.check(min(self.num_shelves, 0), "magpo_rware_num_shelves")
+
+    @property
+    def obs_dim(self):
+        return self.num_agents + 8 + 7 * (2 * self.sensor_range + 1) ** 2
+
+    @property
+    def action_dim(self):
+        return 5
+
+    def alloc_state(self, B: int, dev) -> dict:
+        i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+        A, S, Q = self.num_agents, self.num_shelves, self.request_queue_size
+        H, W = self.grid_size
+        z = lambda *s, dt=i32: torch.zeros(*s, dtype=dt, device=dev)
+        return dict(grid=z(B, 2, H, W), agent_pos=z(B, A, 2), agent_dir=z(B, A), agent_carry=z(B, A, dt=u8), shelf_pos=z(B, S, 2),
+                    shelf_req=z(B, S, dt=u8), request_queue=z(B, Q), step_count=z(B), action_mask=z(B, A, 5, dt=u8), key=z(B, 2),
+                    metrics_key=z(B, 2), running_return=z(B, dt=f32), running_length=z(B), episode_return=z(B, dt=f32),
+                    episode_length=z(B))
+
+    def state_struct(self, st: dict) -> L.RwareState:
+        return L.struct_of(L.RwareState, **st)
+
+
 def alloc_timestep(B, A, d, a, dev) -> dict:
     f32, i32, u8 = torch.float32, torch.int32, torch.uint8
     return dict(step_type=torch.zeros(B, dtype=torch.int8, device=dev), reward=torch.zeros(B, A, dtype=f32, device=dev),

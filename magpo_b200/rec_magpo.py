@@ -25,7 +25,7 @@ import torch
 from . import _lib as L
 from . import init as minit
 from .config import Config, check_total_timesteps, compose
-from .learner import CoordSumVec, LbfVec, MagpoLearner, SystemConfig, param_views
+from .learner import CoordSumVec, LbfVec, RwareVec, MagpoLearner, SystemConfig, param_views
 
 
 # ----------------------------------------------------------------------------- types (systems/gpo/types.py:25-83, mava/types.py:199-207)
@@ -98,7 +98,7 @@ COORDSUM_REGISTRY = {
 
 
 def make_env(config: Config):
-    """mava/utils/make_env.py:90-135,202-218: CoordSum (dynamics in the reference tree) and LevelBasedForaging (jumanji 1.1.0
+    """mava/utils/make_env.py:90-135,202-218: CoordSum (dynamics in the reference tree), LevelBasedForaging and RobotWarehouse (jumanji 1.1.0
     `RandomGenerator(**scenario.task_config)` + `{**env.kwargs, **scenario.env_kwargs}`). The training wrapper stack
     RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(<Env>Wrapper))) is part of the env-step kernel."""
     name = config.env.env_name
@@ -115,7 +115,13 @@ def make_env(config: Config):
         if unknown:
             raise NotImplementedError(f"LevelBasedForaging kwargs {sorted(unknown)}: only the VectorObserver defaults are built")
         return LbfVec(**kw, time_limit=int(env_kw.get("time_limit", 100)))
-    raise NotImplementedError(f"{name}: only CoordSum and LevelBasedForaging dynamics are built (RobotWarehouse: not yet)")
+    if name == "RobotWarehouse":
+        env_kw = {**dict(config.env.get("kwargs", {})), **dict(config.env.scenario.get("env_kwargs", {}) or {})}
+        unknown = set(env_kw) - {"time_limit"}
+        if unknown:
+            raise NotImplementedError(f"RobotWarehouse kwargs {sorted(unknown)} are not built")
+        return RwareVec(**dict(config.env.scenario.task_config), time_limit=int(env_kw.get("time_limit", 500)))
+    raise NotImplementedError(f"{name}: only CoordSum, LevelBasedForaging and RobotWarehouse dynamics are built")
 
 
 def _system_config(config: Config) -> SystemConfig:
@@ -285,7 +291,7 @@ def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, 
 
 
 def run_experiment(config: Config, device=None, log=print) -> float:
-    """rec_magpo.py:688-831 without the evaluator / logger / checkpointer backends: `num_evaluation` calls of `learn`, each
+    """rec_magpo.py:688-831 without the logger / checkpointer backends: `num_evaluation` calls of `learn`, each
     `num_updates_per_eval` updates, reporting steps per second and the mean return of the episodes that ended."""
     import torch.distributed as dist
 
@@ -296,11 +302,24 @@ def run_experiment(config: Config, device=None, log=print) -> float:
     env = make_env(config)
     key, key_e, actor_net_key, net_key = minit.split(minit.prng_key(int(config.system.seed)), 4, device or "cuda:0")
     allreduce = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
-    learn, _, state = learner_setup(env, (key, actor_net_key, net_key), config, device=device, allreduce=allreduce, rank=rank,
-                                    world_size=world)
+    learn, actor_network, state = learner_setup(env, (key, actor_net_key, net_key), config, device=device, allreduce=allreduce,
+                                                rank=rank, world_size=world)
+    lrn = actor_network.lrn
+    # evaluator of the learner policy (rec_magpo.py:706-710): episodes sharded over the devices, no collective (evaluator.py:163)
+    from . import evaluator as mev
+
+    evaluator = mev.get_eval_fn(env, actor_network, config, absolute_metric=False, n_devices=world)
     steps_per_rollout = (world * config.system.num_updates_per_eval * config.system.rollout_length *
                          config.system.update_batch_size * config.arch.num_envs)
-    last = float("nan")
+
+    def world_mean(x: torch.Tensor) -> float:
+        m = x.float().mean().reshape(1).to(lrn.dev)
+        if world > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.SUM)
+            m /= world
+        return float(m)
+
+    max_episode_return, best_params, eval_performance = float("-inf"), None, float("nan")
     for ev in range(int(config.arch.num_evaluation)):
         t0 = time.perf_counter()
         out = learn(state)
@@ -308,13 +327,30 @@ def run_experiment(config: Config, device=None, log=print) -> float:
         dt = time.perf_counter() - t0
         state = out.learner_state
         term = out.episode_metrics["is_terminal_step"]
-        if bool(term.any()):
-            last = float(out.episode_metrics["episode_return"][term].mean())
+        train_return = float(out.episode_metrics["episode_return"][term].mean()) if bool(term.any()) else float("nan")
+        # rec_magpo.py:770-777: key_e, *eval_keys = split(key_e, n_devices + 1); evaluator(trained_params, eval_keys, ...)
+        ks = minit.split(key_e, world + 1, device or "cuda:0")
+        key_e, eval_key = ks[0], ks[1 + rank]
+        eval_metrics = evaluator(lrn.actor, eval_key)
+        eval_performance = world_mean(eval_metrics[config.env.eval_metric])
+        if config.arch.absolute_metric and max_episode_return <= eval_performance:  # rec_magpo.py:787-789
+            best_params, max_episode_return = lrn.actor.clone(), eval_performance
         if rank == 0:
             log(f"eval {ev}: steps_per_second={steps_per_rollout / dt:.0f} timestep={steps_per_rollout * (ev + 1)} "
-                f"episode_return={last:.4f} total_loss={float(out.train_metrics['total_loss'].mean()):.5f} "
+                f"train_episode_return={train_return:.4f} eval_{config.env.eval_metric}={eval_performance:.4f} "
+                f"eval_steps_per_second={eval_metrics['steps_per_second']:.0f} "
+                f"total_loss={float(out.train_metrics['total_loss'].mean()):.5f} "
                 f"value_loss={float(out.train_metrics['value_loss'].mean()):.5f} entropy={float(out.train_metrics['entropy'].mean()):.4f}")
-    return last
+    if config.arch.absolute_metric and best_params is not None:  # rec_magpo.py:798-812: 10x episodes with the best parameters
+        abs_evaluator = mev.get_eval_fn(env, actor_network, config, absolute_metric=True, n_devices=world)
+        ks = minit.split(key_e, world + 1, device or "cuda:0")
+        abs_metrics = abs_evaluator(best_params, ks[1 + rank])
+        if rank == 0:
+            log(f"absolute metric: {config.env.eval_metric}={world_mean(abs_metrics[config.env.eval_metric]):.4f} over "
+                f"{world * abs_metrics['episode_return'].numel()} episodes")
+        elif world > 1:
+            world_mean(abs_metrics[config.env.eval_metric])
+    return eval_performance
 
 
 def main(argv=None) -> float:

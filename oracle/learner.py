@@ -30,6 +30,10 @@ def env_module(spec):
 
     if isinstance(spec, lbf.LbfSpec):
         return lbf
+    from . import rware
+
+    if isinstance(spec, rware.RwareSpec):
+        return rware
     raise TypeError(f"no env restatement for {type(spec).__name__}")
 
 

@@ -98,3 +98,17 @@ def test_evaluator_matches_oracle(dev, greedy):
     assert (got["episode_length"].cpu().numpy() == ref["episode_length"]).all()
     assert np.allclose(got["episode_return"].cpu().numpy(), ref["episode_return"], rtol=0, atol=1e-5)
     assert got["steps_per_second"] > 0
+
+
+@pytest.mark.parametrize("env_args", [[], ["env=lbf"], ["env=rware", "env/scenario=tiny-4ag", "env.kwargs.time_limit=30"]])
+def test_run_experiment_trains_and_evaluates(dev, env_args):
+    """rec_magpo.py:688-815 end to end (`python -m magpo_b200.rec_magpo env=...`): learn, evaluate the learner policy after every
+    `learn`, absolute metric with the best parameters at the end — on all three env families."""
+    lines = []
+    cfg = compose("default/rec_magpo", [*env_args, "arch.num_envs=8", "system.rollout_length=8", "system.num_updates=2",
+                                        "arch.num_evaluation=2", "system.total_timesteps=~", "arch.num_eval_episodes=4",
+                                        "arch.num_absolute_metric_eval_episodes=8"])
+    perf = rm.run_experiment(cfg, device=dev, log=lines.append)
+    assert len(lines) == 3, lines
+    assert lines[0].startswith("eval 0:") and "eval_episode_return=" in lines[0] and "absolute metric" in lines[-1]
+    assert np.isfinite(perf)

@@ -22,4 +22,7 @@ done
 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"sable_step_kernel" -s 1 -c 1 -f \
   -o gpurun_out/full_${TAG}_sable_step_kernel python tools/profile_update.py --rollout-steps 4 > gpurun_out/ncu_full_retention_fwd.log 2>&1
 tail -1 gpurun_out/ncu_full_retention_fwd.log
+timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"lbf_step_kernel" -s 1 -c 1 -f \
+  -o gpurun_out/full_${TAG}_lbf_step_kernel python tools/profile_update.py --rollout-steps 4 > gpurun_out/ncu_full_lbf_step.log 2>&1
+tail -1 gpurun_out/ncu_full_lbf_step.log
 ls -la gpurun_out/full_${TAG}_*.ncu-rep

@@ -11,16 +11,17 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from magpo_b200 import init as minit  # noqa: E402
-from magpo_b200.learner import CoordSumVec, MagpoLearner, SystemConfig  # noqa: E402
+from magpo_b200.learner import CoordSumVec, LbfVec, MagpoLearner, SystemConfig  # noqa: E402
 
 ap = argparse.ArgumentParser()
+ap.add_argument("--env", default="lbf", choices=["lbf", "coordsum"])
 ap.add_argument("--num-envs", type=int, default=4096)
 ap.add_argument("--update-batch-size", type=int, default=2)
 ap.add_argument("--rollout-length", type=int, default=128)
 ap.add_argument("--rollout-steps", type=int, default=0)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-env = CoordSumVec(num_agents=3, num_actions=10, time_limit=100, maxval=30)
+env = LbfVec() if args.env == "lbf" else CoordSumVec(num_agents=3, num_actions=10, time_limit=100, maxval=30)
 T = args.rollout_steps or args.rollout_length
 sysc = SystemConfig(num_envs=args.num_envs, update_batch_size=args.update_batch_size, rollout_length=T)
 lrn = MagpoLearner(env, sysc, device=dev, graph_rollout=False)
