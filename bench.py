@@ -28,6 +28,10 @@ WORKLOADS = {
     "lbf": dict(kw=dict(grid_size=8, fov=2, num_agents=2, num_food=2, max_agent_level=2, force_coop=True, time_limit=100),
                 label="LevelBasedForaging 2s-8x8-2p-2f-coop (A=2, a=6, d=14; BASELINE configs[1]; dynamics restated from jumanji "
                       "1.1.0, see oracle/lbf.py)"),
+    "rware": dict(kw=dict(column_height=8, shelf_rows=1, shelf_columns=3, num_agents=4, sensor_range=1, request_queue_size=4,
+                          time_limit=500),
+                  label="RobotWarehouse tiny-4ag (A=4, a=5, d=75; BASELINE configs[2], 8192 envs / 8 GPUs = --num-envs 1024 "
+                        "--update-batch-size 1 per GPU; dynamics restated from jumanji 1.1.0, see oracle/rware.py)"),
     "coordsum": dict(kw=dict(num_agents=3, num_actions=10, time_limit=100, maxval=30),
                      label="CoordSum 3x10-30 (A=3, a=10, d=4; BASELINE configs[4] sweep point)"),
 }
@@ -94,12 +98,12 @@ def run_reference(args, as_baseline=False):
     """The CPU restatement (oracle/) of the same step on the host cores: the reference itself is JAX-only and
     cannot be installed here (no jax/flax/optax/jumanji wheels), so kind = "port"."""
     import torch
-    from oracle import coordsum as ocs, lbf as olbf, learner as olr, nets as onets
+    from oracle import coordsum as ocs, lbf as olbf, learner as olr, nets as onets, rware as orw
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     E = 16  # bounded sample of the workload: 16 of the envs per slot, everything else as configured
-    spec = (olbf.LbfSpec if args.env == "lbf" else ocs.CoordSumSpec)(**WORKLOADS[args.env]["kw"])
+    spec = {"lbf": olbf.LbfSpec, "rware": orw.RwareSpec, "coordsum": ocs.CoordSumSpec}[args.env](**WORKLOADS[args.env]["kw"])
     ncfg = onets.NetCfg(spec.num_agents, spec.obs_dim, spec.action_dim)
     osys = olr.SysCfg(num_envs=E, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length)
     state = olr.learner_setup(spec, ncfg, osys, seed=42)
@@ -154,7 +158,7 @@ def run():
 
     from magpo_b200 import _lib as L
     from magpo_b200 import init as minit
-    from magpo_b200.learner import CoordSumVec, LbfVec, MagpoLearner, SystemConfig
+    from magpo_b200.learner import CoordSumVec, LbfVec, MagpoLearner, RwareVec, SystemConfig
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -165,7 +169,7 @@ def run():
         dist.init_process_group("nccl", device_id=dev)
         allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
-    env = (LbfVec if args.env == "lbf" else CoordSumVec)(**WORKLOADS[args.env]["kw"])
+    env = {"lbf": LbfVec, "rware": RwareVec, "coordsum": CoordSumVec}[args.env](**WORKLOADS[args.env]["kw"])
     sysc = SystemConfig(num_envs=args.num_envs, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length,
                         chunk_envs=args.chunk_envs)
     lrn = MagpoLearner(env, sysc, device=dev, allreduce=allreduce, world_size=world)

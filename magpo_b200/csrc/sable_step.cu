@@ -222,7 +222,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
   // ------------------------------------------------------------------ encoder
   float2 xin[RE], cur[RE];
   int stp[RE];
-  {
+  if constexpr (KMAX > 0) {
     float2 w[KMAX];
     float sc[KMAX];
 #pragma unroll
@@ -250,6 +250,48 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
         z.y = fmaf(o, w[k].y, z.y);
       }
       xin[r] = rmsnorm(make_float2(gelu_tanh(z.x), gelu_tanh(z.y)), ln);
+      stp[r] = __ldg(s.step + row);
+      cur[r] = f2add(xin[r], pe_row(s.pe, stp[r], s.max_step, lane));
+    }
+  } else {
+    // wide observations (RWARE d = 75, the larger LBF scenarios): the embedding runs over chunks of 16 features; the RMSNorm
+    // factor of the observation is linear in the projection, so it is applied once after the last chunk
+    float2 zacc[RE];
+    float ssq[RE];
+#pragma unroll
+    for (int r = 0; r < RE; ++r) {
+      zacc[r] = make_float2(0.f, 0.f);
+      ssq[r] = 0.f;
+    }
+    for (int k0 = 0; k0 < s.d; k0 += 16) {
+      float2 w[16];
+      float sc[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int kk = k0 + k;
+        w[k] = kk < s.d ? ldg2(p.Wobs + (size_t)kk * kD + 2 * lane) : make_float2(0.f, 0.f);
+        sc[k] = kk < s.d ? __ldg(p.obs_scale + kk) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < RE; ++r) {
+        const int64_t row = (int64_t)b[r / A] * A + (r % A);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float x = (k0 + k) < s.d ? __ldg(s.obs + row * s.d + k0 + k) : 0.f;
+          ssq[r] = fmaf(x, x, ssq[r]);
+          const float o = x * sc[k];
+          zacc[r].x = fmaf(o, w[k].x, zacc[r].x);
+          zacc[r].y = fmaf(o, w[k].y, zacc[r].y);
+        }
+      }
+    }
+    const float2 ln = ldg2(p.ln + 2 * lane);
+    const float inv_d = 1.0f / (float)s.d;
+#pragma unroll
+    for (int r = 0; r < RE; ++r) {
+      const int64_t row = (int64_t)b[r / A] * A + (r % A);
+      const float rstd0 = rsqrtf(ssq[r] * inv_d + kEps);
+      xin[r] = rmsnorm(make_float2(gelu_tanh(zacc[r].x * rstd0), gelu_tanh(zacc[r].y * rstd0)), ln);
       stp[r] = __ldg(s.step + row);
       cur[r] = f2add(xin[r], pe_row(s.pe, stp[r], s.max_step, lane));
     }
@@ -545,18 +587,20 @@ int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
     attr = true;
   }
   if (s.d <= 4) sable_step_kernel<A, 4><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
   else if (s.d <= 8) sable_step_kernel<A, 8><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
-  else sable_step_kernel<A, 16><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
+  else if (s.d <= 16) sable_step_kernel<A, 16><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
+  else sable_step_kernel<A, 0><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
 
 }  // namespace
 
-bool sable_step_supported(int A, int d, int a) { return A >= 1 && A <= 4 && d >= 1 && d <= 16 && a >= 1 && a <= 32; }
+bool sable_step_supported(int A, int d, int a) { return A >= 1 && A <= 4 && d >= 1 && d <= 128 && a >= 1 && a <= 32; }
 
 size_t sable_step_table_floats(const MagpoNetCfg* net) { return (size_t)(net->action_dim + 1 + net->max_step_count + 1) * 4 * kD; }
 

@@ -311,7 +311,7 @@ obs_embed_fwd_kernel(int64_t R, int d, const float* __restrict__ obs, const floa
 }
 
 template <int KMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 obs_embed_bwd_kernel(int64_t R, int d, const float* __restrict__ obs, const float* __restrict__ obs_scale,
                      const float* __restrict__ Wobs, const float* __restrict__ dz0, float* __restrict__ dWobs,
                      float* __restrict__ dscale) {
@@ -329,15 +329,23 @@ obs_embed_bwd_kernel(int64_t R, int d, const float* __restrict__ obs, const floa
   }
   const float inv_d = 1.0f / (float)d;
   const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), stride = (int64_t)gridDim.x * 8;
+  // software-pipelined over rows: the loads of the next group of UN rows are in flight while the current group is reduced
+  float x[UN][KMAX], xn_[UN][KMAX];
+  float2 dz[UN], dzn[UN];
+#pragma unroll
+  for (int u = 0; u < UN; ++u) {
+    const int64_t row = w0 + u * stride;
+    const bool ok = row < R;
+    dz[u] = ok ? ld2(dz0, row, kD, lane) : make_float2(0.f, 0.f);
+    load_thin_row<KMAX>(x[u], obs, row, d, d, ok);
+  }
   for (int64_t row0 = w0; row0 < R; row0 += UN * stride) {
-    float x[UN][KMAX];
-    float2 dz[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const int64_t row = row0 + u * stride;
+      const int64_t row = row0 + (UN + u) * stride;
       const bool ok = row < R;
-      dz[u] = ok ? ld2(dz0, row, kD, lane) : make_float2(0.f, 0.f);
-      load_thin_row<KMAX>(x[u], obs, row, d, d, ok);
+      dzn[u] = ok ? ld2(dz0, row, kD, lane) : make_float2(0.f, 0.f);
+      load_thin_row<KMAX>(xn_[u], obs, row, d, d, ok);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -353,6 +361,12 @@ obs_embed_bwd_kernel(int64_t R, int d, const float* __restrict__ obs, const floa
         acc[k].y = fmaf(o, dz[u].y, acc[k].y);
         ds[k] = fmaf(dz[u].x * w[k].x + dz[u].y * w[k].y, xn, ds[k]);  // lane partial of d(on_k) * x_k * rstd
       }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      dz[u] = dzn[u];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) x[u][k] = xn_[u][k];
     }
   }
   for (int i = threadIdx.x; i < KMAX * kD + KMAX; i += 256) red[i] = 0.f;

@@ -14,7 +14,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import coordsum as ocs  # noqa: E402
+from oracle import lbf as olbf  # noqa: E402
 from oracle import prng  # noqa: E402
+from oracle import rware as orw  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -39,6 +41,32 @@ def main():
     np.savez_compressed(os.path.join(HERE, "coordsum_trace.npz"), keys=keys, actions=np.stack(acts), rewards=np.stack(rewards),
                         agents_view=np.stack(views), step_type=np.stack(steps), final_target=st["env_state"]["target"],
                         final_key=st["env_state"]["key"], episode_return=st["episode_return"])
+    # LBF / RWARE traces: 6 envs, a fixed stream of (mostly legal) actions through several auto-resets
+    for name, mod, spec, n_steps in (("lbf", olbf, olbf.LbfSpec(**olbf.SCENARIOS["2s-8x8-2p-2f-coop"]), 230),
+                                     ("rware", orw, orw.RwareSpec(**dict(orw.SCENARIOS["tiny-4ag"], time_limit=70)), 160)):
+        np.savez_compressed(os.path.join(HERE, f"{name}_trace.npz"), **env_trace(mod, spec, n_steps))
+
+
+def env_trace(mod, spec, n_steps, n_envs=6, seed=9):
+    keys = prng.split(prng.prng_key(seed), n_envs)
+    st, ts = mod.reset(spec, keys)
+    rng = np.random.default_rng(1)
+    a_dim = spec.action_dim
+    acts, rewards, views, masks, steps, rets = [], [], [ts["observation"]["agents_view"].copy()], [ts["observation"]["action_mask"].copy()], [], []
+    for _ in range(n_steps):
+        m = ts["observation"]["action_mask"]
+        a = rng.integers(0, a_dim, (n_envs, spec.num_agents)).astype(np.int32)
+        legal = np.take_along_axis(m, a[..., None].astype(np.int64), -1)[..., 0]
+        a = np.where(legal | (rng.random(a.shape) < 0.1), a, 0).astype(np.int32)
+        if a_dim == 6:  # LBF: load whenever possible, most of the time
+            a = np.where(m[..., 5] & (rng.random(a.shape) < 0.6), 5, a).astype(np.int32)
+        st, ts = mod.step(spec, st, a)
+        acts.append(a); rewards.append(ts["reward"].copy()); views.append(ts["observation"]["agents_view"].copy())
+        masks.append(ts["observation"]["action_mask"].copy()); steps.append(ts["step_type"].copy())
+        rets.append(ts["extras"]["episode_metrics"]["episode_return"].copy())
+    return dict(keys=keys, actions=np.stack(acts), rewards=np.stack(rewards), agents_view=np.stack(views).astype(np.float32),
+                action_mask=np.stack(masks), step_type=np.stack(steps), episode_return=np.stack(rets),
+                final_key=st["env_state"]["key"])
 
 
 if __name__ == "__main__":
