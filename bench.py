@@ -32,6 +32,10 @@ WORKLOADS = {
                           time_limit=500),
                   label="RobotWarehouse tiny-4ag (A=4, a=5, d=75; BASELINE configs[2], 8192 envs / 8 GPUs = --num-envs 1024 "
                         "--update-batch-size 1 per GPU; dynamics restated from jumanji 1.1.0, see oracle/rware.py)"),
+    "rware-small": dict(kw=dict(column_height=8, shelf_rows=2, shelf_columns=3, num_agents=4, sensor_range=1, request_queue_size=4,
+                                time_limit=500),
+                        label="RobotWarehouse small-4ag (A=4, a=5, d=75; BASELINE configs[3]: run with a long --rollout-length, "
+                              "BPTT-heavy update; dynamics restated from jumanji 1.1.0, see oracle/rware.py)"),
     "coordsum": dict(kw=dict(num_agents=3, num_actions=10, time_limit=100, maxval=30),
                      label="CoordSum 3x10-30 (A=3, a=10, d=4; BASELINE configs[4] sweep point)"),
 }
@@ -103,7 +107,7 @@ def run_reference(args, as_baseline=False):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     E = 16  # bounded sample of the workload: 16 of the envs per slot, everything else as configured
-    spec = {"lbf": olbf.LbfSpec, "rware": orw.RwareSpec, "coordsum": ocs.CoordSumSpec}[args.env](**WORKLOADS[args.env]["kw"])
+    spec = {"lbf": olbf.LbfSpec, "rware": orw.RwareSpec, "rware-small": orw.RwareSpec, "coordsum": ocs.CoordSumSpec}[args.env](**WORKLOADS[args.env]["kw"])
     ncfg = onets.NetCfg(spec.num_agents, spec.obs_dim, spec.action_dim)
     osys = olr.SysCfg(num_envs=E, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length)
     state = olr.learner_setup(spec, ncfg, osys, seed=42)
@@ -169,7 +173,7 @@ def run():
         dist.init_process_group("nccl", device_id=dev)
         allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
-    env = {"lbf": LbfVec, "rware": RwareVec, "coordsum": CoordSumVec}[args.env](**WORKLOADS[args.env]["kw"])
+    env = {"lbf": LbfVec, "rware": RwareVec, "rware-small": RwareVec, "coordsum": CoordSumVec}[args.env](**WORKLOADS[args.env]["kw"])
     sysc = SystemConfig(num_envs=args.num_envs, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length,
                         chunk_envs=args.chunk_envs)
     lrn = MagpoLearner(env, sysc, device=dev, allreduce=allreduce, world_size=world)
