@@ -15,6 +15,7 @@
 // 3xTF32 throughout (fp32-faithful). warps 0-15: gates, warp 16: TMA producer, warp 17: MMA issuer, warp 18: L2 prefetch
 // (warp 19 only donates its registers to the gate warps through setmaxnreg).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "actor.cuh"
 #include "tc_ptx.cuh"
@@ -57,14 +58,14 @@ struct GateGeom {
 };
 __device__ __forceinline__ int vidx(int rr, int e) { return (rr >> 1) * 4 + 2 * (rr & 1) + e; }
 
-__device__ __forceinline__ GateGeom make_geom(int sp, int lane, int64_t tile_row0, int64_t Rs) {
+__device__ __forceinline__ GateGeom make_geom(int sp, int lane, int64_t tile_row0, int64_t Rs, int rpt) {
   GateGeom gg;
   gg.m = lane & 3;
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     gg.row[rr] = sp * 32 + (rr >> 1) * 16 + (rr & 1) * 8 + (lane >> 2);
     gg.grow[rr] = tile_row0 + gg.row[rr];
-    gg.valid[rr] = gg.grow[rr] < Rs;
+    gg.valid[rr] = gg.row[rr] < rpt && gg.grow[rr] < Rs;
   }
   return gg;
 }
@@ -135,6 +136,7 @@ struct GruFwdArgs {
   unsigned long long* dbg;
   int T, N, A;
   int64_t Rs;
+  int rpt;              // rows per CTA
   const float* gi;      // [T, Rs, 384]  x @ Wi + bi
   const float* bhn;     // [128]
   const uint8_t* done;  // [T, N]
@@ -161,8 +163,10 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T;
-  const int64_t tile_row0 = (int64_t)blockIdx.x * 128;
-  const int64_t tile_rows = p.Rs - tile_row0 < 128 ? p.Rs - tile_row0 : 128;
+  // a CTA owns p.rpt (32, 64 or 128) rows of its 128-row MMA tile: with few rows, spreading them over more SMs divides the
+  // per-SM stream of saved activations; the unused rows of the tile are zero operands
+  const int64_t tile_row0 = (int64_t)blockIdx.x * p.rpt;
+  const int64_t tile_rows = p.Rs - tile_row0 < p.rpt ? p.Rs - tile_row0 : p.rpt;
 
   if (warp == GS_GATE_WARPS + 1 && lane == 0) {
     for (int i = 0; i < GS_STAGES; ++i) {
@@ -248,7 +252,7 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     regs_gate_warps();
     // ===================== gates: warp = (32 rows, 8 of every 32 hidden units), thread = 4 x 2 patch =====================
     const int sp = warp & 3, cq = warp >> 2;
-    const GateGeom gg = make_geom(sp, lane, tile_row0, p.Rs);
+    const GateGeom gg = make_geom(sp, lane, tile_row0, p.Rs, p.rpt);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(sp * 32) << 16);
     float h[32];  // masked previous state: block jb at [8 jb, 8 jb + 8)
     float bh[8];
@@ -336,6 +340,7 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
 struct GruBwdArgs {
   int T, N, A;
   int64_t Rs;
+  int rpt;              // rows per CTA
   const float* dY;      // [T, Rs, 128]
   const float* rzn;     // [T, Rs, 384]
   const float* ghn;     // [T, Rs, 128]
@@ -362,8 +367,10 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T;
-  const int64_t tile_row0 = (int64_t)blockIdx.x * 128;
-  const int64_t tile_rows = p.Rs - tile_row0 < 128 ? p.Rs - tile_row0 : 128;
+  // a CTA owns p.rpt (32, 64 or 128) rows of its 128-row MMA tile: with few rows, spreading them over more SMs divides the
+  // per-SM stream of saved activations; the unused rows of the tile are zero operands
+  const int64_t tile_row0 = (int64_t)blockIdx.x * p.rpt;
+  const int64_t tile_rows = p.Rs - tile_row0 < p.rpt ? p.Rs - tile_row0 : p.rpt;
 
   if (warp == GS_GATE_WARPS + 1 && lane == 0) {
     for (int i = 0; i < GS_STAGES; ++i) {
@@ -446,7 +453,7 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     regs_gate_warps();
     // ============ gate backward: warp = (32 rows, 8 of every 32 hidden units), thread = 4 x 2 patch ============
     const int sp = warp & 3, cq = warp >> 2;
-    const GateGeom gg = make_geom(sp, lane, tile_row0, p.Rs);
+    const GateGeom gg = make_geom(sp, lane, tile_row0, p.Rs, p.rpt);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(sp * 32) << 16);
     float cz[32];  // dh_{t+1} * z_{t+1}
 #pragma unroll
@@ -528,6 +535,24 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
 
 unsigned long long* g_gru_dbg = nullptr;
 
+// Rows per CTA. Measured on B200 (tools/gru_rpt_experiment.sh): the per-timestep chain of a scan CTA shortens when it owns fewer
+// rows (RWARE shard, 2048 rows: 57.6 / 41.2 / 33.7 ms per step of 8 minibatches at 128 / 64 / 32 rows), but the scans run on a
+// forked stream beside the guider's persistent kernels and a scan CTA fills its SM (227 KB of shared memory): more than ~64 scan
+// CTAs starve the guider and the step gets slower (LBF, 8192 rows: GRU 63 -> 45 ms but the step 284 -> 289 ms at 64 rows). So: the
+// fewest rows per CTA that keep the scan on at most 64 SMs. MAGPO_GRU_RPT overrides, for experiments.
+static int gru_rows_per_tile(int64_t Rs) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("MAGPO_GRU_RPT");
+    const int v = e ? atoi(e) : 0;
+    forced = (v == 32 || v == 64 || v == 128) ? v : 0;
+  }
+  if (forced) return forced;
+  if (ceil_div(Rs, 32) <= 64) return 32;
+  if (ceil_div(Rs, 64) <= 64) return 64;
+  return 128;
+}
+
 // HU[0] must already hold the masked initial state. WhT_hi/lo: TF32 images of W_h^T [384, 128].
 int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const float* WhT_hi, const float* WhT_lo, const float* bhn,
                  const uint8_t* done, float* rzn, float* ghn, float* Y, float* HU) {
@@ -539,10 +564,11 @@ int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const flo
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
     attr = true;
   }
-  GruFwdArgs a{g_gru_dbg, T, N, A, Rs, gi, bhn, done, rzn, ghn, Y, HU};
+  const int rpt = gru_rows_per_tile(Rs);
+  GruFwdArgs a{g_gru_dbg, T, N, A, Rs, rpt, gi, bhn, done, rzn, ghn, Y, HU};
   // per row and step: 3xTF32 MMAs are the pipe work; bytes: gi 1536 read, rzn+ghn+Y+HU 3072 written
   ProfScope ps(PROF_GRU, s, 4608.0 * (double)Rs * T);
-  gru_scan_fwd_kernel<<<(unsigned)ceil_div(Rs, 128), GS_THREADS, GS_SMEM, s>>>(tmh, tml, a);
+  gru_scan_fwd_kernel<<<(unsigned)ceil_div(Rs, rpt), GS_THREADS, GS_SMEM, s>>>(tmh, tml, a);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
@@ -558,9 +584,10 @@ int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const flo
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
     attr = true;
   }
-  GruBwdArgs a{T, N, A, Rs, dY, rzn, ghn, HU, done, dgi, dgh};
+  const int rpt = gru_rows_per_tile(Rs);
+  GruBwdArgs a{T, N, A, Rs, rpt, dY, rzn, ghn, HU, done, dgi, dgh};
   ProfScope ps(PROF_GRU, s, 6144.0 * (double)Rs * T);
-  gru_scan_bwd_kernel<<<(unsigned)ceil_div(Rs, 128), GS_THREADS, GS_SMEM, s>>>(tmh, tml, a);
+  gru_scan_bwd_kernel<<<(unsigned)ceil_div(Rs, rpt), GS_THREADS, GS_SMEM, s>>>(tmh, tml, a);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }

@@ -18,6 +18,7 @@
 //     traffic is 32 + 2 (16 A + 16) KiB instead of 32 (1 + 2 A) KiB.
 // All arithmetic is fp32 FMA (no TF32 split on this path). Algorithmic HBM bytes per env-step: state traffic above +
 // A (4 d + a + 4) in + 12 A out.
+#include <stdlib.h>
 #include "kernels.cuh"
 #include "params.cuh"
 #include "prng.cuh"
@@ -28,7 +29,6 @@ namespace {
 constexpr float kEps = 1e-6f;
 constexpr int EPW = 2;         // envs per warp
 constexpr int SS_WARPS = 14;   // warps per CTA (28 envs; one CTA per SM, the register file is the occupancy limit): 8192 envs = 1.98 waves
-constexpr int SS_THREADS = SS_WARPS * 32;
 constexpr int SS_WBUF = kD * 4 * kD;  // floats of the largest layer [64, 256]
 constexpr int SS_XROWS = 8;  // rows of the per-warp activation scratch (EPW x A <= 8)
 constexpr uint32_t SS_SMEM = (2 * SS_WBUF + SS_WARPS * SS_XROWS * kD) * sizeof(float);
@@ -101,7 +101,7 @@ __device__ __forceinline__ void dense1(const float* __restrict__ W, const float2
 // Weight pipeline: every thread copies its 16-byte pieces of the next layer's matrix (global, contiguous) into the idle buffer.
 __device__ __forceinline__ void stage_issue(float* dst /*shared*/, const float* __restrict__ src, int nfloats) {
   const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
-  for (int i = threadIdx.x * 4; i < nfloats; i += SS_THREADS * 4)
+  for (int i = threadIdx.x * 4; i < nfloats; i += blockDim.x * 4)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i * 4), "l"(src + i) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -192,7 +192,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
   float* const w_b = wbuf + SS_WBUF;
   float* const xs = wbuf + 2 * SS_WBUF + (threadIdx.x >> 5) * SS_XROWS * kD;  // this warp's activation scratch
   const int lane = threadIdx.x & 31;
-  const int64_t pair = (int64_t)blockIdx.x * SS_WARPS + (threadIdx.x >> 5);  // warps past the batch run dead (no stores)
+  const int64_t pair = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // warps past the batch run dead (no stores)
   stage_issue(w_a, p.qkvg, kD * 4 * kD);
   float* cur_w = w_a;  // buffer of the layer about to be computed
   float* nxt_w = w_b;  // buffer the following layer is prefetched into
@@ -581,7 +581,18 @@ decoder_tables_kernel(const GuiderP p, int a, int max_step, const float* __restr
 
 template <int A>
 int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
-  const unsigned grid = (unsigned)ceil_div(ceil_div(s.B, EPW), SS_WARPS);
+  // small batches: fewer warps per CTA spread the envs over more SMs, but every CTA streams the step's weights (0.4 MB) through its
+  // own shared memory, so below ~7 warps the copies dominate (RWARE shard of 1024 envs, rollout of 128 steps: 40.1 ms at 14 warps,
+  // 34.8 ms at 7, 118 ms at 4 — tools/step_warps_experiment.sh)
+  const int64_t pairs = ceil_div(s.B, EPW);
+  static int forced_warps = -1;
+  if (forced_warps < 0) {
+    const char* e = getenv("MAGPO_STEP_WARPS");
+    forced_warps = e ? std::min(std::max(atoi(e), 1), SS_WARPS) : 0;
+  }
+  const int warps = forced_warps ? forced_warps : (int)std::min<int64_t>(SS_WARPS, std::max<int64_t>(7, ceil_div(pairs, kNumSMs)));
+  const unsigned grid = (unsigned)ceil_div(pairs, warps);
+  const unsigned threads = (unsigned)warps * 32;
   static bool attr = false;
   if (!attr) {
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
@@ -590,10 +601,10 @@ int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
     attr = true;
   }
-  if (s.d <= 4) sable_step_kernel<A, 4><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
-  else if (s.d <= 8) sable_step_kernel<A, 8><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
-  else if (s.d <= 16) sable_step_kernel<A, 16><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
-  else sable_step_kernel<A, 0><<<grid, SS_THREADS, SS_SMEM, st>>>(p, s);
+  if (s.d <= 4) sable_step_kernel<A, 4><<<grid, threads, SS_SMEM, st>>>(p, s);
+  else if (s.d <= 8) sable_step_kernel<A, 8><<<grid, threads, SS_SMEM, st>>>(p, s);
+  else if (s.d <= 16) sable_step_kernel<A, 16><<<grid, threads, SS_SMEM, st>>>(p, s);
+  else sable_step_kernel<A, 0><<<grid, threads, SS_SMEM, st>>>(p, s);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
