@@ -291,7 +291,7 @@ def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, 
 
 
 def run_experiment(config: Config, device=None, log=print) -> float:
-    """rec_magpo.py:688-831 without the logger / checkpointer backends: `num_evaluation` calls of `learn`, each
+    """rec_magpo.py:688-831 (console / JSON logger and an npz checkpointer instead of the TensorBoard / Neptune / orbax back-ends): `num_evaluation` calls of `learn`, each
     `num_updates_per_eval` updates, reporting steps per second and the mean return of the episodes that ended."""
     import torch.distributed as dist
 
@@ -319,6 +319,19 @@ def run_experiment(config: Config, device=None, log=print) -> float:
             m /= world
         return float(m)
 
+    # logger and checkpointer (rec_magpo.py:729-741); rank 0 logs, as the reference's single process does
+    from .checkpointing import Checkpointer, unreplicate_n_dims
+    from .logger import LogEvent, MavaLogger
+
+    config.logger.system_name = "rec_magpo"
+    logger = MavaLogger(config, console_sink=log) if rank == 0 else None
+    if logger:
+        logger.log_config(config.to_dict())
+    save_checkpoint = bool(config.logger.checkpointing.save_model) and rank == 0
+    if save_checkpoint:
+        checkpointer = Checkpointer(metadata=config, model_name=config.logger.system_name,
+                                    **{k: v for k, v in config.logger.checkpointing.save_args.to_dict().items()})
+
     max_episode_return, best_params, eval_performance = float("-inf"), None, float("nan")
     for ev in range(int(config.arch.num_evaluation)):
         t0 = time.perf_counter()
@@ -326,30 +339,37 @@ def run_experiment(config: Config, device=None, log=print) -> float:
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         state = out.learner_state
-        term = out.episode_metrics["is_terminal_step"]
-        train_return = float(out.episode_metrics["episode_return"][term].mean()) if bool(term.any()) else float("nan")
+        t = int(steps_per_rollout * (ev + 1))
+        # rec_magpo.py:756-767: steps per second, the metrics of the episodes that ended, the mean losses
+        term = out.episode_metrics["is_terminal_step"].bool()
+        if logger:
+            logger.log({"timestep": t}, t, ev, LogEvent.MISC)
+            if bool(term.any()):  # get_final_step_metrics (utils/training / logger): only completed episodes are reported
+                act = {k: v[term] for k, v in out.episode_metrics.items() if k != "is_terminal_step"}
+                act["steps_per_second"] = steps_per_rollout / dt
+                logger.log(act, t, ev, LogEvent.ACT)
+            logger.log(dict(out.train_metrics), t, ev, LogEvent.TRAIN)
         # rec_magpo.py:770-777: key_e, *eval_keys = split(key_e, n_devices + 1); evaluator(trained_params, eval_keys, ...)
         ks = minit.split(key_e, world + 1, device or "cuda:0")
         key_e, eval_key = ks[0], ks[1 + rank]
         eval_metrics = evaluator(lrn.actor, eval_key)
         eval_performance = world_mean(eval_metrics[config.env.eval_metric])
+        if logger:
+            logger.log(dict(eval_metrics), t, ev, LogEvent.EVAL)
+        if save_checkpoint:  # rec_magpo.py:779-786
+            checkpointer.save(timestep=t, unreplicated_learner_state=unreplicate_n_dims(state), episode_return=eval_performance)
         if config.arch.absolute_metric and max_episode_return <= eval_performance:  # rec_magpo.py:787-789
             best_params, max_episode_return = lrn.actor.clone(), eval_performance
-        if rank == 0:
-            log(f"eval {ev}: steps_per_second={steps_per_rollout / dt:.0f} timestep={steps_per_rollout * (ev + 1)} "
-                f"train_episode_return={train_return:.4f} eval_{config.env.eval_metric}={eval_performance:.4f} "
-                f"eval_steps_per_second={eval_metrics['steps_per_second']:.0f} "
-                f"total_loss={float(out.train_metrics['total_loss'].mean()):.5f} "
-                f"value_loss={float(out.train_metrics['value_loss'].mean()):.5f} entropy={float(out.train_metrics['entropy'].mean()):.4f}")
     if config.arch.absolute_metric and best_params is not None:  # rec_magpo.py:798-812: 10x episodes with the best parameters
         abs_evaluator = mev.get_eval_fn(env, actor_network, config, absolute_metric=True, n_devices=world)
         ks = minit.split(key_e, world + 1, device or "cuda:0")
         abs_metrics = abs_evaluator(best_params, ks[1 + rank])
-        if rank == 0:
-            log(f"absolute metric: {config.env.eval_metric}={world_mean(abs_metrics[config.env.eval_metric]):.4f} over "
-                f"{world * abs_metrics['episode_return'].numel()} episodes")
-        elif world > 1:
-            world_mean(abs_metrics[config.env.eval_metric])
+        world_mean(abs_metrics[config.env.eval_metric])
+        if logger:
+            logger.log(dict(abs_metrics), int(steps_per_rollout * int(config.arch.num_evaluation)), int(config.arch.num_evaluation) - 1,
+                       LogEvent.ABSOLUTE)
+    if logger:
+        logger.stop()
     return eval_performance
 
 

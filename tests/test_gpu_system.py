@@ -1,5 +1,7 @@
 """-m gpu: the system entry (`learner_setup` / `learn`, rec_magpo.py:533-685,501-530) and the evaluator hook
 (`actor_network.apply`) on the GPU: pytree shapes of Appendix B, metric shapes of scan∘vmap∘scan, state adoption."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -100,15 +102,31 @@ def test_evaluator_matches_oracle(dev, greedy):
     assert got["steps_per_second"] > 0
 
 
-@pytest.mark.parametrize("env_args", [[], ["env=lbf"], ["env=rware", "env/scenario=tiny-4ag", "env.kwargs.time_limit=30"]])
-def test_run_experiment_trains_and_evaluates(dev, env_args):
+@pytest.mark.parametrize("env_args,env_dims", [([], (3, 10)), (["env=lbf"], (2, 6)),
+                                               (["env=rware", "env/scenario=tiny-4ag", "env.kwargs.time_limit=30"], (4, 5))])
+def test_run_experiment_trains_and_evaluates(dev, env_args, env_dims, tmp_path_factory, monkeypatch):
     """rec_magpo.py:688-815 end to end (`python -m magpo_b200.rec_magpo env=...`): learn, evaluate the learner policy after every
     `learn`, absolute metric with the best parameters at the end — on all three env families."""
     lines = []
     cfg = compose("default/rec_magpo", [*env_args, "arch.num_envs=8", "system.rollout_length=8", "system.num_updates=2",
                                         "arch.num_evaluation=2", "system.total_timesteps=~", "arch.num_eval_episodes=4",
                                         "arch.num_absolute_metric_eval_episodes=8"])
+    tmp_path = tmp_path_factory.mktemp("run")
+    monkeypatch.chdir(tmp_path)
+    cfg.logger.checkpointing.save_model = True
+    cfg.logger.use_json = True
+    cfg.logger.base_exp_path = str(tmp_path / "results")
     perf = rm.run_experiment(cfg, device=dev, log=lines.append)
-    assert len(lines) == 3, lines
-    assert lines[0].startswith("eval 0:") and "eval_episode_return=" in lines[0] and "absolute metric" in lines[-1]
+    kinds = [ln.split(" - ")[0] for ln in lines]
+    assert kinds.count("EVALUATOR") == 2 and kinds.count("TRAINER") == 2 and kinds.count("ABSOLUTE") == 1 and kinds.count("MISC") == 2
+    assert any("Episode return mean" in ln for ln in lines if ln.startswith("EVALUATOR"))
     assert np.isfinite(perf)
+    # checkpoint of the unreplicated learner state (rec_magpo.py:779-786) and the marl-eval JSON
+    from magpo_b200.checkpointing import Checkpointer
+    uid = os.listdir(tmp_path / "checkpoints" / "rec_magpo")[0]
+    ck = Checkpointer("rec_magpo", checkpoint_uid=uid)
+    flat = ck.restore()
+    assert flat["params/actor_params/action_head/Dense_0/kernel"].shape == (128, env_dims[1])
+    assert flat["hstates/policy_hidden_state"].shape == (8, env_dims[0], 128) and flat["key"].shape == (2,)
+    jf = list((tmp_path / "results").rglob("metrics.json"))
+    assert len(jf) == 1 and "absolute_metrics" in open(jf[0]).read()

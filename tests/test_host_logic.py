@@ -84,3 +84,54 @@ def test_two_process_gloo_sharding_and_gradient_mean():
     assert (res["all"] == res["ref"]).all()          # the ranks' blocks tile the global key array in order
     assert (res["keys"][0] == res["keys"][1]).all()  # identical step key on every device
     assert np.allclose(res["mean"], res["expect"])
+
+
+def test_logger_describes_and_writes_marl_eval_json(tmp_path):
+    """MavaLogger.log semantics of mava/utils/logger.py:126-150 and the marl-eval JSON layout of JsonLogger (:300-346)."""
+    import json
+
+    import numpy as np
+
+    from magpo_b200.config import compose
+    from magpo_b200.logger import LogEvent, MavaLogger, describe
+
+    assert describe(np.array([1.0, 3.0])) == {"mean": 2.0, "std": 1.0, "min": 1.0, "max": 3.0} and describe(np.float32(2)) == 2.0
+    cfg = compose("default/rec_magpo", ["env=lbf", "logger.use_json=True"])
+    cfg.logger.base_exp_path = str(tmp_path)
+    lines = []
+    lg = MavaLogger(cfg, console_sink=lines.append)
+    lg.log({"episode_return": np.array([0.5, 1.0]), "is_terminal_step": np.array([1, 1]), "steps_per_second": 10.0}, 100, 0, LogEvent.ACT)
+    lg.log({"total_loss": np.ones((1, 2, 2, 4, 2)), "entropy": np.full((1, 2, 2, 4, 2), 0.5)}, 100, 0, LogEvent.TRAIN)
+    lg.log({"episode_return": np.array([0.5, 1.0]), "steps_per_second": 9.0}, 100, 0, LogEvent.EVAL)
+    lg.log({"episode_return": np.array([1.0, 1.0])}, 200, 1, LogEvent.ABSOLUTE)
+    assert lines[0].startswith("ACTOR - ") and "Episode return mean: 0.750" in lines[0] and "terminal" not in lines[0]
+    assert lines[1] == "TRAINER - Entropy: 0.500 | Total loss: 1.000"
+    files = list(tmp_path.rglob("metrics.json"))
+    run = json.load(open(files[0]))["LevelBasedForaging"]["2s-8x8-2p-2f-coop"]["rec_magpo"]["seed_42"]
+    assert run["step_0"] == {"step_count": 100, "mean_episode_return": [0.75], "steps_per_second": [9.0]}
+    assert run["absolute_metrics"] == {"mean_episode_return": [1.0]}
+
+
+def test_checkpointer_keeps_the_best_and_restores(tmp_path, monkeypatch):
+    """Checkpointer surface of mava/utils/checkpointing.py:34-215: best_fn = episode_return (max), max_to_keep, keep_period."""
+    from collections import namedtuple
+
+    import numpy as np
+
+    from magpo_b200.checkpointing import Checkpointer, unreplicate_n_dims
+
+    monkeypatch.chdir(tmp_path)
+    P = namedtuple("Params", "guider_params actor_params")
+    H = namedtuple("HiddenStates", "sable_hidden_state policy_hidden_state")
+    S = namedtuple("State", "params key hstates")
+    st = S(P({"enc/w": np.ones((1, 2, 3, 4))}, {"head/b": np.zeros((1, 2, 5))}), np.zeros((1, 2, 2), np.uint32),
+           H({"encoder": np.ones((1, 2, 7))}, np.full((1, 2, 6), 2.0)))
+    un = unreplicate_n_dims(st)
+    assert un.params.guider_params["enc/w"].shape == (3, 4) and un.key.shape == (2,)
+    ck = Checkpointer("rec_magpo", metadata={"system": {"seed": 42}}, checkpoint_uid="u", max_to_keep=1, keep_period=40)
+    assert ck.save(10, un, 0.5) and ck.save(20, un, 0.2) and ck.save(30, un, 0.9) and ck.save(40, un, 0.1)
+    assert sorted(ck._index) == ["30", "40"]  # the best, plus the one protected by keep_period
+    ck2 = Checkpointer("rec_magpo", checkpoint_uid="u")
+    params, hs = ck2.restore_params(un.params, timestep=30, restore_hstates=True, THiddenState=H)
+    assert params.guider_params["enc/w"].shape == (3, 4) and hs.policy_hidden_state.shape == (6,) and hs.sable_hidden_state["encoder"].shape == (7,)
+    assert ck2.get_cfg()["checkpointer_version"] == 1.0 and ck2.get_cfg()["system"]["seed"] == 42
