@@ -8,6 +8,7 @@
 #include "envs.cuh"
 #include "prng.cuh"
 #include "sable.cuh"
+#include "update.cuh"
 
 namespace magpo {
 
@@ -114,6 +115,21 @@ __global__ void copy_zero_done_kernel(int64_t B, const float* __restrict__ src, 
 }
 
 inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n, 256); }
+
+// The learner's GRU push of a step (rec_magpo.py:146-159) depends only on the step's observation, not on the guider's actions: it
+// trails along on a forked stream and fills the SMs the fused guider kernel and the one-warp-per-env step kernel leave idle.
+struct RolloutSide {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int init() {
+    if (s) return MAGPO_OK;
+    MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    return MAGPO_OK;
+  }
+};
+RolloutSide g_rside;
 
 struct RolloutWs {
   SableActs sa;
@@ -283,15 +299,25 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
   rollout_keys_kernel<<<1, 32, 0, s>>>(key, T + 1, A, w.sample_keys);
   MAGPO_LAUNCH_OK();
 
+  const bool overlap = nets_overlap_enabled();
+  cudaStream_t s2 = s;
+  if (overlap) {
+    MAGPO_TRY(g_rside.init());
+    s2 = g_rside.s;
+  }
   for (int t = 0; t < T; ++t) {
     const float* obs = traj.agents_view + (size_t)t * BA * d;
     const uint8_t* mask = traj.action_mask + (size_t)t * BA * a;
     const int32_t* stepc = traj.step_count + (size_t)t * BA;
     const uint8_t* prev_done = traj.done + (size_t)t * B;
     int32_t* act = traj.action + (size_t)t * BA;
+    if (overlap) {  // observation slot t and done[t] are complete on `s` here
+      MAGPO_CUDA_OK(cudaEventRecord(g_rside.fork, s));
+      MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_rside.fork, 0));
+    }
+    MAGPO_TRY(actor_forward(s2, ap, atp, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
     MAGPO_TRY(get_actions(s, net, B, E, gp, gtp, kappa, obs, mask, stepc, prev_done, w.sample_keys + (size_t)t * A * 2, hs,
                           false, act, traj.log_prob + (size_t)t * BA, traj.value + (size_t)t * BA, nullptr, w));
-    MAGPO_TRY(actor_forward(s, ap, atp, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
     MagpoTimeStep o = ts;
     o.reward = traj.reward + (size_t)t * BA;
     o.agents_view = traj.agents_view + (size_t)(t + 1) * BA * d;
@@ -309,6 +335,10 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
     else
       MAGPO_TRY(coordsum_step_launch(s, static_cast<const MagpoCoordSumCfg*>(env_cfg), B, act,
                                      *static_cast<MagpoCoordSumState*>(env_state), o, done_next));
+  }
+  if (overlap) {
+    MAGPO_CUDA_OK(cudaEventRecord(g_rside.join, s2));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_rside.join, 0));
   }
   // bootstrap value (rec_magpo.py:202-208): a full get_actions of which only the value is kept
   MAGPO_TRY(get_actions(s, net, B, E, gp, gtp, kappa, traj.agents_view + (size_t)T * BA * d, nullptr,

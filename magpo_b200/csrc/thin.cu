@@ -274,14 +274,21 @@ obs_embed_fwd_kernel(int64_t R, int d, const float* __restrict__ obs, const floa
   const float2 ls = *reinterpret_cast<const float2*>(ln_scale + 2 * lane);
   const float inv_d = 1.0f / (float)d;
   const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), stride = (int64_t)gridDim.x * 8;
+  // software-pipelined over rows: the next group's observation rows / step counts are in flight while this group is written
+  float x[UN][KMAX], xn_[UN][KMAX];
+  int st[UN], stn[UN];
+#pragma unroll
+  for (int u = 0; u < UN; ++u) {
+    const int64_t row = w0 + u * stride;
+    load_thin_row<KMAX>(x[u], obs, row, d, d, row < R);
+    st[u] = row < R ? step[row] : 0;
+  }
   for (int64_t row0 = w0; row0 < R; row0 += UN * stride) {
-    float x[UN][KMAX];
-    int st[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const int64_t row = row0 + u * stride;
-      load_thin_row<KMAX>(x[u], obs, row, d, d, row < R);
-      st[u] = row < R ? step[row] : 0;
+      const int64_t row = row0 + (UN + u) * stride;
+      load_thin_row<KMAX>(xn_[u], obs, row, d, d, row < R);
+      stn[u] = row < R ? step[row] : 0;
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -306,6 +313,12 @@ obs_embed_fwd_kernel(int64_t R, int d, const float* __restrict__ obs, const floa
       st2(xin, row, kD, lane, o);
       const float2 e = ld2(pe, min(max(st[u], 0), max_step), kD, lane);
       st2(kqv, row, kD, lane, make_float2(o.x + e.x, o.y + e.y));
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      st[u] = stn[u];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) x[u][k] = xn_[u][k];
     }
   }
 }

@@ -277,6 +277,12 @@ SideStream g_side;
 bool g_overlap_nets = true;
 }  // namespace
 
+}  // extern "C"
+namespace magpo {
+bool nets_overlap_enabled() { return g_overlap_nets; }
+}  // namespace magpo
+extern "C" {
+
 int magpo_debug_set_overlap(int on) {
   g_overlap_nets = on != 0;
   return MAGPO_OK;

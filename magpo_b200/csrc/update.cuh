@@ -13,4 +13,7 @@ int magpo_losses(cudaStream_t s, int64_t R, int N, int A, int a, const MagpoSysC
                  const float* adv, const float* value, const float* value_old, const float* targets,
                  const int32_t* env_slot, const float* stats, float* dlg, float* dll, float* dvalue, float* loss_sums);
 
+// guider / learner work may run on forked streams (magpo_debug_set_overlap)
+bool nets_overlap_enabled();
+
 }  // namespace magpo
