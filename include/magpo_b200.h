@@ -62,6 +62,10 @@ typedef struct MagpoSysCfg {
   int32_t num_minibatches;   /* M */
   /* Python floats in the reference (weak-typed f64 constants); rounded to f32 where JAX would. */
   double gamma, gae_lambda, clip_eps, ent_coef, vf_coef, max_grad_norm, clip_gpo, alpha, lr;
+  /* 0: rec_magpo (guider + learner). 1: rec_sable (mava/systems/sable/anakin/rec_sable.py): the Sable network alone under the
+   * clipped PPO objective — no learner push in the rollout, no learner pass in the update; the MAGPO guider loss with the
+   * learner's log-probs replaced by the guider's own is exactly rec_sable's loss (KL term 0, double clip = PPO clip). */
+  int32_t sable_only;
 } MagpoSysCfg;
 
 /* ------------------------------------------------------------------ parameters

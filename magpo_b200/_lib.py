@@ -36,7 +36,7 @@ class SysCfg(C.Structure):
     _fields_ = [("num_envs", C.c_int32), ("update_batch_size", C.c_int32), ("rollout_length", C.c_int32),
                 ("ppo_epochs", C.c_int32), ("num_minibatches", C.c_int32)] + [
         (n, C.c_double) for n in ("gamma", "gae_lambda", "clip_eps", "ent_coef", "vf_coef", "max_grad_norm",
-                                  "clip_gpo", "alpha", "lr")]
+                                  "clip_gpo", "alpha", "lr")] + [("sable_only", C.c_int32)]
 
 
 class TimeStep(C.Structure):

@@ -299,7 +299,7 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
   rollout_keys_kernel<<<1, 32, 0, s>>>(key, T + 1, A, w.sample_keys);
   MAGPO_LAUNCH_OK();
 
-  const bool overlap = nets_overlap_enabled();
+  const bool overlap = nets_overlap_enabled() && !sys->sable_only;
   cudaStream_t s2 = s;
   if (overlap) {
     MAGPO_TRY(g_rside.init());
@@ -315,7 +315,7 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
       MAGPO_CUDA_OK(cudaEventRecord(g_rside.fork, s));
       MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_rside.fork, 0));
     }
-    MAGPO_TRY(actor_forward(s2, ap, atp, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
+    if (!sys->sable_only) MAGPO_TRY(actor_forward(s2, ap, atp, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
     MAGPO_TRY(get_actions(s, net, B, E, gp, gtp, kappa, obs, mask, stepc, prev_done, w.sample_keys + (size_t)t * A * 2, hs,
                           false, act, traj.log_prob + (size_t)t * BA, traj.value + (size_t)t * BA, nullptr, w));
     MagpoTimeStep o = ts;

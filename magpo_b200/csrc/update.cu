@@ -317,7 +317,8 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
   }
   const SableBatch b = make_batch(net, mb, w.pe);
   const int skip = g_debug_skip;
-  const bool overlap = g_overlap_nets && !skip;
+  bool skip_learner = false;
+  const bool overlap = g_overlap_nets && !skip && !sys->sable_only;
   cudaStream_t s2 = s;
   if (overlap) {
     MAGPO_TRY(g_side.init());
@@ -325,20 +326,25 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
     MAGPO_CUDA_OK(cudaEventRecord(g_side.fork, s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_side.fork, 0));
   }
-  if (!(skip & 2)) MAGPO_TRY(actor_forward(s2, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
+  const bool sable_only = sys->sable_only != 0;
+  if (sable_only) skip_learner = true;
+  if (!(skip & 2) && !skip_learner)
+    MAGPO_TRY(actor_forward(s2, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
   if (!(skip & 1)) MAGPO_TRY(sable_train_forward(s, gp, &w.gt, b, w.sa, w.value, w.lg, true));
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_side.join, s2));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_side.join, 0));
   }
-  MAGPO_TRY(magpo_losses(s, R, N, A, a, sys, inv_tokens, w.lg, w.ll, mb.action_mask, mb.action, mb.log_prob,
+  // rec_sable: the learner's masked logits are the guider's own (constants to the gradient): the guidance KL vanishes and the
+  // double clip of the MAGPO ratio collapses to the PPO clip (rec_sable.py:196-226)
+  MAGPO_TRY(magpo_losses(s, R, N, A, a, sys, inv_tokens, w.lg, sable_only ? w.lg : w.ll, mb.action_mask, mb.action, mb.log_prob,
                          mb.advantages, w.value, mb.value, mb.targets, env_slot, adv_stats_, w.dlg, w.dll, w.dvalue,
                          loss_sums));
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_side.fork, s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_side.fork, 0));
   }
-  if (!(skip & 10)) MAGPO_TRY(actor_backward(s2, ap, w.at, T, N, A, d, a, mb.agents_view, mb.done, w.aa, w.dll, ag));
+  if (!(skip & 10) && !skip_learner) MAGPO_TRY(actor_backward(s2, ap, w.at, T, N, A, d, a, mb.agents_view, mb.done, w.aa, w.dll, ag));
   if (!(skip & 5)) MAGPO_TRY(sable_train_backward(s, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_side.join, s2));

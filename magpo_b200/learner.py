@@ -35,11 +35,12 @@ class SystemConfig:
     alpha: float = 1.0
     actor_lr: float = 2.5e-4
     chunk_envs: int = 0  # envs differentiated per pass (0 = whole minibatch); gradients add up exactly
+    sable_only: bool = False  # rec_sable (systems/sable/anakin/rec_sable.py): the guider network alone under PPO
 
     def c_struct(self) -> L.SysCfg:
         return L.SysCfg(self.num_envs, self.update_batch_size, self.rollout_length, self.ppo_epochs,
                         self.num_minibatches, self.gamma, self.gae_lambda, self.clip_eps, self.ent_coef,
-                        self.vf_coef, self.max_grad_norm, self.clip_gpo, self.alpha, self.actor_lr)
+                        self.vf_coef, self.max_grad_norm, self.clip_gpo, self.alpha, self.actor_lr, int(self.sable_only))
 
 
 @dataclass

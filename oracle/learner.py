@@ -53,6 +53,7 @@ class SysCfg:
     clip_gpo: float = 1.5
     alpha: float = 1.0
     actor_lr: float = 2.5e-4
+    sable_only: bool = False  # rec_sable (mava/systems/sable/anakin/rec_sable.py): Sable alone under PPO, no learner
 
 
 # ----------------------------------------------------------------------------- GAE
@@ -137,6 +138,20 @@ def guider_loss(g_logits, value, g_ent, a_logits, mb, sys: SysCfg):
     return total, (g_loss, ent, v_loss, kl_loss)
 
 
+def sable_ppo_loss(g_logits, value, g_ent, mb, sys: SysCfg):
+    """rec_sable.py:196-226 (`_loss_fn` after the network call): clipped PPO + clipped value loss - entropy bonus."""
+    act = mb["action"].to(torch.int64)[..., None]
+    log_prob = nets.log_softmax(g_logits).gather(-1, act)[..., 0]
+    ratio = torch.exp(log_prob - mb["log_prob"])
+    adv = _norm_adv(mb["adv"])
+    a_loss = -torch.minimum(ratio * adv, torch.clamp(ratio, 1.0 - sys.clip_eps, 1.0 + sys.clip_eps) * adv).mean()
+    ent = g_ent.mean()
+    vclip = mb["value"] + (value - mb["value"]).clamp(-sys.clip_eps, sys.clip_eps)
+    v_loss = 0.5 * torch.maximum((value - mb["targets"]) ** 2, (vclip - mb["targets"]) ** 2).mean()
+    total = a_loss - sys.ent_coef * ent + sys.vf_coef * v_loss
+    return total, (a_loss, ent, v_loss)
+
+
 def actor_loss(a_logits, g_logits, mb, sys: SysCfg):
     """_actor_loss_fn body after the network calls (rec_magpo.py:338-370). g_logits is detached."""
     act = mb["action"].to(torch.int64)[..., None]
@@ -183,6 +198,14 @@ def minibatch_losses_and_grads(gp_np, ap_np, mb_np, ncfg: nets.NetCfg, sys: SysC
     value, g_logp, g_ent, g_logits = nets.sable_apply(
         gp, ncfg, obs, mb["action_mask"], mb["step_count"], mb["action"], mb["prev_hstates"], mb["done"], T
     )
+    if sys.sable_only:  # rec_sable.py:172-258: one network, one loss
+        tot, (a_loss, ent, v_loss) = sable_ppo_loss(g_logits, value, g_ent, mb, sys)
+        gg = torch.autograd.grad(tot, list(gp.values()), allow_unused=True)
+        g_grads = {k: (np.zeros_like(gp_np[k]) if g is None else g.detach().to(torch.float32).numpy()) for k, g in zip(gp, gg)}
+        a_grads = {k: np.zeros_like(v) for k, v in ap_np.items()}
+        info = dict(total_loss=float(tot), value_loss=float(v_loss), actor_loss=float(a_loss), guider_loss=float(a_loss),
+                    kl_loss=0.0, entropy=float(ent), total_guider=float(tot), total_actor=0.0, actor_kl=0.0)
+        return g_grads, a_grads, info, dict(value=value.detach().numpy(), g_logits=g_logits.detach().numpy(), a_logits=None)
     _, a_logits_t = nets.actor_apply(
         ap, ncfg, mb["policy_h0"], forward_reshape(obs, A), forward_reshape(mb["done"], A), forward_reshape(mb["action_mask"], A)
     )
@@ -229,9 +252,12 @@ def rollout(spec, ncfg: nets.NetCfg, sys: SysCfg, gp_np, ap_np, slot):
                 gp, ncfg, obs_f, torch.tensor(ob["action_mask"]), torch.tensor(ob["step_count"]), hs_t, policy_key
             )
             last_done = slot["dones"]
-            ph, _ = nets.actor_apply(
-                ap, ncfg, torch.tensor(slot["hstates"]["policy"]), obs_f[None], torch.tensor(last_done)[None], torch.tensor(ob["action_mask"])[None]
-            )
+            if sys.sable_only:  # rec_sable.py:86-120 has no learner
+                ph = torch.tensor(slot["hstates"]["policy"])
+            else:
+                ph, _ = nets.actor_apply(
+                    ap, ncfg, torch.tensor(slot["hstates"]["policy"]), obs_f[None], torch.tensor(last_done)[None], torch.tensor(ob["action_mask"])[None]
+                )
             prev_done = np.repeat((ts["step_type"] == coordsum.STEP_LAST)[:, None], A, axis=1)
             env_state, new_ts = env_module(spec).step(spec, slot["env_state"], action)
             done = new_ts["step_type"] == coordsum.STEP_LAST
