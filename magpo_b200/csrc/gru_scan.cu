@@ -545,7 +545,7 @@ static int gru_rows_per_tile(int64_t Rs) {
   if (forced < 0) {
     const char* e = getenv("MAGPO_GRU_RPT");
     const int v = e ? atoi(e) : 0;
-    forced = (v == 32 || v == 64 || v == 128) ? v : 0;
+    forced = (v >= 8 && v <= 128) ? v : 0;
   }
   if (forced) return forced;
   if (ceil_div(Rs, 32) <= 64) return 32;

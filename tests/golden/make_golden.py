@@ -45,6 +45,32 @@ def main():
     for name, mod, spec, n_steps in (("lbf", olbf, olbf.LbfSpec(**olbf.SCENARIOS["2s-8x8-2p-2f-coop"]), 230),
                                      ("rware", orw, orw.RwareSpec(**dict(orw.SCENARIOS["tiny-4ag"], time_limit=70)), 160)):
         np.savez_compressed(os.path.join(HERE, f"{name}_trace.npz"), **env_trace(mod, spec, n_steps))
+    # one whole `_update_step` of the oracle on the two in-tree env families: sampled actions, rewards, losses, parameter sums
+    with open(os.path.join(HERE, "update_step.json"), "w") as f:
+        json.dump({name: update_fixture(spec, **kw) for name, spec, kw in UPDATE_CASES()}, f, indent=1)
+
+
+def UPDATE_CASES():
+    return [("coordsum_3x10-30", ocs.CoordSumSpec(**ocs.SCENARIOS["3x10-30-v0"]), dict(E=4, U=1, T=8, P=2, M=2, seed=42)),
+            ("lbf_2s-8x8-2p-2f-coop", olbf.LbfSpec(**olbf.SCENARIOS["2s-8x8-2p-2f-coop"]), dict(E=4, U=2, T=8, P=2, M=2, seed=42))]
+
+
+def update_fixture(spec, E, U, T, P, M, seed):
+    from oracle import learner as olr, nets as onets
+
+    ncfg = onets.NetCfg(spec.num_agents, spec.obs_dim, spec.action_dim)
+    osys = olr.SysCfg(num_envs=E, update_batch_size=U, rollout_length=T, ppo_epochs=P, num_minibatches=M)
+    state = olr.learner_setup(spec, ncfg, osys, seed=seed)
+    rec = {}
+    _, infos = olr.update_step(state, spec, ncfg, osys, record=rec)
+    names = ("value_loss", "actor_loss", "guider_loss", "kl_loss", "entropy", "total_loss")
+    return dict(cfg=dict(E=E, U=U, T=T, P=P, M=M, seed=seed),
+                actions=[rec["traj"][u]["action"].tolist() for u in range(U)],
+                reward_sum=[float(rec["traj"][u]["reward"].sum()) for u in range(U)],
+                losses=[{n: i[n] for n in names} for i in infos],
+                guider_param_abs_sum={k: float(np.abs(v).sum(dtype=np.float64)) for k, v in state["guider_params"].items()},
+                actor_param_abs_sum={k: float(np.abs(v).sum(dtype=np.float64)) for k, v in state["actor_params"].items()},
+                final_key=state["slots"][0]["key"].tolist())
 
 
 def env_trace(mod, spec, n_steps, n_envs=6, seed=9):
