@@ -1,75 +1,72 @@
 // Reverse-scan GAE over the [T,B,A] trajectory — mava/utils/multistep.py:24-68 (calculate_gae).
-// One thread per (env, agent) column walks t = T-1..0; consecutive threads own consecutive columns,
-// so every load/store is a coalesced 128-byte line per warp. Loads run two blocks of timesteps
-// ahead of the dependent chain that consumes them. Arithmetic is the un-fused fp32 sequence
-// of the reference (delta = r + g*nv*(1-nd) - v; gae = delta + (g*l)*(1-nd)*gae), so results are
-// bit-identical to the NumPy oracle. Algorithmic traffic: 17 B per agent-step.
+// The recurrence is a dependent chain per (env, agent) column, but only its ARITHMETIC is sequential: the inputs are known up
+// front. A CTA owns 32 consecutive columns (lane = column, so every load/store is a coalesced 128-byte line per warp) and its
+// 4 warps own the four 32-step segments of a 128-step block of the time axis. All warps first pull their segment into registers
+// (96 independent loads per thread, 14 warps per SM at the bench size: the memory system is saturated instead of waiting on a
+// 128-step latency chain), then the segments run one after the other, latest first, handing the running advantage to the next
+// through shared memory (2 dependent flops per step: ~0.5 us for the whole chain). Arithmetic is the un-fused fp32 sequence of
+// the reference (delta = r + g*nv*(1-nd) - v; gae = delta + (g*l)*(1-nd)*gae), so results are bit-identical to the NumPy oracle.
+// Algorithmic traffic: 17 B per agent-step.
 #include "common.cuh"
 
 namespace magpo {
 
-constexpr int kGaeUnroll = 16;
+constexpr int kGaeSeg = 32;    // timesteps per warp segment
+constexpr int kGaeWarps = 4;   // segments per block of the time axis
 
-struct GaeBlock {
-  float r[kGaeUnroll], v[kGaeUnroll];
-  uint8_t d[kGaeUnroll];
-};
-
-// loads of timesteps t, t-1, ..., t-kGaeUnroll+1 of column c (those >= 0)
-__device__ __forceinline__ void gae_load(GaeBlock& k, int t, int64_t cols, int64_t c, int B, int b, const float* __restrict__ reward,
-                                         const float* __restrict__ value, const uint8_t* __restrict__ done) {
-#pragma unroll
-  for (int u = 0; u < kGaeUnroll; ++u) {
-    if (t - u >= 0) {
-      const int64_t off = (int64_t)(t - u) * cols + c;
-      k.r[u] = __ldg(reward + off);
-      k.v[u] = __ldg(value + off);
-      k.d[u] = __ldg(done + (int64_t)(t - u) * B + b);
-    }
-  }
-}
-
-// The columns of a step are few (B*A = 16 K at the bench size: 3.5 warps per SM), so the kernel lives on the bytes each thread keeps
-// in flight: two blocks of 16 timesteps are ping-ponged, the loads of the next block are issued before the dependent chain of
-// the current one runs (96 loads in flight per thread).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kGaeWarps * 32, 4)
 gae_kernel(int T, int B, int A, const float* __restrict__ reward, const float* __restrict__ value,
            const uint8_t* __restrict__ done, const float* __restrict__ last_value,
            const uint8_t* __restrict__ last_done, float gamma, float gl, float* __restrict__ adv,
            float* __restrict__ targets) {
+  __shared__ float carry[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t cols = (int64_t)B * A;
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const int b = (int)(c / A);
-  float acc = 0.0f;
-  float nv = last_value[c];
-  float nd = last_done[b] ? 1.0f : 0.0f;
-  auto consume = [&](const GaeBlock& k, int t) {
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = c < cols;
+  const int b = live ? (int)(c / A) : 0;
+  if (w == 0) carry[lane] = 0.0f;
+  constexpr int kBlock = kGaeSeg * kGaeWarps;
+  for (int base = ((T - 1) / kBlock) * kBlock; base >= 0; base -= kBlock) {
+    const int s0 = base + w * kGaeSeg, s1 = min(s0 + kGaeSeg, T);  // this warp's timesteps [s0, s1), possibly empty
+    float r[kGaeSeg], v[kGaeSeg];
+    uint8_t d[kGaeSeg];
+    float nv = 0.0f, nd = 0.0f;
+    if (live && s0 < s1) {
 #pragma unroll
-    for (int u = 0; u < kGaeUnroll; ++u) {
-      if (t - u >= 0) {
-        const float nnd = __fsub_rn(1.0f, nd);
-        const float delta = __fsub_rn(__fadd_rn(k.r[u], __fmul_rn(__fmul_rn(gamma, nv), nnd)), k.v[u]);
-        acc = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnd), acc));
-        const int64_t off = (int64_t)(t - u) * cols + c;
-        adv[off] = acc;
-        targets[off] = __fadd_rn(acc, k.v[u]);
-        nv = k.v[u];
-        nd = k.d[u] ? 1.0f : 0.0f;
+      for (int i = 0; i < kGaeSeg; ++i) {
+        if (s0 + i < s1) {
+          const int64_t off = (int64_t)(s0 + i) * cols + c;
+          r[i] = __ldg(reward + off);
+          v[i] = __ldg(value + off);
+          d[i] = __ldg(done + (int64_t)(s0 + i) * B + b);
+        }
+      }
+      // value / done that follow the segment's last step
+      nv = s1 < T ? __ldg(value + (int64_t)s1 * cols + c) : last_value[c];
+      nd = (s1 < T ? __ldg(done + (int64_t)s1 * B + b) : last_done[b]) ? 1.0f : 0.0f;
+    }
+    for (int seg = kGaeWarps - 1; seg >= 0; --seg) {
+      __syncthreads();  // the carry of the later segment (or of the previous block / the initial 0) is visible
+      if (w == seg && live && s0 < s1) {
+        float acc = carry[lane];
+#pragma unroll
+        for (int i = kGaeSeg - 1; i >= 0; --i) {
+          if (s0 + i < s1) {
+            const float nnd = __fsub_rn(1.0f, nd);
+            const float delta = __fsub_rn(__fadd_rn(r[i], __fmul_rn(__fmul_rn(gamma, nv), nnd)), v[i]);
+            acc = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnd), acc));
+            const int64_t off = (int64_t)(s0 + i) * cols + c;
+            adv[off] = acc;
+            targets[off] = __fadd_rn(acc, v[i]);
+            nv = v[i];
+            nd = d[i] ? 1.0f : 0.0f;
+          }
+        }
+        carry[lane] = acc;
       }
     }
-  };
-  GaeBlock k0, k1;
-  int t = T - 1;
-  gae_load(k0, t, cols, c, B, b, reward, value, done);
-  while (t >= 0) {
-    gae_load(k1, t - kGaeUnroll, cols, c, B, b, reward, value, done);
-    consume(k0, t);
-    t -= kGaeUnroll;
-    if (t < 0) break;
-    gae_load(k0, t - kGaeUnroll, cols, c, B, b, reward, value, done);
-    consume(k1, t);
-    t -= kGaeUnroll;
+    __syncthreads();
   }
 }
 
@@ -85,7 +82,7 @@ extern "C" int magpo_gae(magpo_stream_t s, int32_t T, int32_t B, int32_t A, cons
   if (T == 0 || B == 0) return MAGPO_OK;
   const int64_t cols = (int64_t)B * A;
   ProfScope ps(PROF_GAE, as_stream(s), 17.0 * (double)T * cols + 5.0 * cols);
-  gae_kernel<<<(unsigned)ceil_div(cols, 128), 128, 0, as_stream(s)>>>(
+  gae_kernel<<<(unsigned)ceil_div(cols, 32), kGaeWarps * 32, 0, as_stream(s)>>>(
       T, B, A, reward, value, done, last_value, last_done, (float)gamma, (float)(gamma * gae_lambda), advantages, targets);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;

@@ -104,7 +104,7 @@ def test_coordsum_bit_exact(dev, scenario):
     check("end")
 
 
-@pytest.mark.parametrize("T,B,A", [(128, 32, 3), (16, 1, 1), (33, 1000, 4), (1, 5, 2)])
+@pytest.mark.parametrize("T,B,A", [(128, 32, 3), (16, 1, 1), (33, 1000, 4), (1, 5, 2), (300, 50, 2), (129, 7, 3), (512, 11, 4)])
 def test_gae_bit_exact(dev, T, B, A):
     rng = np.random.default_rng(1)
     reward = rng.standard_normal((T, B, A)).astype(np.float32)

@@ -25,4 +25,6 @@ tail -1 gpurun_out/ncu_full_retention_fwd.log
 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"lbf_step_kernel" -s 1 -c 1 -f \
   -o gpurun_out/full_${TAG}_lbf_step_kernel python tools/profile_update.py --rollout-steps 4 > gpurun_out/ncu_full_lbf_step.log 2>&1
 tail -1 gpurun_out/ncu_full_lbf_step.log
+python tools/profile_update.py --gae > gpurun_out/pg_plain.log 2>&1 && \
+ncu $M --log-file gpurun_out/launches_${TAG}_gae.csv python tools/profile_update.py --gae > gpurun_out/pg_ncu.log 2>&1
 ls -la gpurun_out/full_${TAG}_*.ncu-rep

@@ -19,6 +19,7 @@ ap.add_argument("--num-envs", type=int, default=4096)
 ap.add_argument("--update-batch-size", type=int, default=2)
 ap.add_argument("--rollout-length", type=int, default=128)
 ap.add_argument("--rollout-steps", type=int, default=0)
+ap.add_argument("--gae", action="store_true", help="profile the GAE kernel on a full-length trajectory instead")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 env = LbfVec() if args.env == "lbf" else CoordSumVec(num_agents=3, num_actions=10, time_limit=100, maxval=30)
@@ -32,7 +33,9 @@ lrn.rollout(); lrn.gae(); lrn.epoch_indices(True)
 lrn.minibatch_grads(0); lrn.apply_grads()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-if args.rollout_steps:
+if args.gae:
+    lrn.gae()
+elif args.rollout_steps:
     lrn.rollout()
 else:
     lrn.minibatch_grads(1); lrn.apply_grads()
