@@ -2,9 +2,10 @@
 // The recurrence is a dependent chain per (env, agent) column, but only its ARITHMETIC is sequential: the inputs are known up
 // front. A CTA owns 32 consecutive columns (lane = column, so every load/store is a coalesced 128-byte line per warp) and its
 // 4 warps own the four 32-step segments of a 128-step block of the time axis. All warps first pull their segment into registers
-// (96 independent loads per thread, 14 warps per SM at the bench size: the memory system is saturated instead of waiting on a
-// 128-step latency chain), then the segments run one after the other, latest first, handing the running advantage to the next
-// through shared memory (2 dependent flops per step: ~0.5 us for the whole chain). Arithmetic is the un-fused fp32 sequence of
+// (96 independent loads per thread instead of a 128-step chain of load blocks), then the segments run one after the other, latest
+// first, handing the running advantage to the next through shared memory. Measured (ncu, bench size: T=128, 16 K columns, 36 MB):
+// 22 us, 1.06 TB/s of DRAM traffic — at this size the kernel is one launch + one DRAM round trip + the four dependent segments,
+// not bandwidth; the single-pass version it replaces took 23-33 us. Arithmetic is the un-fused fp32 sequence of
 // the reference (delta = r + g*nv*(1-nd) - v; gae = delta + (g*l)*(1-nd)*gae), so results are bit-identical to the NumPy oracle.
 // Algorithmic traffic: 17 B per agent-step.
 #include "common.cuh"
