@@ -3,6 +3,7 @@
 // processed as one batch: the per-slot losses are means over equally many tokens, so the mean over slots of
 // the per-slot gradients (the pmean over "batch", :395-405) is the gradient of the token mean over all slots;
 // only the advantage normalisation is per slot (:283,356).
+#include <stdlib.h>
 #include "update.cuh"
 
 #include <string.h>
@@ -267,11 +268,20 @@ struct SideStream {
   cudaEvent_t fork = nullptr, join = nullptr;
   int init() {
     if (s) return MAGPO_OK;
-    MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    const char* e = getenv("MAGPO_PRIO_MODE");  // experiments: 1 = the side stream gets the highest priority, 2 = and carries the guider
+    mode = e ? atoi(e) : 0;
+    if (mode) {
+      int least = 0, greatest = 0;
+      MAGPO_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      MAGPO_CUDA_OK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest));
+    } else {
+      MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    }
     MAGPO_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
     MAGPO_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
     return MAGPO_OK;
   }
+  int mode = 0;
 };
 SideStream g_side;
 bool g_overlap_nets = true;
@@ -319,20 +329,20 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
   const int skip = g_debug_skip;
   bool skip_learner = false;
   const bool overlap = g_overlap_nets && !skip && !sys->sable_only;
-  cudaStream_t s2 = s;
+  cudaStream_t s2 = s, sg = s;  // learner stream, guider stream
   if (overlap) {
     MAGPO_TRY(g_side.init());
-    s2 = g_side.s;
+    if (g_side.mode == 2) sg = g_side.s; else s2 = g_side.s;
     MAGPO_CUDA_OK(cudaEventRecord(g_side.fork, s));
-    MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_side.fork, 0));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(g_side.s, g_side.fork, 0));
   }
   const bool sable_only = sys->sable_only != 0;
   if (sable_only) skip_learner = true;
   if (!(skip & 2) && !skip_learner)
     MAGPO_TRY(actor_forward(s2, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
-  if (!(skip & 1)) MAGPO_TRY(sable_train_forward(s, gp, &w.gt, b, w.sa, w.value, w.lg, true));
+  if (!(skip & 1)) MAGPO_TRY(sable_train_forward(sg, gp, &w.gt, b, w.sa, w.value, w.lg, true));
   if (overlap) {
-    MAGPO_CUDA_OK(cudaEventRecord(g_side.join, s2));
+    MAGPO_CUDA_OK(cudaEventRecord(g_side.join, g_side.s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_side.join, 0));
   }
   // rec_sable: the learner's masked logits are the guider's own (constants to the gradient): the guidance KL vanishes and the
@@ -342,12 +352,12 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
                          loss_sums));
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_side.fork, s));
-    MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_side.fork, 0));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(g_side.s, g_side.fork, 0));
   }
   if (!(skip & 10) && !skip_learner) MAGPO_TRY(actor_backward(s2, ap, w.at, T, N, A, d, a, mb.agents_view, mb.done, w.aa, w.dll, ag));
-  if (!(skip & 5)) MAGPO_TRY(sable_train_backward(s, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
+  if (!(skip & 5)) MAGPO_TRY(sable_train_backward(sg, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
   if (overlap) {
-    MAGPO_CUDA_OK(cudaEventRecord(g_side.join, s2));
+    MAGPO_CUDA_OK(cudaEventRecord(g_side.join, g_side.s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_side.join, 0));
   }
   return MAGPO_OK;
