@@ -101,3 +101,61 @@ def get_eval_fn(env, actor_network, config, absolute_metric: bool, n_devices: in
         return metrics
 
     return eval_fn
+
+
+def get_sable_eval_fn(env, lrn, config, absolute_metric: bool, n_devices: int = 1, n_envs: int | None = None,
+                      episode_loops: int | None = None):
+    """The same evaluator loop with rec_sable's act function (rec_sable.py:497-516, `make_rec_sable_act_fn`): the Sable network
+    acts — `get_actions(params, observation, hidden_state, act_key)` — and carries its three retention states, which start at zero
+    for every episode loop (`get_init_hidden_state`, rec_sable.py:545-547) and are neither reset nor masked inside an episode."""
+    dev, net = lrn.dev, lrn.net
+    A, d, a = net.n_agents, net.obs_dim, net.action_dim
+    eval_episodes = config.arch.num_absolute_metric_eval_episodes if absolute_metric else config.arch.num_eval_episodes
+    n = n_envs or get_num_eval_envs(config, absolute_metric, n_devices)
+    loops = episode_loops or math.ceil(eval_episodes / (n * n_devices))
+    state = env.alloc_state(n, dev)
+    ts = alloc_timestep(n, A, d, a, dev)
+    lib = L.lib()
+    lib.magpo_rollout_workspace_bytes.restype = C.c_size_t
+    nbytes = int(lib.magpo_rollout_workspace_bytes(C.byref(lrn.c_net), n, 1))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+    hs = {k: z(n, 64, 64) for k in ("encoder", "decoder_self", "decoder_cross")}
+    action, log_prob, value = z(n, A, dt=torch.int32), z(n, A), z(n, A)
+
+    def eval_fn(guider_flat: torch.Tensor, key) -> dict:
+        t0 = time.perf_counter()
+        s = L.stream_ptr()
+        key = np.asarray(key, np.uint32)
+        rets, lens = [], []
+        for _ in range(loops):
+            key, reset_key = minit.split(key, 2, dev)
+            reset_keys = torch.as_tensor(minit.split(reset_key, n, dev).view(np.int32)).to(dev)
+            L.call(env.reset_fn, s, C.byref(env.cfg), n, L.ptr(reset_keys), env.state_struct(state), L.struct_of(L.TimeStep, **ts))
+            for h in hs.values():
+                h.zero_()
+            last_l, ret_l, len_l = [], [], []
+            for _ in range(env.time_limit + 1):
+                key, act_key = minit.split(key, 2, dev)
+                sample_keys = np.zeros((A, 2), np.uint32)  # discrete_autoregressive_act: key, sample_key = split(key) per agent
+                k = act_key
+                for i in range(A):
+                    k, sample_keys[i] = minit.split(k, 2, dev)
+                sk = torch.as_tensor(sample_keys.view(np.int32)).to(dev)
+                L.call("magpo_sable_get_actions", s, C.byref(lrn.c_net), n, n, L.ptr(guider_flat), L.ptr(ts["agents_view"]),
+                       L.ptr(ts["action_mask"]), L.ptr(ts["step_count"]), None, L.ptr(sk), L.struct_of(L.SableHState, **hs),
+                       L.ptr(action), L.ptr(log_prob), L.ptr(value), None, L.ptr(ws), C.c_size_t(nbytes))
+                L.call(env.step_fn, s, C.byref(env.cfg), n, L.ptr(action), env.state_struct(state), L.struct_of(L.TimeStep, **ts))
+                last_l.append(ts["step_type"] == 2)
+                ret_l.append(ts["episode_return"].clone())
+                len_l.append(ts["episode_length"].clone())
+            done_idx = torch.stack(last_l).to(torch.int8).argmax(0)
+            ar = torch.arange(n, device=dev)
+            rets.append(torch.stack(ret_l)[done_idx, ar])
+            lens.append(torch.stack(len_l)[done_idx, ar])
+        metrics = dict(episode_return=torch.cat(rets), episode_length=torch.cat(lens))
+        torch.cuda.synchronize()
+        metrics["steps_per_second"] = float(metrics["episode_length"].sum()) / (time.perf_counter() - t0)
+        return metrics
+
+    return eval_fn

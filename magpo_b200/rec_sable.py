@@ -94,10 +94,12 @@ def _with_magpo_defaults(config: Config) -> Config:
 
 
 def run_experiment(config: Config, device=None, log=print) -> float:
-    """rec_sable.py:481-625 without the evaluator: `num_evaluation` calls of `learn`, logging ACT / TRAIN events; returns the mean
-    return of the training episodes that ended in the last call."""
+    """rec_sable.py:481-625: `num_evaluation` x (`learn`, evaluation of the Sable policy with `make_rec_sable_act_fn`), logging
+    MISC / ACT / TRAIN / EVAL events, optional checkpoints, the absolute metric with the best parameters at the end."""
     import torch.distributed as dist
 
+    from . import evaluator as mev
+    from .checkpointing import Checkpointer, unreplicate_n_dims
     from .logger import LogEvent, MavaLogger
 
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -107,11 +109,26 @@ def run_experiment(config: Config, device=None, log=print) -> float:
     env = rm.make_env(config)
     key, key_e, net_key = minit.split(minit.prng_key(int(config.system.seed)), 3, device or "cuda:0")
     allreduce = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
-    learn, _, state = learner_setup(env, (key, net_key), config, device=device, allreduce=allreduce, rank=rank, world_size=world)
+    learn, lrn, state = learner_setup(env, (key, net_key), config, device=device, allreduce=allreduce, rank=rank, world_size=world)
+    evaluator = mev.get_sable_eval_fn(env, lrn, config, absolute_metric=False, n_devices=world)
     config.logger.system_name = "rec_sable"
     logger = MavaLogger(config, console_sink=log) if rank == 0 else None
+    if logger:
+        logger.log_config(config.to_dict())
+    save_checkpoint = bool(config.logger.checkpointing.save_model) and rank == 0
+    if save_checkpoint:
+        checkpointer = Checkpointer(metadata=config, model_name=config.logger.system_name,
+                                    **config.logger.checkpointing.save_args.to_dict())
     steps = world * config.system.num_updates_per_eval * config.system.rollout_length * config.system.update_batch_size * config.arch.num_envs
-    last = float("nan")
+
+    def world_mean(x: torch.Tensor) -> float:
+        m = x.float().mean().reshape(1).to(lrn.dev)
+        if world > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.SUM)
+            m /= world
+        return float(m)
+
+    max_episode_return, best_params, eval_performance = float("-inf"), None, float("nan")
     for ev in range(int(config.arch.num_evaluation)):
         t0 = time.perf_counter()
         out = learn(state)
@@ -120,8 +137,6 @@ def run_experiment(config: Config, device=None, log=print) -> float:
         state = out.learner_state
         t = int(steps * (ev + 1))
         term = out.episode_metrics["is_terminal_step"].bool()
-        if bool(term.any()):
-            last = float(out.episode_metrics["episode_return"][term].mean())
         if logger:
             logger.log({"timestep": t}, t, ev, LogEvent.MISC)
             if bool(term.any()):
@@ -129,9 +144,26 @@ def run_experiment(config: Config, device=None, log=print) -> float:
                 act["steps_per_second"] = steps / dt
                 logger.log(act, t, ev, LogEvent.ACT)
             logger.log(dict(out.train_metrics), t, ev, LogEvent.TRAIN)
+        ks = minit.split(key_e, world + 1, device or "cuda:0")
+        key_e, eval_key = ks[0], ks[1 + rank]
+        eval_metrics = evaluator(lrn.guider, eval_key)
+        eval_performance = world_mean(eval_metrics[config.env.eval_metric])
+        if logger:
+            logger.log(dict(eval_metrics), t, ev, LogEvent.EVAL)
+        if save_checkpoint:
+            checkpointer.save(timestep=t, unreplicated_learner_state=unreplicate_n_dims(state), episode_return=eval_performance)
+        if config.arch.absolute_metric and max_episode_return <= eval_performance:
+            best_params, max_episode_return = lrn.guider.clone(), eval_performance
+    if config.arch.absolute_metric and best_params is not None:
+        abs_evaluator = mev.get_sable_eval_fn(env, lrn, config, absolute_metric=True, n_devices=world)
+        ks = minit.split(key_e, world + 1, device or "cuda:0")
+        abs_metrics = abs_evaluator(best_params, ks[1 + rank])
+        world_mean(abs_metrics[config.env.eval_metric])
+        if logger:
+            logger.log(dict(abs_metrics), int(steps * int(config.arch.num_evaluation)), int(config.arch.num_evaluation) - 1, LogEvent.ABSOLUTE)
     if logger:
         logger.stop()
-    return last
+    return eval_performance
 
 
 def main(argv=None) -> float:

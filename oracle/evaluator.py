@@ -61,3 +61,32 @@ def eval_fn(spec, ncfg, actor_params, key, n_envs, episode_loops, greedy=False):
         rets.append(np.stack(ers)[done_idx, ar])
         lens.append(np.stack(els)[done_idx, ar])
     return dict(episode_return=np.concatenate(rets).astype(np.float32), episode_length=np.concatenate(lens).astype(np.int32))
+
+
+def eval_fn_sable(spec, ncfg, guider_params, key, n_envs, episode_loops):
+    """get_eval_fn with rec_sable's act function (rec_sable.py:497-516): the Sable network acts and carries its retention states."""
+    gp_t = nets.to_torch(guider_params)
+    rets, lens = [], []
+    key = np.asarray(key, np.uint32)
+    hs_shape = (n_envs, ncfg.n_head, ncfg.n_block, ncfg.head_size, ncfg.head_size)
+    for _ in range(episode_loops):
+        key, reset_key = prng.split(key)
+        state, ts = env_module(spec).reset(spec, prng.split(reset_key, n_envs))
+        hs = tuple(torch.zeros(hs_shape) for _ in range(3))
+        lasts, ers, els = [], [], []
+        for _ in range(spec.time_limit + 1):
+            ks = prng.split(key)
+            key, act_key = ks[0], ks[1]
+            ob = ts["observation"]
+            with torch.no_grad():
+                action, _, _, hs = nets.sable_get_actions(gp_t, ncfg, torch.tensor(ob["agents_view"].astype(np.float32)),
+                                                          torch.tensor(ob["action_mask"]), torch.tensor(ob["step_count"]), hs, act_key)
+            state, ts = env_module(spec).step(spec, state, np.asarray(action, np.int32))
+            lasts.append(ts["step_type"] == ocs.STEP_LAST)
+            ers.append(ts["extras"]["episode_metrics"]["episode_return"].copy())
+            els.append(ts["extras"]["episode_metrics"]["episode_length"].copy())
+        done_idx = np.stack(lasts).argmax(axis=0)
+        ar = np.arange(n_envs)
+        rets.append(np.stack(ers)[done_idx, ar])
+        lens.append(np.stack(els)[done_idx, ar])
+    return dict(episode_return=np.concatenate(rets).astype(np.float32), episode_length=np.concatenate(lens).astype(np.int32))

@@ -203,8 +203,8 @@ def minibatch_losses_and_grads(gp_np, ap_np, mb_np, ncfg: nets.NetCfg, sys: SysC
         gg = torch.autograd.grad(tot, list(gp.values()), allow_unused=True)
         g_grads = {k: (np.zeros_like(gp_np[k]) if g is None else g.detach().to(torch.float32).numpy()) for k, g in zip(gp, gg)}
         a_grads = {k: np.zeros_like(v) for k, v in ap_np.items()}
-        info = dict(total_loss=float(tot), value_loss=float(v_loss), actor_loss=float(a_loss), guider_loss=float(a_loss),
-                    kl_loss=0.0, entropy=float(ent), total_guider=float(tot), total_actor=0.0, actor_kl=0.0)
+        info = dict(total_loss=float(tot.detach()), value_loss=float(v_loss.detach()), actor_loss=float(a_loss.detach()), guider_loss=float(a_loss.detach()),
+                    kl_loss=0.0, entropy=float(ent.detach()), total_guider=float(tot.detach()), total_actor=0.0, actor_kl=0.0)
         return g_grads, a_grads, info, dict(value=value.detach().numpy(), g_logits=g_logits.detach().numpy(), a_logits=None)
     _, a_logits_t = nets.actor_apply(
         ap, ncfg, mb["policy_h0"], forward_reshape(obs, A), forward_reshape(mb["done"], A), forward_reshape(mb["action_mask"], A)
@@ -217,9 +217,9 @@ def minibatch_losses_and_grads(gp_np, ap_np, mb_np, ncfg: nets.NetCfg, sys: SysC
     g_grads = {k: (np.zeros_like(gp_np[k]) if g is None else g.detach().to(torch.float32).numpy()) for k, g in zip(gp, gg)}
     a_grads = {k: (np.zeros_like(ap_np[k]) if g is None else g.detach().to(torch.float32).numpy()) for k, g in zip(ap, ga)}
     info = dict(
-        total_loss=float(tot_g) + float(tot_a), value_loss=float(v_loss), actor_loss=float(a_loss),
-        guider_loss=float(g_loss), kl_loss=float(kl_g), entropy=float(ent),
-        total_guider=float(tot_g), total_actor=float(tot_a), actor_kl=float(kl_a),
+        total_loss=float(tot_g.detach()) + float(tot_a.detach()), value_loss=float(v_loss.detach()), actor_loss=float(a_loss.detach()),
+        guider_loss=float(g_loss.detach()), kl_loss=float(kl_g.detach()), entropy=float(ent.detach()),
+        total_guider=float(tot_g.detach()), total_actor=float(tot_a.detach()), actor_kl=float(kl_a.detach()),
     )
     aux = dict(value=value.detach().numpy(), g_logits=g_logits.detach().numpy(), a_logits=a_logits.detach().numpy())
     return g_grads, a_grads, info, aux

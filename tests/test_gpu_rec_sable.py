@@ -85,6 +85,31 @@ def test_rec_sable_system_entry(dev):
     assert int(out.learner_state.opt_states.count[0, 0]) == 2 * P * M
     assert not torch.equal(out.learner_state.params["decoder/head/layers_3/kernel"][0, 0], w0)
     lines = []
-    rs.run_experiment(compose("default/rec_sable", ["env=lbf", "arch.num_envs=8", "system.rollout_length=8", "system.num_updates=2",
-                                                    "arch.num_evaluation=2"]), device=dev, log=lines.append)
-    assert [ln.split(" - ")[0] for ln in lines].count("TRAINER") == 2
+    perf = rs.run_experiment(compose("default/rec_sable", ["env=lbf", "arch.num_envs=8", "system.rollout_length=8", "system.num_updates=2",
+                                                           "arch.num_evaluation=2", "arch.num_eval_episodes=4",
+                                                           "arch.num_absolute_metric_eval_episodes=8"]), device=dev, log=lines.append)
+    kinds = [ln.split(" - ")[0] for ln in lines]
+    assert kinds.count("TRAINER") == 2 and kinds.count("EVALUATOR") == 2 and kinds.count("ABSOLUTE") == 1 and np.isfinite(perf)
+
+
+def test_sable_evaluator_matches_oracle(dev):
+    """rec_sable's evaluation (rec_sable.py:497-516 + evaluator.py:82-163): same keys -> same per-episode returns / lengths."""
+    from magpo_b200 import evaluator as mev
+    from oracle import evaluator as oev
+
+    cfg = compose("default/rec_sable", ["env=lbf", "arch.num_envs=6", "system.rollout_length=10", "system.num_updates=4",
+                                        "arch.num_evaluation=2"])
+    cfg.system.num_updates_per_eval = 2
+    env = rs.rm.make_env(cfg)
+    key, _, nk = minit.split(minit.prng_key(42), 3, dev)
+    learn, lrn, state = rs.learner_setup(env, (key, nk), cfg, device=dev)
+    learn(state)  # move the policy off its initialisation
+    n, loops = 5, 2
+    ekey = oprng.split(oprng.prng_key(3))[1]
+    got = mev.get_sable_eval_fn(env, lrn, cfg, absolute_metric=False, n_envs=n, episode_loops=loops)(lrn.guider, ekey)
+    gp, _ = lrn.get_params()
+    spec = olbf.LbfSpec(**olbf.SCENARIOS["2s-8x8-2p-2f-coop"])
+    ncfg = onets.NetCfg(spec.num_agents, spec.obs_dim, spec.action_dim)
+    ref = oev.eval_fn_sable(spec, ncfg, {k: v.cpu().numpy() for k, v in gp.items()}, ekey, n, loops)
+    assert (got["episode_length"].cpu().numpy() == ref["episode_length"]).all()
+    assert np.allclose(got["episode_return"].cpu().numpy(), ref["episode_return"], rtol=0, atol=1e-5)
