@@ -179,3 +179,17 @@ def test_make_env_builds_every_family_from_config():
     assert get_num_eval_envs(cfg, absolute_metric=False) == 16  # 32 episodes > 16 envs -> num_envs (evaluator.py:66-80)
     assert get_num_eval_envs(compose("default/rec_magpo", ["arch.num_envs=64"]), absolute_metric=False) == 32
     assert get_num_eval_envs(compose("default/rec_magpo", ["arch.num_envs=64"]), absolute_metric=False, n_devices=4) == 8
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without the built shared library the first call into the product raises."""
+    import pytest
+
+    from magpo_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libmagpo_b200.so"))
+    with pytest.raises(_lib.MagpoError, match="no CPU fallback"):
+        _lib.lib()
+    with pytest.raises(_lib.MagpoError):
+        _lib.call("magpo_gae")
