@@ -51,13 +51,30 @@ __device__ __forceinline__ void mma3(float (&c)[4], const Frag& a, const FragB& 
   mma8(c, a.h, b.h);
 }
 
-// A[m][k] = X[m][k]  (16 x 8 tile at (m0, k0))
+// ldmatrix moves 8 x 16-byte rows per matrix: for fp32 data that is an 8 x 4 tile whose word (row r, col c) lands in lane 4 r + c —
+// exactly the m16n8k8 TF32 fragment layout (a: row g, col tq). One instruction replaces the 4 (A) or 2 (B) scalar LDS of a
+// K-contiguous fragment; rows are 16-byte aligned (ld % 4 == 0, k0 % 4 == 0) and ld % 32 == 4 keeps the 8 rows on distinct banks.
+__device__ __forceinline__ void ldsm_x4(const float* p, uint32_t (&r)[4]) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2(const float* p, uint32_t (&r)[2]) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void split_u(uint32_t x, uint32_t& hi, uint32_t& lo) {
+  hi = x & 0xFFFFE000u;
+  lo = __float_as_uint(__uint_as_float(x) - __uint_as_float(hi));
+}
+
+// A[m][k] = X[m][k]  (16 x 8 tile at (m0, k0)); matrices: (rows 0-7, k 0-3), (rows 8-15, k 0-3), (rows 0-7, k 4-7), (rows 8-15, k 4-7)
 __device__ __forceinline__ Frag lda_row(const float* X, int ld, int m0, int k0, int g, int tq) {
+  const int lane = 4 * g + tq;
+  uint32_t r[4];
+  ldsm_x4(X + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ld + k0 + (lane >> 4) * 4, r);
   Frag f;
-  split(X[(m0 + g) * ld + k0 + tq], f.h[0], f.l[0]);
-  split(X[(m0 + g + 8) * ld + k0 + tq], f.h[1], f.l[1]);
-  split(X[(m0 + g) * ld + k0 + tq + 4], f.h[2], f.l[2]);
-  split(X[(m0 + g + 8) * ld + k0 + tq + 4], f.h[3], f.l[3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_u(r[i], f.h[i], f.l[i]);
   return f;
 }
 // A[m][k] = X[k][m]
@@ -76,11 +93,14 @@ __device__ __forceinline__ FragB ldb(const float* Y, int ld, int k0, int n0, int
   split(Y[(k0 + tq + 4) * ld + n0 + g], f.h[1], f.l[1]);
   return f;
 }
-// B[k][n] = Y[n][k]
+// B[k][n] = Y[n][k]; matrices: (rows n0..n0+7, k 0-3), (same rows, k 4-7)
 __device__ __forceinline__ FragB ldb_tr(const float* Y, int ld, int k0, int n0, int g, int tq) {
+  const int lane = 4 * g + tq;
+  uint32_t r[2];
+  ldsm_x2(Y + (n0 + (lane & 7)) * ld + k0 + ((lane >> 3) & 1) * 4, r);
   FragB f;
-  split(Y[(n0 + g) * ld + k0 + tq], f.h[0], f.l[0]);
-  split(Y[(n0 + g) * ld + k0 + tq + 4], f.h[1], f.l[1]);
+  split_u(r[0], f.h[0], f.l[0]);
+  split_u(r[1], f.h[1], f.l[1]);
   return f;
 }
 
