@@ -1,7 +1,10 @@
 // Sable guider sequencers: training forward + hand-derived backward, and the building blocks the
 // rollout uses for SableNetwork.get_actions.  Reference: networks/sable_network.py:40-482,
 // networks/utils/sable/{encode,decode}.py, networks/retention.py:265-323.  Backward: SURVEY.md Appendix G.
+#include <stdlib.h>
+
 #include "sable.cuh"
+#include "update.cuh"
 
 namespace magpo {
 
@@ -99,12 +102,15 @@ int sable_encoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
 // Decoder over R rows (Decoder.__call__/recurrent, sable_network.py:296-343). `embed_A`: agents per timestep for
 // the shifted-action tokens (>0 training; 0: action[] holds the previous agent's action; <0: start tokens).
 // `ret_A`: tokens per timestep seen by the retention scans. x_rep / x_rep_pe: encoder output (+PE) rows.
-int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int ret_A, int embed_A, int a,
-                          int max_step, const int32_t* action, const float* x_rep, const float* x_rep_pe,
-                          const int32_t* step, const uint8_t* done, const float* Hself0, const float* Hcross0,
-                          float kappa, const float* pe, const SableActs& w, float* logits, float* Hs_self,
-                          float* Hs_cross, float* Hself_out, float* Hcross_out) {
+// phase 1: the part that does not depend on the encoder (token embedding, self retention, the key / value / gate projections of the
+// cross retention); phase 2: the rest; phase 0: both.
+static int decoder_forward_phase(int phase, cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int ret_A, int embed_A, int a,
+                                 int max_step, const int32_t* action, const float* x_rep, const float* x_rep_pe,
+                                 const int32_t* step, const uint8_t* done, const float* Hself0, const float* Hcross0,
+                                 float kappa, const float* pe, const SableActs& w, float* logits, float* Hs_self,
+                                 float* Hs_cross, float* Hself_out, float* Hcross_out) {
   const int64_t R = (int64_t)T * N * ret_A;
+  if (phase != 2) {
   MAGPO_TRY(embed_fwd(s, R, embed_A, action, p.Wa, p.dln, pe, step, max_step, w.xD, w.xpeD));
   MAGPO_TRY(gemm_nn(s, R, 4 * kD, kD, w.xpeD, kD, wref(p.qkvg1, 4 * kD, pt ? pt->qkvg1T : nullptr, kD), nullptr, w.qkvg1, 4 * kD, 0));
   MAGPO_TRY(retention_fwd(s, T, N, ret_A, kappa, true, w.qkvg1, w.qkvg1 + kD, w.qkvg1 + 2 * kD, 4 * kD, Hself0, done,
@@ -113,8 +119,10 @@ int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
   MAGPO_TRY(gemm_nn(s, R, kD, kD, w.gated1, kD, wref(p.wo1, kD, pt ? pt->wo1T : nullptr, kD), nullptr, w.o1, kD, 0));
   MAGPO_TRY(act_rms_fwd(s, R, w.o1, w.xD, p.dln1, 0, pe, step, max_step, nullptr, w.rpe));
   // cross retention: key = value = r (+PE), query = obs_rep (+PE); gate input is the PE-added key
-  MAGPO_TRY(gemm_nn(s, R, kD, kD, x_rep_pe, kD, wref(p.qkvg2, 4 * kD, pt ? pt->qkvg2T : nullptr, kD), nullptr, w.qkvg2, 4 * kD, 0));
   MAGPO_TRY(gemm_nn(s, R, 3 * kD, kD, w.rpe, kD, wref(p.qkvg2 + kD, 4 * kD, pt ? pt->qkvg2T + kD * kD : nullptr, kD), nullptr, w.qkvg2 + kD, 4 * kD, 0));
+  }
+  if (phase == 1) return MAGPO_OK;
+  MAGPO_TRY(gemm_nn(s, R, kD, kD, x_rep_pe, kD, wref(p.qkvg2, 4 * kD, pt ? pt->qkvg2T : nullptr, kD), nullptr, w.qkvg2, 4 * kD, 0));
   MAGPO_TRY(retention_fwd(s, T, N, ret_A, kappa, true, w.qkvg2, w.qkvg2 + kD, w.qkvg2 + 2 * kD, 4 * kD, Hcross0, done,
                           w.ret2, Hs_cross, Hcross_out));
   MAGPO_TRY(gn_gate_fwd(s, R, w.qkvg2 + 3 * kD, 4 * kD, w.ret2, p.gn2_s, p.gn2_b, w.gated2));
@@ -129,14 +137,57 @@ int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
   return MAGPO_OK;
 }
 
+int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int ret_A, int embed_A, int a,
+                          int max_step, const int32_t* action, const float* x_rep, const float* x_rep_pe,
+                          const int32_t* step, const uint8_t* done, const float* Hself0, const float* Hcross0,
+                          float kappa, const float* pe, const SableActs& w, float* logits, float* Hs_self,
+                          float* Hs_cross, float* Hself_out, float* Hcross_out) {
+  return decoder_forward_phase(0, s, p, pt, T, N, ret_A, embed_A, a, max_step, action, x_rep, x_rep_pe, step, done, Hself0, Hcross0,
+                               kappa, pe, w, logits, Hs_self, Hs_cross, Hself_out, Hcross_out);
+}
+
+namespace {
+// The decoder's encoder-independent prefix runs beside the encoder on its own stream: both are chains of kernels that sit at
+// 0.3-0.7 of the HBM roofline each, so together they use the memory system better than one after the other.
+struct DecStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int init() {
+    if (s) return MAGPO_OK;
+    MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    return MAGPO_OK;
+  }
+};
+DecStream g_dec;
+}  // namespace
+
 int sable_train_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, const SableBatch& b, const SableActs& w,
                         float* value, float* logits, bool save_states) {
+  static int split = -1;
+  if (split < 0) {
+    const char* e = getenv("MAGPO_DEC_OVERLAP");
+    split = e ? atoi(e) : 1;
+  }
+  const bool overlap = split && nets_overlap_enabled();
+  float* hs_self = save_states ? w.Hs_self : nullptr;
+  float* hs_cross = save_states ? w.Hs_cross : nullptr;
+  if (overlap) {
+    MAGPO_TRY(g_dec.init());
+    MAGPO_CUDA_OK(cudaEventRecord(g_dec.fork, s));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(g_dec.s, g_dec.fork, 0));
+    MAGPO_TRY(decoder_forward_phase(1, g_dec.s, p, pt, b.T, b.N, b.A, b.A, b.a, b.max_step, b.action, w.x, w.xpe, b.step_count,
+                                    b.done, b.h_self, b.h_cross, b.kappa, b.pe, w, logits, hs_self, hs_cross, nullptr, nullptr));
+  }
   MAGPO_TRY(sable_encoder_forward(s, p, pt, b.T, b.N, b.A, b.d, b.max_step, b.agents_view, b.step_count, b.done, b.h_enc,
                                   b.kappa, b.pe, w, value, save_states ? w.Hs_enc : nullptr, nullptr));
-  MAGPO_TRY(sable_decoder_forward(s, p, pt, b.T, b.N, b.A, b.A, b.a, b.max_step, b.action, w.x, w.xpe, b.step_count,
-                                  b.done, b.h_self, b.h_cross, b.kappa, b.pe, w, logits,
-                                  save_states ? w.Hs_self : nullptr, save_states ? w.Hs_cross : nullptr, nullptr,
-                                  nullptr));
+  if (overlap) {
+    MAGPO_CUDA_OK(cudaEventRecord(g_dec.join, g_dec.s));
+    MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_dec.join, 0));
+  }
+  MAGPO_TRY(decoder_forward_phase(overlap ? 2 : 0, s, p, pt, b.T, b.N, b.A, b.A, b.a, b.max_step, b.action, w.x, w.xpe, b.step_count,
+                                  b.done, b.h_self, b.h_cross, b.kappa, b.pe, w, logits, hs_self, hs_cross, nullptr, nullptr));
   return MAGPO_OK;
 }
 
