@@ -350,6 +350,12 @@ int magpo_actor_forward(magpo_stream_t s, const MagpoNetCfg* net, const float* a
 int magpo_clip_adam(magpo_stream_t s, int64_t n, float* params, const float* grads, float* mu,
                     float* nu, int32_t* count, float grad_scale, float lr, float max_norm,
                     float* scratch);
+/* The same with make_learning_rate's `decay_learning_rates` schedule (mava/utils/training.py:30-64; rec_magpo.py:581):
+ * lr_t = lr * (1 - (count // decay_period) / num_updates), decay_period = ppo_epochs * num_minibatches, evaluated on the
+ * device from the optimiser count before it is incremented (optax scale_by_schedule). decay_period == 0: constant lr. */
+int magpo_clip_adam_sched(magpo_stream_t s, int64_t n, float* params, const float* grads, float* mu,
+                          float* nu, int32_t* count, float grad_scale, float lr, int32_t decay_period,
+                          int32_t num_updates, float max_norm, float* scratch);
 
 #ifdef __cplusplus
 }

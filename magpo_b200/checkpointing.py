@@ -24,6 +24,8 @@ CHECKPOINTER_VERSION = 1.0
 def flatten_pytree(tree: Any, prefix: str = "") -> Dict[str, np.ndarray]:
     """NamedTuple / dict / tensor pytree -> {"a/b/c": ndarray}; field names follow systems/gpo/types.py."""
     out: Dict[str, np.ndarray] = {}
+    if tree is None:  # None is an empty subtree, as in a JAX pytree
+        return out
     if hasattr(tree, "_fields"):
         items = [(f, getattr(tree, f)) for f in tree._fields]
     elif isinstance(tree, dict):
@@ -40,6 +42,8 @@ def flatten_pytree(tree: Any, prefix: str = "") -> Dict[str, np.ndarray]:
 
 def unreplicate_n_dims(tree: Any, n: int = 2) -> Any:
     """mava/utils/jax_utils.py `unreplicate_n_dims`: index the first `n` (device, update-batch) axes at 0 on every leaf."""
+    if tree is None:
+        return None
     if hasattr(tree, "_fields"):
         return type(tree)(*[unreplicate_n_dims(getattr(tree, f), n) for f in tree._fields])
     if isinstance(tree, dict):

@@ -102,7 +102,8 @@ int embed_bwd(cudaStream_t s, int64_t R, int A, int a, const int32_t* action, co
               const float* dy1, const float* dy2, float* dWa, float* dscale);
 // y = x + pe[step]
 int add_pe(cudaStream_t s, int64_t R, const float* x, const float* pe, const int32_t* step, int max_step, float* y);
-int build_pe_table(cudaStream_t s, int max_step, float* pe);
+// enabled == false (memory_config.timestep_positional_encoding: False, retention.py:278,304): an all-zero table, x + 0 = x exactly
+int build_pe_table(cudaStream_t s, int max_step, float* pe, bool enabled = true);
 int fill_f32(cudaStream_t s, float* p, int64_t n, float v);
 
 // ---- retention.cu : recurrent-form retention over per-env sequences, rows ordered (t, env, agent)

@@ -26,11 +26,21 @@ sumsq_kernel(int64_t n, const float* __restrict__ g, float scale, float* __restr
   }
 }
 
-// scratch[0] = sum of squares (in) ; out: scratch[1] = clip factor numerator flag, [2] = norm, [3] = bc1, [4] = bc2
-__global__ void adam_prelude_kernel(float* __restrict__ scratch, int32_t* __restrict__ count, float max_norm) {
+// scratch[0] = sum of squares (in) ; out: scratch[1] = clip factor numerator flag, [2] = norm, [3] = bc1, [4] = bc2, [5] = lr
+// Learning rate (utils/training.py:30-64, make_learning_rate): constant, or with `decay_learning_rates` the linear schedule
+// init_lr * (1 - (count // (ppo_epochs * num_minibatches)) / num_updates) evaluated at the optimiser count BEFORE the increment
+// (optax scale_by_schedule); the count lives on the device, so the schedule needs no host synchronisation.
+__global__ void adam_prelude_kernel(float* __restrict__ scratch, int32_t* __restrict__ count, float max_norm, float init_lr,
+                                    int32_t decay_period, int32_t num_updates) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float norm = sqrtf(scratch[0]);
   int32_t c = *count;
+  float lr = init_lr;
+  if (decay_period > 0) {
+    const float frac = 1.0f - (float)(c / decay_period) / (float)num_updates;
+    lr = init_lr * frac;
+  }
+  scratch[5] = lr;
   c = c < 2147483647 ? c + 1 : c;  // optax safe_int32_increment
   *count = c;
   scratch[1] = (norm < max_norm) ? 0.0f : 1.0f;  // 1 => rescale by (g / norm) * max_norm
@@ -41,8 +51,8 @@ __global__ void adam_prelude_kernel(float* __restrict__ scratch, int32_t* __rest
 
 __global__ void __launch_bounds__(256)
 adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
-            float* __restrict__ nu, const float* __restrict__ scratch, float grad_scale, float lr, float max_norm) {
-  const float clip = scratch[1], norm = scratch[2], bc1 = scratch[3], bc2 = scratch[4];
+            float* __restrict__ nu, const float* __restrict__ scratch, float grad_scale, float max_norm) {
+  const float clip = scratch[1], norm = scratch[2], bc1 = scratch[3], bc2 = scratch[4], lr = scratch[5];
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-5f;
   const float omb1 = (float)(1.0 - 0.9), omb2 = (float)(1.0 - 0.999);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -62,9 +72,11 @@ adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float
 
 using namespace magpo;
 
-extern "C" int magpo_clip_adam(magpo_stream_t s_, int64_t n, float* params, const float* grads, float* mu, float* nu,
-                               int32_t* count, float grad_scale, float lr, float max_norm, float* scratch) {
+extern "C" int magpo_clip_adam_sched(magpo_stream_t s_, int64_t n, float* params, const float* grads, float* mu, float* nu,
+                                     int32_t* count, float grad_scale, float lr, int32_t decay_period, int32_t num_updates,
+                                     float max_norm, float* scratch) {
   if (n < 0 || !params || !grads || !mu || !nu || !count || !scratch) return MAGPO_ERR_ARG;
+  if (decay_period < 0 || (decay_period > 0 && num_updates < 1)) return MAGPO_ERR_ARG;
   if (n == 0) return MAGPO_OK;
   cudaStream_t s = as_stream(s_);
   ProfScope ps(PROF_OPTIM, s, 32.0 * (double)n);
@@ -72,9 +84,14 @@ extern "C" int magpo_clip_adam(magpo_stream_t s_, int64_t n, float* params, cons
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 4);
   sumsq_kernel<<<grid, 256, 0, s>>>(n, grads, grad_scale, scratch);
   MAGPO_LAUNCH_OK();
-  adam_prelude_kernel<<<1, 32, 0, s>>>(scratch, count, max_norm);
+  adam_prelude_kernel<<<1, 32, 0, s>>>(scratch, count, max_norm, lr, decay_period, num_updates);
   MAGPO_LAUNCH_OK();
-  adam_kernel<<<grid, 256, 0, s>>>(n, params, grads, mu, nu, scratch, grad_scale, lr, max_norm);
+  adam_kernel<<<grid, 256, 0, s>>>(n, params, grads, mu, nu, scratch, grad_scale, max_norm);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
+}
+
+extern "C" int magpo_clip_adam(magpo_stream_t s_, int64_t n, float* params, const float* grads, float* mu, float* nu,
+                               int32_t* count, float grad_scale, float lr, float max_norm, float* scratch) {
+  return magpo_clip_adam_sched(s_, n, params, grads, mu, nu, count, grad_scale, lr, 0, 0, max_norm, scratch);
 }

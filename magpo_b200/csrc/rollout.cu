@@ -225,7 +225,7 @@ int magpo_sable_get_actions(magpo_stream_t s_, const MagpoNetCfg* net, int32_t B
   RolloutWs w;
   w.plan(ar, net, B, 0);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
-  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
+  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
   if (!g_force_unfused && sable_step_supported(net->n_agents, net->obs_dim, net->action_dim))
     MAGPO_TRY(sable_step_tables(s, net, GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim), w.pe, w.dec_tab));
   const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim);
@@ -267,7 +267,7 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
   const ActorP ap = ActorP::bind(const_cast<float*>(actor), d, a);
   const float kappa = net_kappa(net);
 
-  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
+  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
   if (!g_force_unfused && sable_step_supported(net->n_agents, net->obs_dim, net->action_dim))
     MAGPO_TRY(sable_step_tables(s, net, GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim), w.pe, w.dec_tab));
   const GuiderT* gtp = nullptr;

@@ -571,7 +571,11 @@ int add_pe(cudaStream_t s, int64_t R, const float* x, const float* pe, const int
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
-int build_pe_table(cudaStream_t s, int max_step, float* pe) {
+int build_pe_table(cudaStream_t s, int max_step, float* pe, bool enabled) {
+  if (!enabled) {
+    MAGPO_CUDA_OK(cudaMemsetAsync(pe, 0, sizeof(float) * (size_t)(max_step + 1) * kD, s));
+    return MAGPO_OK;
+  }
   pe_table_kernel<<<max_step + 1, 32, 0, s>>>(max_step, pe);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;

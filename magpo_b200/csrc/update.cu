@@ -318,7 +318,7 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
   const GuiderP gg = GuiderP::bind(grads, d, a);
   const ActorP ag = ActorP::bind(grads + gp.total, d, a);
   float* loss_sums = grads + gp.total + ap.total;
-  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
+  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
   MAGPO_TRY(guider_transpose(s, gp, w.gt, d));
   MAGPO_TRY(actor_transpose(s, ap, w.at, a));
   if (tc_enabled()) {
@@ -374,7 +374,7 @@ int magpo_guider_forward(magpo_stream_t s_, const MagpoNetCfg* net, const float*
   w.plan(ar, net, mb.T, mb.N, false);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
   const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim);
-  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe));
+  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
   const SableBatch b = make_batch(net, mb, w.pe);
   MAGPO_TRY(sable_train_forward(s, gp, nullptr, b, w.sa, value, logits, false));
   const int64_t n = (int64_t)mb.T * mb.N * net->n_agents * net->action_dim;

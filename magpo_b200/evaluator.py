@@ -73,8 +73,9 @@ def get_eval_fn(env, actor_network, config, absolute_metric: bool, n_devices: in
             hidden.zero_()
             ts["step_type"].zero_()
             last_l, ret_l, len_l = [], [], []
+            step_key = key  # evaluator.py:139-146: the key the step scan advances is discarded, `_episode` returns the post-reset key
             for _ in range(env.time_limit + 1):
-                key, act_key = minit.split(key, 2, dev)
+                step_key, act_key = minit.split(step_key, 2, dev)
                 mb["done"].copy_((ts["step_type"] == 2).to(torch.uint8).view(1, n))  # timestep.last()
                 L.call("magpo_actor_forward", s, C.byref(lrn.c_net), L.ptr(actor_flat), mbs, L.ptr(logits), L.ptr(ws),
                        C.c_size_t(nbytes))
@@ -135,8 +136,9 @@ def get_sable_eval_fn(env, lrn, config, absolute_metric: bool, n_devices: int = 
             for h in hs.values():
                 h.zero_()
             last_l, ret_l, len_l = [], [], []
+            step_key = key  # evaluator.py:139-146: the key the step scan advances is discarded, `_episode` returns the post-reset key
             for _ in range(env.time_limit + 1):
-                key, act_key = minit.split(key, 2, dev)
+                step_key, act_key = minit.split(step_key, 2, dev)
                 sample_keys = np.zeros((A, 2), np.uint32)  # discrete_autoregressive_act: key, sample_key = split(key) per agent
                 k = act_key
                 for i in range(A):

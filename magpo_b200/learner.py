@@ -36,6 +36,8 @@ class SystemConfig:
     actor_lr: float = 2.5e-4
     chunk_envs: int = 0  # envs differentiated per pass (0 = whole minibatch); gradients add up exactly
     sable_only: bool = False  # rec_sable (systems/sable/anakin/rec_sable.py): the guider network alone under PPO
+    decay_learning_rates: bool = False  # utils/training.py:48-64: linear schedule over num_updates (needs num_updates)
+    num_updates: int = 0
 
     def c_struct(self) -> L.SysCfg:
         return L.SysCfg(self.num_envs, self.update_batch_size, self.rollout_length, self.ppo_epochs,
@@ -220,12 +222,16 @@ class MagpoLearner:
     """All device buffers of one rank + `update_step()` (rollout, GAE, P epochs x M minibatches)."""
 
     def __init__(self, env: CoordSumVec, sys: SystemConfig, device="cuda:0", allreduce=None, world_size: int = 1,
-                 graph_rollout: bool = True):
+                 graph_rollout: bool = True, net: "NetworkConfig | None" = None):
         self.env, self.sys, self.dev = env, sys, torch.device(device)
+        if sys.decay_learning_rates and sys.num_updates < 1:
+            raise ValueError("decay_learning_rates needs system.num_updates >= 1 (utils/training.py:38-44)")
         # The T-step rollout is ~90 short launches per env step: after the first (eager) call it is replayed from one
         # CUDA graph, the way XLA runs command-buffer-compatible FFI handlers. All its operands are device-resident.
         self.graph_rollout, self._rollout_graph, self._rollout_graph_launches = graph_rollout, None, 0
-        self.net = NetworkConfig(env.num_agents, env.obs_dim, env.action_dim, env.time_limit)
+        self.net = net or NetworkConfig(env.num_agents, env.obs_dim, env.action_dim, env.time_limit)
+        if (self.net.n_agents, self.net.obs_dim, self.net.action_dim) != (env.num_agents, env.obs_dim, env.action_dim):
+            raise ValueError("network configuration does not match the environment's (agents, obs_dim, action_dim)")
         self.allreduce, self.world_size = allreduce, world_size
         self.c_net, self.c_sys = self.net.c_struct(), sys.c_struct()
         dev, f32, i32, u8 = self.dev, torch.float32, torch.int32, torch.uint8
@@ -271,6 +277,8 @@ class MagpoLearner:
         lib.magpo_update_workspace_bytes.restype = C.c_size_t
         wr = lib.magpo_rollout_workspace_bytes(C.byref(self.c_net), B, T)
         wu = lib.magpo_update_workspace_bytes(C.byref(self.c_net), T, n)
+        if int(wr) == 0 or int(wu) == 0:  # the size queries return 0 for shapes the kernels do not cover
+            raise L.MagpoError(f"unsupported network / batch configuration: {self.net}")
         self.ws_bytes = max(int(wr), int(wu))
         self.workspace = torch.empty(self.ws_bytes, dtype=u8, device=dev)
         self.first_rollout = True
@@ -296,6 +304,14 @@ class MagpoLearner:
     def set_params(self, guider: dict, actor: dict) -> None:
         load_params(self.guider, self.g_table, guider)
         load_params(self.actor, self.a_table, actor)
+
+    def set_opt_state(self, guider_opt: dict, actor_opt: dict) -> None:
+        """Load both Adam states: dicts with `count`, `mu`, `nu` (the moments keyed like the parameters)."""
+        for opt, table, mu, nu, cnt in ((guider_opt, self.g_table, self.g_mu, self.g_nu, self.g_count),
+                                        (actor_opt, self.a_table, self.a_mu, self.a_nu, self.a_count)):
+            load_params(mu, table, opt["mu"])
+            load_params(nu, table, opt["nu"])
+            cnt.fill_(int(opt["count"]))
 
     def get_params(self):
         return ({k: v.clone() for k, v in param_views(self.guider, self.g_table).items()},
@@ -377,12 +393,14 @@ class MagpoLearner:
             self.allreduce(self.grads)  # sum over ranks; the mean is taken by grad_scale
         scale = 1.0 / self.world_size
         g, a = self.grads[:self.n_g], self.grads[self.n_g:self.n_g + self.n_a]
-        L.call("magpo_clip_adam", s, C.c_int64(self.n_g), L.ptr(self.guider), L.ptr(g), L.ptr(self.g_mu), L.ptr(self.g_nu),
-               L.ptr(self.g_count), C.c_float(scale), C.c_float(sysc.actor_lr), C.c_float(sysc.max_grad_norm),
-               L.ptr(self.adam_scratch))
-        L.call("magpo_clip_adam", s, C.c_int64(self.n_a), L.ptr(self.actor), L.ptr(a), L.ptr(self.a_mu), L.ptr(self.a_nu),
-               L.ptr(self.a_count), C.c_float(scale), C.c_float(sysc.actor_lr), C.c_float(sysc.max_grad_norm),
-               L.ptr(self.adam_scratch[512:]))
+        # both optimisers run on actor_lr (rec_magpo.py:581-589); the schedule is evaluated on the device from the count
+        period = sysc.ppo_epochs * sysc.num_minibatches if sysc.decay_learning_rates else 0
+        L.call("magpo_clip_adam_sched", s, C.c_int64(self.n_g), L.ptr(self.guider), L.ptr(g), L.ptr(self.g_mu), L.ptr(self.g_nu),
+               L.ptr(self.g_count), C.c_float(scale), C.c_float(sysc.actor_lr), period, int(sysc.num_updates),
+               C.c_float(sysc.max_grad_norm), L.ptr(self.adam_scratch))
+        L.call("magpo_clip_adam_sched", s, C.c_int64(self.n_a), L.ptr(self.actor), L.ptr(a), L.ptr(self.a_mu), L.ptr(self.a_nu),
+               L.ptr(self.a_count), C.c_float(scale), C.c_float(sysc.actor_lr), period, int(sysc.num_updates),
+               C.c_float(sysc.max_grad_norm), L.ptr(self.adam_scratch[512:]))
 
     def epoch_indices(self, first: bool) -> None:
         L.call("magpo_epoch_indices", L.stream_ptr(), C.byref(self.c_sys), self.net.n_agents, L.ptr(self.key),

@@ -25,7 +25,7 @@ import torch
 from . import _lib as L
 from . import init as minit
 from .config import Config, check_total_timesteps, compose
-from .learner import CoordSumVec, LbfVec, RwareVec, MagpoLearner, SystemConfig, param_views
+from .learner import CoordSumVec, LbfVec, RwareVec, MagpoLearner, NetworkConfig, SystemConfig, param_views
 
 
 # ----------------------------------------------------------------------------- types (systems/gpo/types.py:25-83, mava/types.py:199-207)
@@ -34,15 +34,40 @@ class Params(NamedTuple):
     actor_params: Dict[str, torch.Tensor]
 
 
-class AdamState(NamedTuple):  # optax ScaleByAdamState
+class EmptyState(NamedTuple):  # optax.EmptyState: clip_by_global_norm and the constant-lr scale carry nothing
+    pass
+
+
+class ScaleByAdamState(NamedTuple):  # optax.ScaleByAdamState
     count: torch.Tensor
     mu: Dict[str, torch.Tensor]
     nu: Dict[str, torch.Tensor]
 
 
+class ScaleByScheduleState(NamedTuple):  # optax.ScaleByScheduleState (only with system.decay_learning_rates)
+    count: torch.Tensor
+
+
+AdamState = ScaleByAdamState  # the name this module used before the optax-shaped tree
+
+
+def optax_state(adam: ScaleByAdamState, scheduled: bool) -> tuple:
+    """The state tree of `optax.chain(optax.clip_by_global_norm(.), optax.adam(lr, eps=1e-5))` (rec_magpo.py:582-589, optax 0.2.4):
+    `(EmptyState(), (ScaleByAdamState(count, mu, nu), EmptyState() | ScaleByScheduleState(count)))` — adam itself is
+    chain(scale_by_adam, scale_by_learning_rate), whose second state is a schedule counter only when lr is a callable."""
+    return (EmptyState(), (adam, ScaleByScheduleState(adam.count) if scheduled else EmptyState()))
+
+
+def adam_of(opt_state) -> ScaleByAdamState:
+    """The ScaleByAdamState inside an optax-shaped optimiser state (or the bare state itself)."""
+    if isinstance(opt_state, ScaleByAdamState):
+        return opt_state
+    return opt_state[1][0]
+
+
 class OptStates(NamedTuple):
-    guider_opt_state: AdamState
-    actor_opt_state: AdamState
+    guider_opt_state: tuple
+    actor_opt_state: tuple
 
 
 class SableHiddenStates(NamedTuple):
@@ -62,11 +87,12 @@ class Observation(NamedTuple):
     step_count: torch.Tensor
 
 
-class TimeStep(NamedTuple):
-    observation: Observation
+class TimeStep(NamedTuple):  # jumanji.types.TimeStep field order
+    step_type: torch.Tensor
     reward: torch.Tensor
     discount: torch.Tensor
-    step_type: torch.Tensor
+    observation: Observation
+    extras: Dict[str, Any]
 
 
 class GPOLearnerState(NamedTuple):
@@ -124,11 +150,41 @@ def make_env(config: Config):
     raise NotImplementedError(f"{name}: only CoordSum, LevelBasedForaging and RobotWarehouse dynamics are built")
 
 
+def _network_config(config: Config, env) -> NetworkConfig:
+    """`config.network` (configs/network/magpo.yaml) + env dims -> the shapes the kernels are built for. Everything the reference
+    reads is read here; a value the kernels do not cover raises instead of being silently ignored (the library's own
+    check_net returns MAGPO_ERR_UNSUPPORTED for the same shapes)."""
+    n = config.network
+    nc, mc = n.net_config, n.memory_config
+    if not bool(config.system.get("add_agent_id", True)):
+        raise NotImplementedError("system.add_agent_id=False: the env kernels emit the AgentIDWrapper observation only")
+    hidden = int(n.get("hidden_state_dim", 128))
+    an = n.get("actor_network")
+    if an is not None:
+        for name in ("pre_torso", "post_torso"):
+            t = an.get(name)
+            if t is None:
+                continue
+            if [int(x) for x in t.layer_sizes] != [hidden] or bool(t.get("use_layer_norm", False)) or t.get("activation", "relu") != "relu":
+                raise NotImplementedError(f"network.actor_network.{name}: only one Dense({hidden}) + relu layer without layer norm is built "
+                                          "(RecurrentActor of configs/network/magpo.yaml:19-31)")
+    # memory_config.timestep_chunk_size: chunking the sequence is mathematically exact (tests/test_oracle.py
+    # ::test_timestep_chunking_is_exact), the kernels always run their own chunked scan, so any value is accepted.
+    net = NetworkConfig(env.num_agents, env.obs_dim, env.action_dim, env.time_limit, embed_dim=int(nc.embed_dim), n_head=int(nc.n_head),
+                        n_block=int(nc.n_block), hidden=hidden, timestep_pe=bool(mc.get("timestep_positional_encoding", True)),
+                        decay_scaling_factor=float(mc.get("decay_scaling_factor", 0.8)))
+    c = net.c_struct()
+    if L.lib().magpo_param_count(C.byref(c), 0) < 0:
+        raise NotImplementedError(f"network configuration outside what the kernels implement: {net} "
+                                  "(built: embed_dim=64, n_head=1, n_block=1, hidden_state_dim=128, timestep PE on, <= 8 agents)")
+    return net
+
+
 def _system_config(config: Config) -> SystemConfig:
     s = config.system
-    if s.get("decay_learning_rates", False):
-        raise NotImplementedError("decay_learning_rates: only the constant schedule is built (utils/training.py:48-64)")
-    return SystemConfig(num_envs=int(config.arch.num_envs), update_batch_size=int(s.update_batch_size),
+    decay = bool(s.get("decay_learning_rates", False))
+    return SystemConfig(decay_learning_rates=decay, num_updates=int(s.get("num_updates") or 0) if decay else 0,
+                        num_envs=int(config.arch.num_envs), update_batch_size=int(s.update_batch_size),
                         rollout_length=int(s.rollout_length), ppo_epochs=int(s.ppo_epochs),
                         num_minibatches=int(s.num_minibatches), gamma=float(s.gamma), gae_lambda=float(s.gae_lambda),
                         clip_eps=float(s.clip_eps), ent_coef=float(s.ent_coef), vf_coef=float(s.vf_coef),
@@ -143,9 +199,13 @@ class ActorNetwork:
     def __init__(self, lrn: MagpoLearner):
         self.lrn = lrn
 
-    def apply(self, actor_flat: torch.Tensor, hstate: torch.Tensor, observation: Observation, done: torch.Tensor):
-        """observation leaves [T, N, A, ...], done [T, N], hstate [N, A, 128]. Returns (carry, logits [T, N, A, a] with
-        illegal actions at finfo.min). The carry is returned for T == 1 (the evaluator's per-step call); else None."""
+    def apply(self, actor_flat: torch.Tensor, hstate: torch.Tensor, observation_done: Tuple[Observation, torch.Tensor]):
+        """`RecurrentActor.__call__(policy_hidden_state, (observation, done))` (networks/base.py:161-165): observation leaves
+        [T, N, A, ...], done [T, N] (or [T, N, A]: constant over agents), hstate [N, A, 128]. Returns (carry, logits [T, N, A, a]
+        with illegal actions at finfo.min). The carry is returned for T == 1 (the evaluator's per-step call); else None."""
+        observation, done = observation_done
+        if done.dim() == 3:
+            done = done[..., 0]
         lrn = self.lrn
         T, N, A = observation.agents_view.shape[:3]
         a, dev = lrn.net.action_dim, lrn.dev
@@ -180,26 +240,56 @@ class ActorNetwork:
         return torch.zeros(n_envs, self.lrn.net.n_agents, self.lrn.net.hidden, device=self.lrn.dev)
 
 
-def _state_views(lrn: MagpoLearner) -> GPOLearnerState:
-    """The learner's device buffers as the reference's pytree, every leaf with the leading [1, U, ...] of this device."""
-    U, E, A = lrn.sys.update_batch_size, lrn.sys.num_envs, lrn.net.n_agents
-    T = lrn.sys.rollout_length
-    lead = lambda t: t.reshape(1, U, E, *t.shape[1:])          # per-env leaves [U*E, ...] -> [1, U, E, ...]
-    rep = lambda t: t.reshape(1, 1, *t.shape).expand(1, U, *t.shape)  # replicated leaves (params, optimiser, key)
-    tree = lambda flat, table: {k: rep(v) for k, v in param_views(flat, table).items()}
+def _cur_slot(lrn: MagpoLearner) -> int:
+    """Observation / done slot of the trajectory buffers that holds LearnerState.timestep: T after a rollout, 0 after reset."""
+    return 0 if lrn.first_rollout else lrn.sys.rollout_length
+
+
+def _replicated_views(lrn: MagpoLearner) -> Tuple[Params, OptStates, torch.Tensor]:
+    """(params, opt_states, key): the leaves every slot shares, as [1, U, ...] broadcast views of the flat device buffers."""
+    U = lrn.sys.update_batch_size
+    rep = lambda t: t.reshape(1, 1, *t.shape).expand(1, U, *t.shape)
+    tree = lambda flat, table: {k_: rep(v) for k_, v in param_views(flat, table).items()}
     params = Params(tree(lrn.guider, lrn.g_table), tree(lrn.actor, lrn.a_table))
-    opt = OptStates(AdamState(rep(lrn.g_count[0]), tree(lrn.g_mu, lrn.g_table), tree(lrn.g_nu, lrn.g_table)),
-                    AdamState(rep(lrn.a_count[0]), tree(lrn.a_mu, lrn.a_table), tree(lrn.a_nu, lrn.a_table)))
-    obs = Observation(lead(lrn.traj["agents_view"][T if not lrn.first_rollout else 0]),
-                      lead(lrn.traj["action_mask"][T if not lrn.first_rollout else 0]),
-                      lead(lrn.traj["step_count"][T if not lrn.first_rollout else 0]))
-    ts = TimeStep(obs, lead(lrn.ts["reward"]), lead(lrn.ts["discount"]), lead(lrn.ts["step_type"]))
-    done_env = lrn.traj["done"][T if not lrn.first_rollout else 0]
+    sched = bool(lrn.sys.decay_learning_rates)
+    opt = OptStates(optax_state(ScaleByAdamState(rep(lrn.g_count[0]), tree(lrn.g_mu, lrn.g_table), tree(lrn.g_nu, lrn.g_table)), sched),
+                    optax_state(ScaleByAdamState(rep(lrn.a_count[0]), tree(lrn.a_mu, lrn.a_table), tree(lrn.a_nu, lrn.a_table)), sched))
+    return params, opt, rep(lrn.key)
+
+
+def _state_views(lrn: MagpoLearner) -> GPOLearnerState:
+    """The learner's device buffers as the reference's pytree (systems/gpo/types.py:25-83), every leaf with the leading
+    [1, U, ...] of this device. Leaves are views of the device buffers wherever the reference's dtype and value allow it; the
+    leaves that need a conversion (CoordSum's int32 `agents_view`, `dones` as bool[E, A], the Sable states with the post-step reset
+    applied) are materialised copies, remembered in `lrn._exported` so that `_adopt` recognises them when they come back."""
+    U, E, A = lrn.sys.update_batch_size, lrn.sys.num_envs, lrn.net.n_agents
+    k = _cur_slot(lrn)
+    lead = lambda t: t.reshape(1, U, E, *t.shape[1:])          # per-env leaves [U*E, ...] -> [1, U, E, ...]
+    params, opt, key = _replicated_views(lrn)
+    exported = {}
+    view = lrn.traj["agents_view"][k]
+    nview = lrn.ts["next_agents_view"]
+    if lrn.env.kind == L.ENV_COORDSUM:  # AgentIDWrapper keeps the wrapped env's dtype: int32 for CoordSum (wrappers/observation.py:47-52)
+        view = exported["agents_view"] = view.to(torch.int32)
+        nview = nview.to(torch.int32)
+    mask = exported["action_mask"] = lrn.traj["action_mask"][k].bool()
+    obs = Observation(lead(view), lead(mask), lead(lrn.traj["step_count"][k]))
+    # extras of the wrapper stack (episode_metrics.py:98-102, auto_reset_wrapper.py:52-58, wrappers/{matrax,jumanji}.py): the real next
+    # observation's action mask is not materialised (nothing on this path reads extras["real_next_obs"])
+    extras = {"episode_metrics": {"episode_return": lead(lrn.ts["episode_return"]), "episode_length": lead(lrn.ts["episode_length"]),
+                                  "is_terminal_step": lead(lrn.ts["is_terminal_step"]).bool()},
+              "env_metrics": {},
+              "real_next_obs": Observation(lead(nview), None, lead(lrn.ts["next_step_count"]))}
+    ts = TimeStep(lead(lrn.ts["step_type"]), lead(lrn.ts["reward"]), lead(lrn.ts["discount"]), obs, extras)
+    done_env = lrn.traj["done"][k]
+    dones = exported["dones"] = lead(done_env)[..., None].expand(1, U, E, A).bool()
     sable = lrn.sable_hidden_state() if not lrn.first_rollout else lrn.hs
-    hs = HiddenStates(SableHiddenStates(*(lead(sable[k]).reshape(1, U, E, 1, 1, 64, 64)
-                                          for k in ("encoder", "decoder_self", "decoder_cross"))), lead(lrn.policy_h))
-    return GPOLearnerState(params, opt, rep(lrn.key), {k: lead(v) for k, v in lrn.env_state.items()}, ts,
-                           lead(done_env)[..., None].expand(1, U, E, A).bool(), hs)
+    for name in ("encoder", "decoder_self", "decoder_cross"):
+        exported["sable/" + name] = sable[name]
+    hs = HiddenStates(SableHiddenStates(*(lead(sable[n_]).reshape(1, U, E, 1, 1, 64, 64)
+                                          for n_ in ("encoder", "decoder_self", "decoder_cross"))), lead(lrn.policy_h))
+    lrn._exported = exported
+    return GPOLearnerState(params, opt, key, {k_: lead(v) for k_, v in lrn.env_state.items()}, ts, dones, hs)
 
 
 def _flatten(x, prefix=""):
@@ -215,15 +305,59 @@ def _flatten(x, prefix=""):
 
 
 def _adopt(lrn: MagpoLearner, state: GPOLearnerState) -> None:
-    """Copy the writable leaves (params, optimiser state, key) of a foreign state into the learner's buffers. Leaves that are
-    views of those buffers already (the state `learn` returned) cost nothing."""
-    mine = dict(_flatten((_state_views(lrn).params, _state_views(lrn).opt_states, _state_views(lrn).key)))
-    theirs = dict(_flatten((state.params, state.opt_states, state.key)))
-    for name, dst in mine.items():
-        src = theirs[name]
-        if src.data_ptr() != dst.data_ptr():
-            # replicated leaves: slot 0 of the foreign state is the value (identical across U, rec_magpo.py:660-673)
-            dst[0, 0].copy_(src[0, 0].to(dst.dtype))
+    """Make the learner's buffers hold `state` (systems/gpo/types.py:62-71: params, opt_states, key, env_state, timestep, dones,
+    hstates). Leaves that are the learner's own views / exports (the state `learn` returned last) cost nothing; anything else — a
+    restored checkpoint, a state edited by the caller — is copied in. `timestep.step_type / reward / discount` are outputs of the
+    env step only (`_env_step`, rec_magpo.py:126-187, reads `observation` and `last()`, which `dones` carries) and are copied too;
+    `extras` are per-step outputs and are not adopted. A component given as None is left as it is (rec_sable has no learner half)."""
+    exported = getattr(lrn, "_exported", {})  # keeps the copies handed out last alive, so a pointer match is an identity match
+    U, E = lrn.sys.update_batch_size, lrn.sys.num_envs
+    params, opt, key = _replicated_views(lrn)
+    # replicated leaves: slot 0 of the foreign state is the value (identical across U, rec_magpo.py:660-673)
+    pairs = [(params.guider_params, state.params.guider_params), (params.actor_params, state.params.actor_params), (key, state.key)]
+    for m_opt, t_opt in zip(opt, state.opt_states):
+        pairs.append((adam_of(m_opt), None if t_opt is None else adam_of(t_opt)))
+    for m_tree, t_tree in pairs:
+        if t_tree is None:
+            continue
+        theirs = dict(_flatten(t_tree))
+        for name, dst in _flatten(m_tree):
+            src = theirs[name]
+            if src.data_ptr() != dst.data_ptr():
+                dst[0, 0].copy_(src[0, 0].to(dst.dtype))
+    # per-env leaves: [1, U, E, ...] -> the learner's [U*E, ...] buffers
+    flat = lambda t: t.reshape(U * E, *t.shape[3:])
+
+    def take(dst: torch.Tensor, src, key_: str | None = None) -> None:
+        if src is None:
+            return
+        if key_ in exported and src.data_ptr() == exported[key_].data_ptr() and src.dtype == exported[key_].dtype:
+            return  # the copy this learner exported, unchanged
+        if src.data_ptr() == dst.data_ptr() and src.dtype == dst.dtype:
+            return  # a view of the buffer itself
+        dst.copy_(flat(src).reshape(dst.shape).to(dst.dtype))
+
+    theirs_env = dict(state.env_state)
+    for name, dst in lrn.env_state.items():
+        take(dst, theirs_env[name])
+    k = _cur_slot(lrn)
+    ob = state.timestep.observation
+    take(lrn.traj["agents_view"][k], ob.agents_view, "agents_view")
+    take(lrn.traj["action_mask"][k], ob.action_mask, "action_mask")
+    take(lrn.traj["step_count"][k], ob.step_count)
+    for name in ("step_type", "reward", "discount"):
+        take(lrn.ts[name], getattr(state.timestep, name))
+    if state.dones is not None:
+        if not ("dones" in exported and state.dones.data_ptr() == exported["dones"].data_ptr()):
+            lrn.traj["done"][k].copy_(flat(state.dones)[:, 0].to(torch.uint8))
+    elif state.timestep.step_type.data_ptr() != lrn.ts["step_type"].data_ptr():  # rec_sable's state has no `dones`: timestep.last()
+        lrn.traj["done"][k].copy_((flat(state.timestep.step_type) == 2).to(torch.uint8))
+    sh = state.hstates.sable_hidden_state
+    for name, src in (("encoder", sh.encoder), ("decoder_self", sh.decoder_self_retn), ("decoder_cross", sh.decoder_cross_retn)):
+        ex = exported.get("sable/" + name)
+        if (ex is None or src.data_ptr() != ex.data_ptr()) and src.data_ptr() != lrn.hs[name].data_ptr():
+            lrn.hs[name].copy_(src.reshape(U * E, 64, 64).to(torch.float32))
+    take(lrn.policy_h, state.hstates.policy_hidden_state)
 
 
 def get_learner_fn(lrn: MagpoLearner, config: Config) -> LearnerFn:
@@ -277,7 +411,8 @@ def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, 
     key, actor_net_key, net_key = keys
     config.system.num_agents = env.num_agents  # rec_magpo.py:541-543
     config.system.num_actions = env.action_dim
-    lrn = MagpoLearner(env, _system_config(config), device=device, allreduce=allreduce, world_size=world_size)
+    lrn = MagpoLearner(env, _system_config(config), device=device, allreduce=allreduce, world_size=world_size,
+                       net=_network_config(config, env))
     # parameters: flax's orthogonal/normal initialisers cannot be reproduced bit-for-bit without jax; same shapes, same
     # gains, NumPy generator seeded from the net keys
     lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, int(np.asarray(net_key)[-1])),

@@ -28,7 +28,7 @@ from .learner import MagpoLearner
 class LearnerState(NamedTuple):
     """mava/systems/sable/types.py LearnerState; every leaf with the leading [1, U, ...] of this device."""
     params: Dict[str, torch.Tensor]
-    opt_states: rm.AdamState
+    opt_states: tuple  # optax.chain(clip_by_global_norm, adam) state, see rec_magpo.optax_state
     key: torch.Tensor
     env_state: Dict[str, torch.Tensor]
     timestep: rm.TimeStep
@@ -47,11 +47,10 @@ def get_learner_fn(lrn: MagpoLearner, config: Config):
     U, E = lrn.sys.update_batch_size, lrn.sys.num_envs
 
     def learn(learner_state: LearnerState) -> rm.ExperimentOutput:
-        mine, theirs = dict(rm._flatten(tuple(_state_views(lrn)[:3]))), dict(rm._flatten(tuple(learner_state[:3])))
-        for name, dst in mine.items():  # adopt foreign params / optimiser state / key
-            src = theirs[name]
-            if src.data_ptr() != dst.data_ptr():
-                dst[0, 0].copy_(src[0, 0].to(dst.dtype))
+        # adopt a foreign state (checkpoint restore, edited leaves); the state `learn` returned last costs nothing
+        rm._adopt(lrn, rm.GPOLearnerState(rm.Params(learner_state.params, None), rm.OptStates(learner_state.opt_states, None),
+                                          learner_state.key, learner_state.env_state, learner_state.timestep, None,
+                                          rm.HiddenStates(learner_state.hstates, None)))
         ep = {k: [] for k in ("episode_return", "episode_length", "is_terminal_step")}
         tr = []
         for _ in range(n_upd):
@@ -76,7 +75,8 @@ def learner_setup(env, keys: Tuple[Any, Any], config: Config, device=None, allre
     key, net_key = keys
     sysc = rm._system_config(_with_magpo_defaults(config))
     sysc.sable_only = True
-    lrn = MagpoLearner(env, sysc, device=device or "cuda:0", allreduce=allreduce, world_size=world_size)
+    lrn = MagpoLearner(env, sysc, device=device or "cuda:0", allreduce=allreduce, world_size=world_size,
+                       net=rm._network_config(config, env))
     lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, int(np.asarray(net_key)[-1])),
                    minit.init_actor(env.obs_dim, env.action_dim, 0))  # the learner buffers exist but are never touched
     U, E = sysc.update_batch_size, sysc.num_envs

@@ -48,9 +48,10 @@ def eval_fn(spec, ncfg, actor_params, key, n_envs, episode_loops, greedy=False):
         state, ts = env_module(spec).reset(spec, prng.split(reset_key, n_envs))
         hidden = np.zeros((n_envs, ncfg.n_agents, ncfg.hidden), np.float32)
         lasts, ers, els = [], [], []
+        step_key = key  # mava/evaluator.py:139-146: the step scan's final key is discarded; `_episode` returns the post-reset key
         for _ in range(spec.time_limit + 1):
-            ks = prng.split(key)
-            key, act_key = ks[0], ks[1]
+            ks = prng.split(step_key)
+            step_key, act_key = ks[0], ks[1]
             action, hidden = eval_act(ap_t, ncfg, ts, act_key, hidden, greedy)
             state, ts = env_module(spec).step(spec, state, action)
             lasts.append(ts["step_type"] == ocs.STEP_LAST)
@@ -74,9 +75,10 @@ def eval_fn_sable(spec, ncfg, guider_params, key, n_envs, episode_loops):
         state, ts = env_module(spec).reset(spec, prng.split(reset_key, n_envs))
         hs = tuple(torch.zeros(hs_shape) for _ in range(3))
         lasts, ers, els = [], [], []
+        step_key = key  # mava/evaluator.py:139-146: the step scan's final key is discarded; `_episode` returns the post-reset key
         for _ in range(spec.time_limit + 1):
-            ks = prng.split(key)
-            key, act_key = ks[0], ks[1]
+            ks = prng.split(step_key)
+            step_key, act_key = ks[0], ks[1]
             ob = ts["observation"]
             with torch.no_grad():
                 action, _, _, hs = nets.sable_get_actions(gp_t, ncfg, torch.tensor(ob["agents_view"].astype(np.float32)),

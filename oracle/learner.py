@@ -54,6 +54,22 @@ class SysCfg:
     alpha: float = 1.0
     actor_lr: float = 2.5e-4
     sable_only: bool = False  # rec_sable (mava/systems/sable/anakin/rec_sable.py): Sable alone under PPO, no learner
+    decay_learning_rates: bool = False  # mava/utils/training.py:48-64
+    num_updates: int = 0
+
+
+def make_learning_rate(sys: "SysCfg", f=np.float32):
+    """mava/utils/training.py:20-64 (rec_magpo.py:581): constant `actor_lr`, or the linear schedule
+    count -> init_lr * (1 - (count // (ppo_epochs * num_minibatches)) / num_updates) in float32 like the traced jnp code."""
+    if not sys.decay_learning_rates:
+        return sys.actor_lr
+    period = sys.ppo_epochs * sys.num_minibatches
+
+    def linear_schedule(count: int):
+        frac = f(1.0) - f(count // period) / f(sys.num_updates)
+        return f(sys.actor_lr) * frac
+
+    return linear_schedule
 
 
 # ----------------------------------------------------------------------------- GAE
@@ -76,25 +92,27 @@ def gae(done, value, reward, last_val, last_done, gamma, lam):
 
 
 # ----------------------------------------------------------------------------- optimiser
-def clip_adam_step(params, grads, opt, lr, max_norm, b1=0.9, b2=0.999, eps=1e-5):
-    """optax.chain(clip_by_global_norm, adam(lr, eps=1e-5)) + apply_updates (Appendix A11). In place, fp32."""
-    f = np.float32
+def clip_adam_step(params, grads, opt, lr, max_norm, b1=0.9, b2=0.999, eps=1e-5, f=np.float32):
+    """optax.chain(clip_by_global_norm, adam(lr, eps=1e-5)) + apply_updates (Appendix A11). In place, fp32
+    (`f=np.float64`: the same arithmetic in double, for the fp32-vs-fp64 tolerance control only). `lr` may be a
+    callable count -> learning rate (optax schedule, evaluated at the count BEFORE the increment)."""
     sq = f(0.0)
     for k in grads:
-        sq += f(np.sum(grads[k].astype(np.float32) ** 2, dtype=np.float32))
+        sq += f(np.sum(grads[k].astype(f) ** 2, dtype=f))
     gnorm = f(np.sqrt(sq))
+    step_lr = lr(int(opt["count"])) if callable(lr) else lr
     opt["count"] = int(opt["count"]) + 1
     c = opt["count"]
-    bc1 = f(1) - f(np.power(f(b1), c, dtype=np.float32))
-    bc2 = f(1) - f(np.power(f(b2), c, dtype=np.float32))
+    bc1 = f(1) - f(np.power(f(b1), c, dtype=f))
+    bc2 = f(1) - f(np.power(f(b2), c, dtype=f))
     for k in params:
-        g = grads[k].astype(np.float32)
+        g = grads[k].astype(f)
         if not (gnorm < f(max_norm)):
             g = (g / gnorm) * f(max_norm)
-        mu = opt["mu"][k] = (f(b1) * opt["mu"][k] + f(1 - b1) * g).astype(np.float32)
-        nu = opt["nu"][k] = (f(b2) * opt["nu"][k] + f(1 - b2) * g * g).astype(np.float32)
+        mu = opt["mu"][k] = (f(b1) * opt["mu"][k] + f(1 - b1) * g).astype(f)
+        nu = opt["nu"][k] = (f(b2) * opt["nu"][k] + f(1 - b2) * g * g).astype(f)
         u = (mu / bc1) / (np.sqrt(nu / bc2) + f(eps))
-        params[k] = (params[k] + u * f(-lr)).astype(np.float32)
+        params[k] = (params[k] + u * f(-step_lr)).astype(f)
     return gnorm
 
 
@@ -214,8 +232,8 @@ def minibatch_losses_and_grads(gp_np, ap_np, mb_np, ncfg: nets.NetCfg, sys: SysC
     tot_a, (a_loss, kl_a) = actor_loss(a_logits, g_logits, mb, sys)
     gg = torch.autograd.grad(tot_g, list(gp.values()), allow_unused=True, retain_graph=True)
     ga = torch.autograd.grad(tot_a, list(ap.values()), allow_unused=True)
-    g_grads = {k: (np.zeros_like(gp_np[k]) if g is None else g.detach().to(torch.float32).numpy()) for k, g in zip(gp, gg)}
-    a_grads = {k: (np.zeros_like(ap_np[k]) if g is None else g.detach().to(torch.float32).numpy()) for k, g in zip(ap, ga)}
+    g_grads = {k: (np.zeros_like(gp_np[k]) if g is None else g.detach().to(dtype).numpy()) for k, g in zip(gp, gg)}
+    a_grads = {k: (np.zeros_like(ap_np[k]) if g is None else g.detach().to(dtype).numpy()) for k, g in zip(ap, ga)}
     info = dict(
         total_loss=float(tot_g.detach()) + float(tot_a.detach()), value_loss=float(v_loss.detach()), actor_loss=float(a_loss.detach()),
         guider_loss=float(g_loss.detach()), kl_loss=float(kl_g.detach()), entropy=float(ent.detach()),
@@ -338,9 +356,13 @@ def learner_setup(spec, ncfg: nets.NetCfg, sys: SysCfg, seed: int = 42, n_device
     return dict(guider_params=gp, actor_params=ap, guider_opt=init_opt(gp), actor_opt=init_opt(ap), slots=slots)
 
 
-def update_step(state, spec, ncfg: nets.NetCfg, sys: SysCfg, grad_allreduce=None, record=None):
+def update_step(state, spec, ncfg: nets.NetCfg, sys: SysCfg, grad_allreduce=None, record=None, dtype=torch.float32):
     """_update_step (rec_magpo.py:106-499) for all U slots of one device. `grad_allreduce(flat)->flat`
-    stands in for the pmean over "device". `record` (dict) collects intermediates for parity tests."""
+    stands in for the pmean over "device". `record` (dict) collects intermediates for parity tests.
+    `dtype=torch.float64` runs the update's network math, gradient mean and Adam in double (the rollout stays fp32):
+    the reference point of the fp32-vs-fp64 tolerance control (tools/tolerance_control.py), never a parity target."""
+    f = np.float64 if dtype == torch.float64 else np.float32
+    lr = make_learning_rate(sys, f)
     U, P, M = sys.update_batch_size, sys.ppo_epochs, sys.num_minibatches
     trajs, advs, tgts, prevs, mets = [], [], [], [], []
     for slot in state["slots"]:
@@ -368,19 +390,19 @@ def update_step(state, spec, ncfg: nets.NetCfg, sys: SysCfg, grad_allreduce=None
         for m in range(M):
             gsum, asum, infos = None, None, []
             for u in range(U):
-                gg, ga, info, aux = minibatch_losses_and_grads(state["guider_params"], state["actor_params"], mbs[u][m], ncfg, sys)
+                gg, ga, info, aux = minibatch_losses_and_grads(state["guider_params"], state["actor_params"], mbs[u][m], ncfg, sys, dtype)
                 gsum = gg if gsum is None else {k: gsum[k] + gg[k] for k in gg}
                 asum = ga if asum is None else {k: asum[k] + ga[k] for k in ga}
                 infos.append(info)
-            gmean = {k: (v / np.float32(U)).astype(np.float32) for k, v in gsum.items()}
-            amean = {k: (v / np.float32(U)).astype(np.float32) for k, v in asum.items()}
+            gmean = {k: (v / f(U)).astype(f) for k, v in gsum.items()}
+            amean = {k: (v / f(U)).astype(f) for k, v in asum.items()}
             info = {k: float(np.mean([i[k] for i in infos])) for k in infos[0]}
             if grad_allreduce is not None:
                 gmean, amean, info = grad_allreduce(gmean, amean, info)
             if record is not None:
                 record["grads"].append((gmean, amean))
-            clip_adam_step(state["guider_params"], gmean, state["guider_opt"], sys.actor_lr, sys.max_grad_norm)
-            clip_adam_step(state["actor_params"], amean, state["actor_opt"], sys.actor_lr, sys.max_grad_norm)
+            clip_adam_step(state["guider_params"], gmean, state["guider_opt"], lr, sys.max_grad_norm, f=f)
+            clip_adam_step(state["actor_params"], amean, state["actor_opt"], lr, sys.max_grad_norm, f=f)
             loss_infos.append(info)
     for u, slot in enumerate(state["slots"]):
         slot["key"] = keys[u]

@@ -82,7 +82,7 @@ def test_rec_sable_system_entry(dev):
     for v in out.train_metrics.values():
         assert v.shape == (1, 2, U, P, M) and torch.isfinite(v).all()
     assert out.episode_metrics["episode_return"].shape == (1, 2, U, T, E)
-    assert int(out.learner_state.opt_states.count[0, 0]) == 2 * P * M
+    assert int(rm.adam_of(out.learner_state.opt_states).count[0, 0]) == 2 * P * M
     assert not torch.equal(out.learner_state.params["decoder/head/layers_3/kernel"][0, 0], w0)
     lines = []
     perf = rs.run_experiment(compose("default/rec_sable", ["env=lbf", "arch.num_envs=8", "system.rollout_length=8", "system.num_updates=2",
