@@ -17,7 +17,7 @@ $(OBJ_DIR)/%.o: $(SRC_DIR)/%.cu $(HDRS)
 
 $(LIB): $(OBJS)
 	@mkdir -p $(dir $(LIB))
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
 
 clean:
 	rm -rf build $(LIB)

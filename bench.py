@@ -67,7 +67,7 @@ def workload_config(args, n_gpus):
                         f"update_batch_size={args.update_batch_size}, rollout_length={args.rollout_length}, ppo_epochs=4, "
                         f"num_minibatches=2, Sable D=64 + GRU H=128",
             "env": args.env, "num_envs": args.num_envs, "update_batch_size": args.update_batch_size, "rollout_length": args.rollout_length,
-            "ppo_epochs": 4, "num_minibatches": 2, "parallelism": f"dp{n_gpus}",
+            "ppo_epochs": 4, "num_minibatches": 2, "parallelism": f"dp{n_gpus}", "collective": "magpo_comm_allreduce_sum (NCCL via the C ABI), issued inside magpo_minibatch_grads" if n_gpus > 1 else None,
             "l2": "working set per step (>10 GB of activations + 400 MB of Sable state) exceeds the 126 MB L2"}
 
 
@@ -171,7 +171,6 @@ def run():
 
     import numpy as np
     import torch
-    import torch.distributed as dist
 
     from magpo_b200 import _lib as L
     from magpo_b200 import init as minit
@@ -181,15 +180,17 @@ def run():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    allreduce = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    comm = None
+    if world > 1:  # one process per GPU; the gradient exchange is the library's own NCCL all-reduce (magpo_comm_*, include/magpo_b200.h)
+        from magpo_b200.comm import NcclComm
+        comm = NcclComm.from_env(dev)
 
     env = {"lbf": LbfVec, "rware": RwareVec, "rware-small": RwareVec, "coordsum": CoordSumVec}[args.env](**WORKLOADS[args.env]["kw"])
     sysc = SystemConfig(num_envs=args.num_envs, update_batch_size=args.update_batch_size, rollout_length=args.rollout_length,
                         chunk_envs=args.chunk_envs)
-    lrn = MagpoLearner(env, sysc, device=dev, allreduce=allreduce, world_size=world)
+    lrn = MagpoLearner(env, sysc, device=dev, world_size=world)
+    if comm is not None:
+        comm.attach(lrn)  # magpo_minibatch_grads reduces the gradients itself, the learner's half under the guider's backward
     lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, 0), minit.init_actor(env.obs_dim, env.action_dim, 1))
     env_keys, step_key, _ = minit.setup_keys(42, world, sysc.update_batch_size, sysc.num_envs, dev)
     lrn.reset(env_keys[rank], step_key)
@@ -199,8 +200,8 @@ def run():
     lib.magpo_launch_count.restype = C.c_int64
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        if comm is not None:
+            comm.barrier()
         torch.cuda.synchronize()
 
     def timed(fn, k):
@@ -212,8 +213,8 @@ def run():
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if comm is not None:
+            comm.allreduce_max(ms)
         return float(ms.item()) / k
 
     for _ in range(1 if args.quick else max(3, args.warmup)):
@@ -332,9 +333,9 @@ def run():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt, cores, sample, _, _ = run_reference(args, as_baseline=True)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if comm is not None:
+        comm.barrier()
+        comm.close()
     return json.dumps(out) if rank == 0 else None
 
 

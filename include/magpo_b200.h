@@ -5,9 +5,10 @@
  * offers is the Python calling convention inside mava/systems/gpo/anakin/rec_magpo.py.  Each
  * entry point below cites the reference code it replaces.  Conventions (shaped so that an
  * XLA-FFI handler `XLA_FFI_Error* h(XLA_FFI_CallFrame*)` can wrap each op 1:1):
- *   - first argument is the CUDA stream (cudaStream_t passed as void*); all work is enqueued
- *     on it, nothing synchronises, nothing allocates: every buffer is a caller-owned DEVICE
- *     pointer, scratch is passed explicitly and sized by the matching *_workspace_bytes();
+ *   - the CUDA stream (cudaStream_t passed as void*) comes first, after the per-device MagpoContext* for the entry points that
+ *     need one (see below); all work is enqueued on that stream (forked context streams are joined back before the call
+ *     returns), nothing synchronises, nothing allocates: every buffer is a caller-owned DEVICE pointer, scratch is passed
+ *     explicitly and sized by the matching *_workspace_bytes(); there is no process-global state;
  *   - POD attribute structs by const pointer; no torch / C++ types in any signature;
  *   - return 0 on success, a negative MAGPO_ERR_* otherwise (no exceptions cross the ABI);
  *   - single host thread per device (the reference path is single-threaded).
@@ -34,8 +35,21 @@ enum {
 };
 
 const char* magpo_version(void);
+
 /* cudaGetLastError() text of the most recent MAGPO_ERR_CUDA on this thread. */
 const char* magpo_last_cuda_error(void);
+
+/* ------------------------------------------------------------------ context
+ * Per-device context, created by the caller and passed to every entry point that needs more than its arguments: the entry points that
+ * fork work onto side streams (rollout, minibatch_grads, guider_forward) or that look up the TF32 images of weight matrices they
+ * prepared in the caller's workspace (all GEMM users). It owns three non-blocking streams with their fork / join events and a
+ * host-side table of prepared weight regions; nothing in the library is process-global, so several learners — on the same device
+ * or on different ones — can be driven from one process and interleaved freely. A context is bound to the device it was created
+ * on: calling with another device current returns MAGPO_ERR_ARG. One host thread at a time per context. The remaining entry points
+ * (PRNG, envs, GAE, shuffle / pack, clip+Adam) are stateless and take no context. */
+typedef struct MagpoContext MagpoContext;
+int magpo_context_create(int32_t device /* CUDA ordinal, < 0: the current device */, MagpoContext** out);
+int magpo_context_destroy(MagpoContext* ctx);
 
 /* ------------------------------------------------------------------ configuration */
 
@@ -258,7 +272,7 @@ size_t magpo_rollout_workspace_bytes(const MagpoNetCfg* net, int32_t B, int32_t 
  *   left by the previous call).  The Sable states in `hs` are stored WITHOUT the reset of rec_magpo.py:165-169;
  *   the reset is applied from traj.done when they are next read (and when they are copied to traj.sable_h0), so
  *   the reference's hstates are `where(done[T], 0, hs)`. */
-int magpo_rollout(magpo_stream_t s, const MagpoNetCfg* net, const MagpoSysCfg* sys, int env_kind,
+int magpo_rollout(MagpoContext* ctx, magpo_stream_t s, const MagpoNetCfg* net, const MagpoSysCfg* sys, int env_kind,
                   const void* env_cfg, void* env_state, MagpoTimeStep ts, const float* guider,
                   const float* actor, uint32_t* key, MagpoSableHState hs, float* policy_h,
                   MagpoTrajectory traj, int32_t carry_over, void* workspace, size_t workspace_bytes);
@@ -267,7 +281,7 @@ int magpo_rollout(magpo_stream_t s, const MagpoNetCfg* net, const MagpoSysCfg* s
  * sample_keys [A,2]: the per-agent `sample_key`s of discrete_autoregressive_act (decode.py:140);
  * gumbel_rows E: noise index of env b is (b % E)*a + j.  Updates hs in place (decay included).
  * Any of action/log_prob/logits may be NULL; with action==NULL only the encoder/value runs. */
-int magpo_sable_get_actions(magpo_stream_t s, const MagpoNetCfg* net, int32_t B, int32_t gumbel_rows,
+int magpo_sable_get_actions(MagpoContext* ctx, magpo_stream_t s, const MagpoNetCfg* net, int32_t B, int32_t gumbel_rows,
                             const float* guider, const float* agents_view, const uint8_t* action_mask,
                             const int32_t* step_count, const uint8_t* prev_done /*[B] or NULL*/,
                             const uint32_t* sample_keys, MagpoSableHState hs, int32_t* action,
@@ -275,7 +289,7 @@ int magpo_sable_get_actions(magpo_stream_t s, const MagpoNetCfg* net, int32_t B,
                             void* workspace, size_t workspace_bytes);
 
 /* RecurrentActor.apply with a length-1 time axis (rec_magpo.py:146-159): h <- GRU(h, obs, done). */
-int magpo_actor_step(magpo_stream_t s, const MagpoNetCfg* net, int32_t B, const float* actor,
+int magpo_actor_step(MagpoContext* ctx, magpo_stream_t s, const MagpoNetCfg* net, int32_t B, const float* actor,
                      const float* agents_view, const uint8_t* done /*[B]*/, float* policy_h,
                      void* workspace, size_t workspace_bytes);
 
@@ -329,19 +343,22 @@ size_t magpo_update_workspace_bytes(const MagpoNetCfg* net, int32_t T, int32_t N
  *   inv_tokens = 1 / (U * (E/M) * T * A): weight of one token in the slot-averaged mean losses (:395-405).
  *   grads : [n_guider + n_actor + 8] flat, ACCUMULATED into (zero it per optimiser step): guider grads |
  *           learner grads | {-, guider_loss, entropy, value_loss, kl_loss, -, actor_loss, actor_kl}
- *           — the buffer the caller all-reduces over devices (the pmean over "device", :399-409). */
-int magpo_minibatch_grads(magpo_stream_t s, const MagpoNetCfg* net, const MagpoSysCfg* sys,
+ *           — the buffer that is all-reduced over devices (the pmean over "device", :399-409): with reduce_grads != 0 and a
+ *           communicator attached to the context (magpo_context_set_comm) this call does it itself — sum over ranks, the learner's
+ *           half + loss sums on the learner's stream under the guider's remaining backward, the guider's half at the end; pass
+ *           reduce_grads only with the LAST env chunk of a minibatch. Otherwise the caller reduces (magpo_comm_allreduce_sum). */
+int magpo_minibatch_grads(MagpoContext* ctx, magpo_stream_t s, const MagpoNetCfg* net, const MagpoSysCfg* sys,
                           const float* guider, const float* actor, MagpoMinibatch mb, const int32_t* env_slot,
-                          const float* adv_stats, float inv_tokens, float* grads, void* workspace,
-                          size_t workspace_bytes);
+                          const float* adv_stats, float inv_tokens, float* grads, int32_t reduce_grads,
+                          void* workspace, size_t workspace_bytes);
 
 /* Forward-only pieces of the above, exposed for parity tests:
  * SableNetwork.__call__ (sable_network.py:412-441): value [T,N,A], masked logits [T,N,A,a]. */
-int magpo_guider_forward(magpo_stream_t s, const MagpoNetCfg* net, const float* guider,
+int magpo_guider_forward(MagpoContext* ctx, magpo_stream_t s, const MagpoNetCfg* net, const float* guider,
                          MagpoMinibatch mb, float* value, float* logits, void* workspace,
                          size_t workspace_bytes);
 /* RecurrentActor.apply over T steps (rec_magpo.py:243-250): masked logits [T,N,A,a]. */
-int magpo_actor_forward(magpo_stream_t s, const MagpoNetCfg* net, const float* actor,
+int magpo_actor_forward(MagpoContext* ctx, magpo_stream_t s, const MagpoNetCfg* net, const float* actor,
                         MagpoMinibatch mb, float* logits, void* workspace, size_t workspace_bytes);
 
 /* optax.chain(clip_by_global_norm(max_norm), adam(lr, eps=1e-5)) + apply_updates
@@ -356,6 +373,22 @@ int magpo_clip_adam(magpo_stream_t s, int64_t n, float* params, const float* gra
 int magpo_clip_adam_sched(magpo_stream_t s, int64_t n, float* params, const float* grads, float* mu,
                           float* nu, int32_t* count, float grad_scale, float lr, int32_t decay_period,
                           int32_t num_updates, float max_norm, float* scratch);
+
+/* ------------------------------------------------------------------ data-parallel exchange
+ * `jax.lax.pmean(..., "device")` (rec_magpo.py:399-409) as NCCL all-reduces over NVLink / NVSwitch, one process per GPU. libnccl.so.2
+ * is resolved with dlopen at first use (no link-time dependency). Bootstrap: rank 0 calls magpo_comm_unique_id, the 128 bytes reach
+ * the other ranks by any host channel (the launcher's key-value store), every rank calls magpo_comm_init with its device current.
+ * The reductions are sums; the mean's 1/Nd is magpo_clip_adam's grad_scale. */
+typedef struct MagpoComm MagpoComm;
+int magpo_comm_available(void); /* 1 if libnccl could be loaded */
+int magpo_comm_version(void);   /* ncclGetVersion code, 0 if unavailable */
+int magpo_comm_unique_id(void* id128 /* out: 128 bytes */);
+int magpo_comm_init(int32_t nranks, int32_t rank, const void* id128, MagpoComm** out);
+int magpo_comm_destroy(MagpoComm* comm);
+int magpo_comm_allreduce_sum(MagpoComm* comm, magpo_stream_t s, float* buf, int64_t n); /* in place, enqueued on s */
+int magpo_comm_allreduce_max(MagpoComm* comm, magpo_stream_t s, float* buf, int64_t n);
+/* Attach (or with NULL detach) the communicator magpo_minibatch_grads reduces through. The context does not own it. */
+int magpo_context_set_comm(MagpoContext* ctx, MagpoComm* comm);
 
 #ifdef __cplusplus
 }

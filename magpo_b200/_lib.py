@@ -110,6 +110,37 @@ def lib() -> C.CDLL:
     return _lib
 
 
+_contexts: dict = {}
+
+
+def create_context(device=None) -> vp:
+    """A new MagpoContext (include/magpo_b200.h) on `device` (torch device / ordinal; default: the current CUDA device). The caller
+    owns it: `destroy_context` when done. Every MagpoLearner creates its own."""
+    import torch
+
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    out = vp()
+    check(lib().magpo_context_create(int(idx), C.byref(out)), "magpo_context_create")
+    return out
+
+
+def destroy_context(ctx: vp) -> None:
+    if ctx:
+        lib().magpo_context_destroy(ctx)
+
+
+def context(device=None) -> vp:
+    """The shared per-device context of helper code that has no learner of its own (evaluator loops, tests, tools)."""
+    import torch
+
+    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    if idx not in _contexts:
+        _contexts[idx] = create_context(idx)
+    return _contexts[idx]
+
+
 def ptr(t) -> vp:
     """Device (or host) pointer of a torch tensor / None."""
     if t is None:

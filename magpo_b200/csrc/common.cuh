@@ -10,6 +10,7 @@
 namespace magpo {
 
 void set_cuda_error(cudaError_t e, const char* file, int line);
+void set_error_text(const char* msg);  // text returned by magpo_last_cuda_error() (also used for NCCL failures)
 
 #define MAGPO_CUDA_OK(expr)                                   \
   do {                                                        \
@@ -45,6 +46,52 @@ struct ProfScope {
     int _r = (expr);             \
     if (_r != MAGPO_OK) return _r; \
   } while (0)
+
+// ---- per-device context (MagpoContext of the C ABI): everything an entry point needs besides its arguments. Created by the caller
+// (magpo_context_create), passed to every entry point that forks streams or looks up tensor-core weight images; nothing of it is
+// process-global, so several learners (and several devices) can be driven from one process.
+struct ForkJoin {  // a forked stream + the events that fork it off / join it back into the caller's stream
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int init();
+  void destroy();
+};
+struct TcRegion {  // a weight region whose TF32 hi / lo images exist (gemm_tc.cu)
+  const float* base;
+  int64_t n;
+  const float *hi, *lo;
+};
+}  // namespace magpo
+#include <vector>
+struct MagpoComm;
+struct MagpoContext {
+  int device = -1;
+  MagpoComm* comm = nullptr;  // data-parallel communicator (comm.cu), attached by magpo_context_set_comm
+  magpo::ForkJoin side;   // update: the learner's forward / backward beside the guider's (update.cu)
+  magpo::ForkJoin dec;    // guider forward: the decoder's encoder-independent prefix beside the encoder (sable.cu)
+  magpo::ForkJoin rside;  // rollout: the learner's GRU push beside the guider step kernel (rollout.cu)
+  std::vector<magpo::TcRegion> regions;
+};
+namespace magpo {
+using Context = ::MagpoContext;
+// The context of the entry point running on this thread. Entry points that take a MagpoContext* install it with CtxScope for the
+// duration of the call; the magpo_test_* hooks, which take none, get a thread-local scratch context.
+Context& ctx();
+struct CtxScope {
+  Context* prev;
+  bool ok;
+  explicit CtxScope(Context* c);
+  ~CtxScope();
+};
+#define MAGPO_CTX(c)             \
+  ::magpo::CtxScope _ctx_scope(c); \
+  if (!_ctx_scope.ok) return MAGPO_ERR_ARG
+// sum (op 0) / max (op 2) all-reduce of n floats in place over the communicator, enqueued on s; no-op for a single rank
+int comm_allreduce(MagpoComm* c, cudaStream_t s, float* buf, int64_t n, int op);
+// true exactly once per (device, id): guards cudaFuncSetAttribute, which is per device
+bool once_per_device(int id);
+enum { ONCE_GEMM_TC = 0, ONCE_GEMM_TN, ONCE_GRU_FWD, ONCE_GRU_BWD, ONCE_RET_FWD, ONCE_RET_BWD, ONCE_SABLE_STEP_1, ONCE_SABLE_STEP_2,
+       ONCE_SABLE_STEP_3, ONCE_SABLE_STEP_4, ONCE_NUM };
 
 constexpr int kNumSMs = 148;
 constexpr float kF32Min = -3.4028234663852886e+38f;  // jnp.finfo(float32).min

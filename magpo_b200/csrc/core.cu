@@ -14,6 +14,46 @@ void set_cuda_error(cudaError_t e, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
 }
 
+int ForkJoin::init() {
+  if (s) return MAGPO_OK;
+  MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  MAGPO_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  MAGPO_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+  return MAGPO_OK;
+}
+void ForkJoin::destroy() {
+  if (fork) cudaEventDestroy(fork);
+  if (join) cudaEventDestroy(join);
+  if (s) cudaStreamDestroy(s);
+  s = nullptr; fork = join = nullptr;
+}
+
+static thread_local Context* t_ctx = nullptr;
+Context& ctx() {
+  if (t_ctx) return *t_ctx;
+  static thread_local Context scratch;  // magpo_test_* hooks only
+  cudaGetDevice(&scratch.device);
+  return scratch;
+}
+CtxScope::CtxScope(Context* c) : prev(t_ctx), ok(false) {
+  int dev = -1;
+  if (!c || cudaGetDevice(&dev) != cudaSuccess || dev != c->device) return;  // a context is bound to the device it was created on
+  t_ctx = c;
+  ok = true;
+}
+CtxScope::~CtxScope() { t_ctx = prev; }
+
+bool once_per_device(int id) {
+  constexpr int kMaxDev = 64;
+  static std::atomic<bool> done[kMaxDev][ONCE_NUM];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev || id < 0 || id >= ONCE_NUM) return true;
+  return !done[dev][id].exchange(true);
+}
+
+void set_error_text(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
 static std::atomic<int64_t> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -43,6 +83,40 @@ ProfScope::~ProfScope() {
 }  // namespace magpo
 
 extern "C" {
+int magpo_context_create(int32_t device, MagpoContext** out) {
+  if (!out) return MAGPO_ERR_ARG;
+  int cur = -1, n = 0;
+  MAGPO_CUDA_OK(cudaGetDevice(&cur));
+  MAGPO_CUDA_OK(cudaGetDeviceCount(&n));
+  if (device < 0) device = cur;
+  if (device >= n) return MAGPO_ERR_ARG;
+  MagpoContext* c = new MagpoContext();
+  c->device = device;
+  // the forked streams belong to the context's device
+  int rc = MAGPO_OK;
+  if (cudaSetDevice(device) != cudaSuccess) rc = MAGPO_ERR_CUDA;
+  if (rc == MAGPO_OK) rc = c->side.init();
+  if (rc == MAGPO_OK) rc = c->dec.init();
+  if (rc == MAGPO_OK) rc = c->rside.init();
+  cudaSetDevice(cur);
+  if (rc != MAGPO_OK) {
+    c->side.destroy(); c->dec.destroy(); c->rside.destroy();
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return MAGPO_OK;
+}
+int magpo_context_destroy(MagpoContext* c) {
+  if (!c) return MAGPO_OK;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  cudaSetDevice(c->device);
+  c->side.destroy(); c->dec.destroy(); c->rside.destroy();
+  cudaSetDevice(cur);
+  delete c;
+  return MAGPO_OK;
+}
 int64_t magpo_launch_count(void) { return magpo::g_launches.load(); }
 // A host that replays a captured graph of library calls adds the launches of each replay (negative n: undo a capture pass).
 int magpo_launch_count_add(int64_t n) {

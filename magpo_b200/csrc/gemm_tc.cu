@@ -407,18 +407,11 @@ bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int cols, int ld,
              swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct TcRegion {
-  const float* base;
-  int64_t n;
-  const float *hi, *lo;
-};
-std::vector<TcRegion> g_regions;
 bool env_tc_default() {
   const char* e = getenv("MAGPO_TENSOR_CORES");  // "0" forces the fp32 SIMT GEMMs everywhere
   return !(e && e[0] == '0');
 }
 bool g_tc_enabled = env_tc_default();
-bool g_attr_set = false;
 
 }  // namespace
 
@@ -436,6 +429,7 @@ int tc_prepare_region(cudaStream_t s, const float* base, int64_t n, float* hi, f
   // Workspaces are re-planned between calls (rollout vs. update, different T/N): drop every older registration whose
   // source range touches memory this one claims (its source or its hi/lo images) — a stale range must never match.
   auto overlaps = [](const float* a, int64_t na, const float* b, int64_t nb) { return a < b + nb && b < a + na; };
+  std::vector<TcRegion>& g_regions = ctx().regions;
   for (size_t i = 0; i < g_regions.size();) {
     const TcRegion& r = g_regions[i];
     if (overlaps(r.base, r.n, base, n) || overlaps(r.base, r.n, hi, n) || overlaps(r.base, r.n, lo, n) ||
@@ -449,6 +443,7 @@ int tc_prepare_region(cudaStream_t s, const float* base, int64_t n, float* hi, f
 }
 
 bool tc_lookup(const float* w, const float** hi, const float** lo) {
+  const std::vector<TcRegion>& g_regions = ctx().regions;
   for (auto it = g_regions.rbegin(); it != g_regions.rend(); ++it) {
     const TcRegion& r = *it;
     if (w >= r.base && w < r.base + r.n) {
@@ -510,10 +505,8 @@ int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
   if (!make_map(&tmX, X, M, K, ldx, TC_BM) || !make_map(&tmBh, Bhi, N, K, ldb, p.BN) || !make_map(&tmBl, Blo, N, K, ldb, p.BN) ||
       !make_map(&tmY, Y, M, N, ldy, TC_BM))
     return MAGPO_ERR_ARG;
-  if (!g_attr_set) {
+  if (once_per_device(ONCE_GEMM_TC))
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-    g_attr_set = true;
-  }
   const int n_tiles = N / p.BN;
   dim3 grid((unsigned)std::max(1, std::min(p.num_row_tiles, kNumSMs / n_tiles)), (unsigned)n_tiles);
   ProfScope ps(M < 65536 ? PROF_GEMM_SMALL : PROF_GEMM_NN, s, 2.0 * (double)M * N * K, 4.0 * (double)M * (K + N + ((flags & GEMM_ACCUMULATE) ? N : 0)));
@@ -567,11 +560,8 @@ int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx,
   if (!make_map(&tmX, X, M, K, ldx, TN_RC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
       !make_map(&tmDY, dY, M, N, ldy, TN_RC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) || !make_map(&tmDW, dW, K, N, ldw, K))
     return MAGPO_ERR_ARG;
-  static bool attr = false;
-  if (!attr) {
+  if (once_per_device(ONCE_GEMM_TN))
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-    attr = true;
-  }
   ProfScope ps(PROF_GEMM_TN, s, 2.0 * (double)M * N * K, 4.0 * (double)M * (K + N));
   gemm_tc_tn_kernel<<<dim3((unsigned)gx, (unsigned)n_tiles), TC_THREADS, smem, s>>>(tmX, tmDY, tmDW, p);
   MAGPO_LAUNCH_OK();

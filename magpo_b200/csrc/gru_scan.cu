@@ -559,11 +559,8 @@ int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const flo
   const int64_t Rs = (int64_t)N * A;
   CUtensorMap tmh, tml;
   if (!tc_make_map(&tmh, WhT_hi, 3 * kH, kH, kH, 32) || !tc_make_map(&tml, WhT_lo, 3 * kH, kH, kH, 32)) return MAGPO_ERR_ARG;
-  static bool attr = false;
-  if (!attr) {
+  if (once_per_device(ONCE_GRU_FWD))
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
-    attr = true;
-  }
   const int rpt = gru_rows_per_tile(Rs);
   GruFwdArgs a{g_gru_dbg, T, N, A, Rs, rpt, gi, bhn, done, rzn, ghn, Y, HU};
   // per row and step: 3xTF32 MMAs are the pipe work; bytes: gi 1536 read, rzn+ghn+Y+HU 3072 written
@@ -579,11 +576,8 @@ int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const flo
   const int64_t Rs = (int64_t)N * A;
   CUtensorMap tmh, tml;
   if (!tc_make_map(&tmh, Wh_hi, kH, 3 * kH, 3 * kH, 128) || !tc_make_map(&tml, Wh_lo, kH, 3 * kH, 3 * kH, 128)) return MAGPO_ERR_ARG;
-  static bool attr = false;
-  if (!attr) {
+  if (once_per_device(ONCE_GRU_BWD))
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
-    attr = true;
-  }
   const int rpt = gru_rows_per_tile(Rs);
   GruBwdArgs a{T, N, A, Rs, rpt, dY, rzn, ghn, HU, done, dgi, dgh};
   ProfScope ps(PROF_GRU, s, 6144.0 * (double)Rs * T);

@@ -517,11 +517,9 @@ int retention_num_chunks(int T, int A) { return (T + retention_chunk_len(A) - 1)
 int retention_chunk_fwd(cudaStream_t s, int T, int N, int A, float kappa, bool causal, const float* q, const float* k,
                         const float* v, int ld, const float* H0, const uint8_t* done, float* ret, float* Hck, float* Hout) {
   const int Lc = retention_chunk_len(A);
-  static bool attr = false;
-  if (!attr) {
+  if (once_per_device(ONCE_RET_FWD)) {
     MAGPO_TRY(set_smem(retention_chunk_fwd_kernel<true>, kFwdSmem));
     MAGPO_TRY(set_smem(retention_chunk_fwd_kernel<false>, kFwdSmem));
-    attr = true;
   }
   ProfScope ps(PROF_RET_FWD, s, 4.0 * 256.0 * (double)T * N * A);
   if (causal)
@@ -536,11 +534,9 @@ int retention_chunk_bwd(cudaStream_t s, int T, int N, int A, float kappa, bool c
                         const float* v, int ld, const uint8_t* done, const float* Hck, const float* dret, float* dq,
                         float* dk, float* dv, int ldd) {
   const int Lc = retention_chunk_len(A);
-  static bool attr = false;
-  if (!attr) {
+  if (once_per_device(ONCE_RET_BWD)) {
     MAGPO_TRY(set_smem(retention_chunk_bwd_kernel<true>, kBwdSmem));
     MAGPO_TRY(set_smem(retention_chunk_bwd_kernel<false>, kBwdSmem));
-    attr = true;
   }
   ProfScope ps(PROF_RET_BWD, s, 7.0 * 256.0 * (double)T * N * A);
   if (causal)

@@ -116,21 +116,6 @@ __global__ void copy_zero_done_kernel(int64_t B, const float* __restrict__ src, 
 
 inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n, 256); }
 
-// The learner's GRU push of a step (rec_magpo.py:146-159) depends only on the step's observation, not on the guider's actions: it
-// trails along on a forked stream and fills the SMs the fused guider kernel and the one-warp-per-env step kernel leave idle.
-struct RolloutSide {
-  cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  int init() {
-    if (s) return MAGPO_OK;
-    MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-    return MAGPO_OK;
-  }
-};
-RolloutSide g_rside;
-
 struct RolloutWs {
   SableActs sa;
   ActorActs aa;
@@ -212,11 +197,12 @@ size_t magpo_rollout_workspace_bytes(const MagpoNetCfg* net, int32_t B, int32_t 
   return ar.off;
 }
 
-int magpo_sable_get_actions(magpo_stream_t s_, const MagpoNetCfg* net, int32_t B, int32_t gumbel_rows,
+int magpo_sable_get_actions(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net, int32_t B, int32_t gumbel_rows,
                             const float* guider, const float* agents_view, const uint8_t* action_mask,
                             const int32_t* step_count, const uint8_t* prev_done, const uint32_t* sample_keys,
                             MagpoSableHState hs, int32_t* action, float* log_prob, float* value, float* logits,
                             void* workspace, size_t workspace_bytes) {
+  MAGPO_CTX(ctx_);
   MAGPO_TRY(check_net(net));
   if (B <= 0 || !guider || !agents_view || !step_count || !value || !workspace) return MAGPO_ERR_ARG;
   if (action && (!action_mask || !sample_keys || !log_prob || gumbel_rows < 1)) return MAGPO_ERR_ARG;
@@ -233,9 +219,10 @@ int magpo_sable_get_actions(magpo_stream_t s_, const MagpoNetCfg* net, int32_t B
                      sample_keys, hs, false, action, log_prob, value, logits, w);
 }
 
-int magpo_actor_step(magpo_stream_t s_, const MagpoNetCfg* net, int32_t B, const float* actor,
+int magpo_actor_step(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net, int32_t B, const float* actor,
                      const float* agents_view, const uint8_t* done, float* policy_h, void* workspace,
                      size_t workspace_bytes) {
+  MAGPO_CTX(ctx_);
   MAGPO_TRY(check_net(net));
   if (B <= 0 || !actor || !agents_view || !policy_h || !workspace) return MAGPO_ERR_ARG;
   Arena ar(workspace, workspace_bytes);
@@ -247,10 +234,11 @@ int magpo_actor_step(magpo_stream_t s_, const MagpoNetCfg* net, int32_t B, const
                        policy_h, w.aa, nullptr, policy_h);
 }
 
-int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* sys, int env_kind,
+int magpo_rollout(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* sys, int env_kind,
                   const void* env_cfg, void* env_state, MagpoTimeStep ts, const float* guider, const float* actor,
                   uint32_t* key, MagpoSableHState hs, float* policy_h, MagpoTrajectory traj, int32_t carry_over,
                   void* workspace, size_t workspace_bytes) {
+  MAGPO_CTX(ctx_);
   MAGPO_TRY(check_net(net));
   if (!sys || !env_cfg || !env_state || !guider || !actor || !key || !policy_h || !workspace) return MAGPO_ERR_ARG;
   if (env_kind != MAGPO_ENV_COORDSUM && env_kind != MAGPO_ENV_LBF && env_kind != MAGPO_ENV_RWARE) return MAGPO_ERR_UNSUPPORTED;
@@ -301,10 +289,10 @@ int magpo_rollout(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* 
 
   const bool overlap = nets_overlap_enabled() && !sys->sable_only;
   cudaStream_t s2 = s;
-  if (overlap) {
-    MAGPO_TRY(g_rside.init());
-    s2 = g_rside.s;
-  }
+  // The learner's GRU push of a step (rec_magpo.py:146-159) depends only on the step's observation, not on the guider's actions: it
+  // trails along on the context's forked stream and fills the SMs the fused guider kernel and the env step kernel leave idle.
+  ForkJoin& g_rside = ctx().rside;
+  if (overlap) s2 = g_rside.s;
   for (int t = 0; t < T; ++t) {
     const float* obs = traj.agents_view + (size_t)t * BA * d;
     const uint8_t* mask = traj.action_mask + (size_t)t * BA * a;

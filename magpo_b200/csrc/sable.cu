@@ -146,23 +146,8 @@ int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
                                kappa, pe, w, logits, Hs_self, Hs_cross, Hself_out, Hcross_out);
 }
 
-namespace {
-// The decoder's encoder-independent prefix runs beside the encoder on its own stream: both are chains of kernels that sit at
-// 0.3-0.7 of the HBM roofline each, so together they use the memory system better than one after the other.
-struct DecStream {
-  cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  int init() {
-    if (s) return MAGPO_OK;
-    MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-    return MAGPO_OK;
-  }
-};
-DecStream g_dec;
-}  // namespace
-
+// The decoder's encoder-independent prefix runs beside the encoder on the context's `dec` stream: both are chains of kernels that sit
+// at 0.3-0.7 of the HBM roofline each, so together they use the memory system better than one after the other.
 int sable_train_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, const SableBatch& b, const SableActs& w,
                         float* value, float* logits, bool save_states) {
   static int split = -1;
@@ -173,8 +158,8 @@ int sable_train_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, con
   const bool overlap = split && nets_overlap_enabled();
   float* hs_self = save_states ? w.Hs_self : nullptr;
   float* hs_cross = save_states ? w.Hs_cross : nullptr;
+  ForkJoin& g_dec = ctx().dec;
   if (overlap) {
-    MAGPO_TRY(g_dec.init());
     MAGPO_CUDA_OK(cudaEventRecord(g_dec.fork, s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(g_dec.s, g_dec.fork, 0));
     MAGPO_TRY(decoder_forward_phase(1, g_dec.s, p, pt, b.T, b.N, b.A, b.A, b.a, b.max_step, b.action, w.x, w.xpe, b.step_count,

@@ -593,13 +593,11 @@ int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
   const int warps = forced_warps ? forced_warps : (int)std::min<int64_t>(SS_WARPS, std::max<int64_t>(7, ceil_div(pairs, kNumSMs)));
   const unsigned grid = (unsigned)ceil_div(pairs, warps);
   const unsigned threads = (unsigned)warps * 32;
-  static bool attr = false;
-  if (!attr) {
+  if (once_per_device(ONCE_SABLE_STEP_1 + A - 1)) {
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
     MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
-    attr = true;
   }
   if (s.d <= 4) sable_step_kernel<A, 4><<<grid, threads, SS_SMEM, st>>>(p, s);
   else if (s.d <= 8) sable_step_kernel<A, 8><<<grid, threads, SS_SMEM, st>>>(p, s);

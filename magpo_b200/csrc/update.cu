@@ -261,29 +261,8 @@ size_t magpo_update_workspace_bytes(const MagpoNetCfg* net, int32_t T, int32_t N
 
 namespace {
 // The guider and the learner are independent until the losses (which need both logits) and again after them. The learner's
-// persistent GRU scans are latency chains on <= 96 of the 148 SMs, so its forward / backward run on a forked stream and the
-// guider's streaming kernels fill the idle SMs and HBM bandwidth meanwhile.
-struct SideStream {
-  cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  int init() {
-    if (s) return MAGPO_OK;
-    const char* e = getenv("MAGPO_PRIO_MODE");  // experiments: 1 = the side stream gets the highest priority, 2 = and carries the guider
-    mode = e ? atoi(e) : 0;
-    if (mode) {
-      int least = 0, greatest = 0;
-      MAGPO_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-      MAGPO_CUDA_OK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest));
-    } else {
-      MAGPO_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    }
-    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    MAGPO_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-    return MAGPO_OK;
-  }
-  int mode = 0;
-};
-SideStream g_side;
+// persistent GRU scans are latency chains on <= 96 of the 148 SMs, so its forward / backward run on the context's `side` stream and
+// the guider's streaming kernels fill the idle SMs and HBM bandwidth meanwhile.
 bool g_overlap_nets = true;
 }  // namespace
 
@@ -298,9 +277,10 @@ int magpo_debug_set_overlap(int on) {
   return MAGPO_OK;
 }
 
-int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* sys, const float* guider,
+int magpo_minibatch_grads(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net, const MagpoSysCfg* sys, const float* guider,
                           const float* actor, MagpoMinibatch mb, const int32_t* env_slot, const float* adv_stats_,
-                          float inv_tokens, float* grads, void* workspace, size_t workspace_bytes) {
+                          float inv_tokens, float* grads, int32_t reduce_grads, void* workspace, size_t workspace_bytes) {
+  MAGPO_CTX(ctx_);
   MAGPO_TRY(check_net(net));
   MAGPO_TRY(check_mb(mb));
   if (!sys || !guider || !actor || !env_slot || !adv_stats_ || !grads || !workspace || !mb.value || !mb.log_prob ||
@@ -330,9 +310,9 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
   bool skip_learner = false;
   const bool overlap = g_overlap_nets && !skip && !sys->sable_only;
   cudaStream_t s2 = s, sg = s;  // learner stream, guider stream
+  ForkJoin& g_side = ctx().side;
   if (overlap) {
-    MAGPO_TRY(g_side.init());
-    if (g_side.mode == 2) sg = g_side.s; else s2 = g_side.s;
+    s2 = g_side.s;
     MAGPO_CUDA_OK(cudaEventRecord(g_side.fork, s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(g_side.s, g_side.fork, 0));
   }
@@ -355,7 +335,13 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
     MAGPO_CUDA_OK(cudaStreamWaitEvent(g_side.s, g_side.fork, 0));
   }
   if (!(skip & 10) && !skip_learner) MAGPO_TRY(actor_backward(s2, ap, w.at, T, N, A, d, a, mb.agents_view, mb.done, w.aa, w.dll, ag));
+  // pmean over "device" (rec_magpo.py:399-409), issued where the gradients are produced: the learner's half (+ the 8 loss sums, which
+  // lie behind it) as soon as the learner's backward is done — on its own stream, under the guider's remaining backward — and the
+  // guider's half at the end. Every rank issues the two all-reduces in this order.
+  MagpoComm* comm = reduce_grads ? ctx().comm : nullptr;
+  if (comm) MAGPO_TRY(comm_allreduce(comm, s2, grads + gp.total, ap.total + 8, 0));
   if (!(skip & 5)) MAGPO_TRY(sable_train_backward(sg, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
+  if (comm) MAGPO_TRY(comm_allreduce(comm, sg, grads, gp.total, 0));
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_side.join, g_side.s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_side.join, 0));
@@ -363,8 +349,9 @@ int magpo_minibatch_grads(magpo_stream_t s_, const MagpoNetCfg* net, const Magpo
   return MAGPO_OK;
 }
 
-int magpo_guider_forward(magpo_stream_t s_, const MagpoNetCfg* net, const float* guider, MagpoMinibatch mb,
+int magpo_guider_forward(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net, const float* guider, MagpoMinibatch mb,
                          float* value, float* logits, void* workspace, size_t workspace_bytes) {
+  MAGPO_CTX(ctx_);
   MAGPO_TRY(check_net(net));
   MAGPO_TRY(check_mb(mb));
   if (!guider || !value || !logits || !workspace) return MAGPO_ERR_ARG;
@@ -383,8 +370,9 @@ int magpo_guider_forward(magpo_stream_t s_, const MagpoNetCfg* net, const float*
   return MAGPO_OK;
 }
 
-int magpo_actor_forward(magpo_stream_t s_, const MagpoNetCfg* net, const float* actor, MagpoMinibatch mb,
+int magpo_actor_forward(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net, const float* actor, MagpoMinibatch mb,
                         float* logits, void* workspace, size_t workspace_bytes) {
+  MAGPO_CTX(ctx_);
   MAGPO_TRY(check_net(net));
   if (!actor || !logits || !workspace || !mb.agents_view || !mb.done || !mb.policy_h0 || !mb.action_mask)
     return MAGPO_ERR_ARG;

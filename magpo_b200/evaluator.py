@@ -77,9 +77,9 @@ def get_eval_fn(env, actor_network, config, absolute_metric: bool, n_devices: in
             for _ in range(env.time_limit + 1):
                 step_key, act_key = minit.split(step_key, 2, dev)
                 mb["done"].copy_((ts["step_type"] == 2).to(torch.uint8).view(1, n))  # timestep.last()
-                L.call("magpo_actor_forward", s, C.byref(lrn.c_net), L.ptr(actor_flat), mbs, L.ptr(logits), L.ptr(ws),
+                L.call("magpo_actor_forward", lrn.ctx, s, C.byref(lrn.c_net), L.ptr(actor_flat), mbs, L.ptr(logits), L.ptr(ws),
                        C.c_size_t(nbytes))
-                L.call("magpo_actor_step", s, C.byref(lrn.c_net), n, L.ptr(actor_flat), L.ptr(mb["agents_view"]),
+                L.call("magpo_actor_step", lrn.ctx, s, C.byref(lrn.c_net), n, L.ptr(actor_flat), L.ptr(mb["agents_view"]),
                        L.ptr(mb["done"]), L.ptr(hidden), L.ptr(ws), C.c_size_t(nbytes))
                 if greedy:
                     action.copy_(logits[0].argmax(-1))
@@ -144,7 +144,7 @@ def get_sable_eval_fn(env, lrn, config, absolute_metric: bool, n_devices: int = 
                 for i in range(A):
                     k, sample_keys[i] = minit.split(k, 2, dev)
                 sk = torch.as_tensor(sample_keys.view(np.int32)).to(dev)
-                L.call("magpo_sable_get_actions", s, C.byref(lrn.c_net), n, n, L.ptr(guider_flat), L.ptr(ts["agents_view"]),
+                L.call("magpo_sable_get_actions", lrn.ctx, s, C.byref(lrn.c_net), n, n, L.ptr(guider_flat), L.ptr(ts["agents_view"]),
                        L.ptr(ts["action_mask"]), L.ptr(ts["step_count"]), None, L.ptr(sk), L.struct_of(L.SableHState, **hs),
                        L.ptr(action), L.ptr(log_prob), L.ptr(value), None, L.ptr(ws), C.c_size_t(nbytes))
                 L.call(env.step_fn, s, C.byref(env.cfg), n, L.ptr(action), env.state_struct(state), L.struct_of(L.TimeStep, **ts))

@@ -224,6 +224,7 @@ class MagpoLearner:
     def __init__(self, env: CoordSumVec, sys: SystemConfig, device="cuda:0", allreduce=None, world_size: int = 1,
                  graph_rollout: bool = True, net: "NetworkConfig | None" = None):
         self.env, self.sys, self.dev = env, sys, torch.device(device)
+        self.ctx = L.create_context(self.dev)  # this learner's MagpoContext: side streams + tensor-core weight images
         if sys.decay_learning_rates and sys.num_updates < 1:
             raise ValueError("decay_learning_rates needs system.num_updates >= 1 (utils/training.py:38-44)")
         # The T-step rollout is ~90 short launches per env step: after the first (eager) call it is replayed from one
@@ -232,7 +233,9 @@ class MagpoLearner:
         self.net = net or NetworkConfig(env.num_agents, env.obs_dim, env.action_dim, env.time_limit)
         if (self.net.n_agents, self.net.obs_dim, self.net.action_dim) != (env.num_agents, env.obs_dim, env.action_dim):
             raise ValueError("network configuration does not match the environment's (agents, obs_dim, action_dim)")
-        self.allreduce, self.world_size = allreduce, world_size
+        # data-parallel exchange: `comm.NcclComm.attach(self)` (the library reduces inside magpo_minibatch_grads), or a host callable
+        # `allreduce(flat)` summing the flat gradient buffer in place (CPU tests with gloo)
+        self.allreduce, self.world_size, self.comm = allreduce, world_size, None
         self.c_net, self.c_sys = self.net.c_struct(), sys.c_struct()
         dev, f32, i32, u8 = self.dev, torch.float32, torch.int32, torch.uint8
         A, d, a = self.net.n_agents, self.net.obs_dim, self.net.action_dim
@@ -283,6 +286,13 @@ class MagpoLearner:
         self.workspace = torch.empty(self.ws_bytes, dtype=u8, device=dev)
         self.first_rollout = True
         self.loss_log: list[torch.Tensor] = []
+
+    def __del__(self):
+        try:
+            torch.cuda.synchronize(self.dev)
+            L.destroy_context(self.ctx)
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ structs
     def _ts_struct(self):
@@ -336,7 +346,7 @@ class MagpoLearner:
 
     # ------------------------------------------------------------------ the step
     def _rollout_call(self, carry_over: int) -> None:
-        L.call("magpo_rollout", L.stream_ptr(), C.byref(self.c_net), C.byref(self.c_sys), self.env.kind, C.byref(self.env.cfg),
+        L.call("magpo_rollout", self.ctx, L.stream_ptr(), C.byref(self.c_net), C.byref(self.c_sys), self.env.kind, C.byref(self.env.cfg),
                C.byref(self.env.state_struct(self.env_state)), self._ts_struct(), L.ptr(self.guider), L.ptr(self.actor),
                L.ptr(self.key), L.struct_of(L.SableHState, **self.hs), L.ptr(self.policy_h), self._traj_struct(),
                carry_over, L.ptr(self.workspace), C.c_size_t(self.ws_bytes))
@@ -383,13 +393,14 @@ class MagpoLearner:
             L.call("magpo_pack_minibatch", s, C.byref(self.c_net), C.byref(self.c_sys), self._traj_struct(),
                    L.ptr(self.adv), L.ptr(self.targets), L.ptr(env_index[c0:c0 + n]), L.ptr(hs_index[c0:c0 + n]),
                    L.ptr(self.agent_perm), n, mbs)
-            L.call("magpo_minibatch_grads", s, C.byref(self.c_net), C.byref(self.c_sys), L.ptr(self.guider),
+            last = c0 + n >= Nmb  # the attached communicator reduces once the whole minibatch has been accumulated
+            L.call("magpo_minibatch_grads", self.ctx, s, C.byref(self.c_net), C.byref(self.c_sys), L.ptr(self.guider),
                    L.ptr(self.actor), mbs, L.ptr(env_slot[c0:c0 + n]), L.ptr(self.stats), C.c_float(inv_tokens),
-                   L.ptr(self.grads), L.ptr(self.workspace), C.c_size_t(self.ws_bytes))
+                   L.ptr(self.grads), 1 if (last and self.comm is not None) else 0, L.ptr(self.workspace), C.c_size_t(self.ws_bytes))
 
     def apply_grads(self) -> None:
         sysc, s = self.sys, L.stream_ptr()
-        if self.allreduce is not None:
+        if self.allreduce is not None and self.comm is None:
             self.allreduce(self.grads)  # sum over ranks; the mean is taken by grad_scale
         scale = 1.0 / self.world_size
         g, a = self.grads[:self.n_g], self.grads[self.n_g:self.n_g + self.n_a]

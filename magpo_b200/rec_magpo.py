@@ -225,12 +225,12 @@ class ActorNetwork:
                      int(lib.magpo_rollout_workspace_bytes(C.byref(lrn.c_net), N, 0)))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         logits = z(T, N, A, a)
-        L.call("magpo_actor_forward", L.stream_ptr(), C.byref(lrn.c_net), L.ptr(actor_flat), s, L.ptr(logits), L.ptr(ws),
+        L.call("magpo_actor_forward", lrn.ctx, L.stream_ptr(), C.byref(lrn.c_net), L.ptr(actor_flat), s, L.ptr(logits), L.ptr(ws),
                C.c_size_t(nbytes))
         carry = None
         if T == 1:
             carry = mb["policy_h0"].clone()
-            L.call("magpo_actor_step", L.stream_ptr(), C.byref(lrn.c_net), N, L.ptr(actor_flat), L.ptr(mb["agents_view"]),
+            L.call("magpo_actor_step", lrn.ctx, L.stream_ptr(), C.byref(lrn.c_net), N, L.ptr(actor_flat), L.ptr(mb["agents_view"]),
                    L.ptr(mb["done"]), L.ptr(carry), L.ptr(ws), C.c_size_t(nbytes))
         torch.cuda.current_stream().synchronize()  # the temporaries above must outlive the launches
         return carry, logits
@@ -403,7 +403,7 @@ def mean_over_devices(flat: torch.Tensor, world_size: int) -> torch.Tensor:
 
 
 def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, device=None, allreduce=None, rank: int = 0,
-                  world_size: int = 1) -> Tuple[LearnerFn, ActorNetwork, GPOLearnerState]:
+                  world_size: int = 1, comm=None) -> Tuple[LearnerFn, ActorNetwork, GPOLearnerState]:
     """rec_magpo.py:533-685. keys = (key, actor_net_key, net_key) as raw uint32[2] arrays (jax.random.PRNGKey layout)."""
     if not torch.cuda.is_available():
         raise RuntimeError("magpo_b200 runs on CUDA devices only (no CPU fallback)")
@@ -413,6 +413,8 @@ def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, 
     config.system.num_actions = env.action_dim
     lrn = MagpoLearner(env, _system_config(config), device=device, allreduce=allreduce, world_size=world_size,
                        net=_network_config(config, env))
+    if comm is not None:  # comm.NcclComm: magpo_minibatch_grads reduces the gradients itself (the pmean over "device", :399-409)
+        comm.attach(lrn)
     # parameters: flax's orthogonal/normal initialisers cannot be reproduced bit-for-bit without jax; same shapes, same
     # gains, NumPy generator seeded from the net keys
     lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, int(np.asarray(net_key)[-1])),
@@ -428,16 +430,20 @@ def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, 
 def run_experiment(config: Config, device=None, log=print) -> float:
     """rec_magpo.py:688-831 (console / JSON logger and an npz checkpointer instead of the TensorBoard / Neptune / orbax back-ends): `num_evaluation` calls of `learn`, each
     `num_updates_per_eval` updates, reporting steps per second and the mean return of the episodes that ended."""
-    import torch.distributed as dist
+    import os
 
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
+    # one process per GPU (the reference's device axis): launched under torchrun, the ranks exchange gradients through the library's
+    # own NCCL communicator (magpo_b200/comm.py)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    comm = None
+    if world > 1:
+        from .comm import NcclComm
+        comm = NcclComm.from_env(device)
     config = check_total_timesteps(config, world)
     config.system.num_updates_per_eval = config.system.num_updates // config.arch.num_evaluation
     env = make_env(config)
     key, key_e, actor_net_key, net_key = minit.split(minit.prng_key(int(config.system.seed)), 4, device or "cuda:0")
-    allreduce = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
-    learn, actor_network, state = learner_setup(env, (key, actor_net_key, net_key), config, device=device, allreduce=allreduce,
+    learn, actor_network, state = learner_setup(env, (key, actor_net_key, net_key), config, device=device, comm=comm,
                                                 rank=rank, world_size=world)
     lrn = actor_network.lrn
     # evaluator of the learner policy (rec_magpo.py:706-710): episodes sharded over the devices, no collective (evaluator.py:163)
@@ -449,8 +455,8 @@ def run_experiment(config: Config, device=None, log=print) -> float:
 
     def world_mean(x: torch.Tensor) -> float:
         m = x.float().mean().reshape(1).to(lrn.dev)
-        if world > 1:
-            dist.all_reduce(m, op=dist.ReduceOp.SUM)
+        if comm is not None:
+            comm.allreduce_sum(m)
             m /= world
         return float(m)
 

@@ -70,13 +70,15 @@ def get_learner_fn(lrn: MagpoLearner, config: Config):
     return learn
 
 
-def learner_setup(env, keys: Tuple[Any, Any], config: Config, device=None, allreduce=None, rank: int = 0, world_size: int = 1):
+def learner_setup(env, keys: Tuple[Any, Any], config: Config, device=None, allreduce=None, rank: int = 0, world_size: int = 1, comm=None):
     """rec_sable.py:351-479."""
     key, net_key = keys
     sysc = rm._system_config(_with_magpo_defaults(config))
     sysc.sable_only = True
     lrn = MagpoLearner(env, sysc, device=device or "cuda:0", allreduce=allreduce, world_size=world_size,
                        net=rm._network_config(config, env))
+    if comm is not None:
+        comm.attach(lrn)
     lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, int(np.asarray(net_key)[-1])),
                    minit.init_actor(env.obs_dim, env.action_dim, 0))  # the learner buffers exist but are never touched
     U, E = sysc.update_batch_size, sysc.num_envs
@@ -96,20 +98,22 @@ def _with_magpo_defaults(config: Config) -> Config:
 def run_experiment(config: Config, device=None, log=print) -> float:
     """rec_sable.py:481-625: `num_evaluation` x (`learn`, evaluation of the Sable policy with `make_rec_sable_act_fn`), logging
     MISC / ACT / TRAIN / EVAL events, optional checkpoints, the absolute metric with the best parameters at the end."""
-    import torch.distributed as dist
+    import os
 
     from . import evaluator as mev
     from .checkpointing import Checkpointer, unreplicate_n_dims
     from .logger import LogEvent, MavaLogger
 
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))  # one process per GPU (torchrun)
+    comm = None
+    if world > 1:
+        from .comm import NcclComm
+        comm = NcclComm.from_env(device)
     config = check_total_timesteps(config, world)
     config.system.num_updates_per_eval = config.system.num_updates // config.arch.num_evaluation
     env = rm.make_env(config)
     key, key_e, net_key = minit.split(minit.prng_key(int(config.system.seed)), 3, device or "cuda:0")
-    allreduce = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
-    learn, lrn, state = learner_setup(env, (key, net_key), config, device=device, allreduce=allreduce, rank=rank, world_size=world)
+    learn, lrn, state = learner_setup(env, (key, net_key), config, device=device, comm=comm, rank=rank, world_size=world)
     evaluator = mev.get_sable_eval_fn(env, lrn, config, absolute_metric=False, n_devices=world)
     config.logger.system_name = "rec_sable"
     logger = MavaLogger(config, console_sink=log) if rank == 0 else None
@@ -123,8 +127,8 @@ def run_experiment(config: Config, device=None, log=print) -> float:
 
     def world_mean(x: torch.Tensor) -> float:
         m = x.float().mean().reshape(1).to(lrn.dev)
-        if world > 1:
-            dist.all_reduce(m, op=dist.ReduceOp.SUM)
+        if comm is not None:
+            comm.allreduce_sum(m)
             m /= world
         return float(m)
 

@@ -93,7 +93,7 @@ def test_guider_and_actor_forward(dev, A, d, a, T, N):
     value = torch.zeros(T, N, A, device=dev)
     logits = torch.zeros(T, N, A, a, device=dev)
     cnet = net.c_struct()
-    L.call("magpo_guider_forward", L.stream_ptr(), C.byref(cnet), L.ptr(gflat), mbs, L.ptr(value), L.ptr(logits), L.ptr(ws),
+    L.call("magpo_guider_forward", L.context(), L.stream_ptr(), C.byref(cnet), L.ptr(gflat), mbs, L.ptr(value), L.ptr(logits), L.ptr(ws),
            C.c_size_t(nbytes))
     p = onets.to_torch(gp)
     onets.RECORD = rec = {}
@@ -120,7 +120,7 @@ def test_guider_and_actor_forward(dev, A, d, a, T, N):
     assert not bad and ev < 1e-4 and el < 1e-4, (bad, ev, el)
     # learner
     ll = torch.zeros(T, N, A, a, device=dev)
-    L.call("magpo_actor_forward", L.stream_ptr(), C.byref(cnet), L.ptr(aflat), mbs, L.ptr(ll), L.ptr(ws), C.c_size_t(nbytes))
+    L.call("magpo_actor_forward", L.context(), L.stream_ptr(), C.byref(cnet), L.ptr(aflat), mbs, L.ptr(ll), L.ptr(ws), C.c_size_t(nbytes))
     _, a_ref = onets.actor_apply(onets.to_torch(ap), cfg, torch.tensor(mb["policy_h0"]), olr.forward_reshape(torch.tensor(mb["obs"]), A),
                                  olr.forward_reshape(torch.tensor(mb["done"]), A), olr.forward_reshape(torch.tensor(mb["action_mask"]), A))
     got = ll.cpu().numpy()  # already [T, N, A, a]
@@ -162,8 +162,8 @@ def test_minibatch_grads(dev, A, d, a, T, Ns, U, tol):
     from magpo_b200.learner import SystemConfig
     csys = SystemConfig(num_envs=Ns, update_batch_size=U, rollout_length=T, num_minibatches=1).c_struct()
     cnet = net.c_struct()
-    L.call("magpo_minibatch_grads", L.stream_ptr(), C.byref(cnet), C.byref(csys), L.ptr(gflat), L.ptr(aflat), mbs, L.ptr(env_slot),
-           L.ptr(stats), C.c_float(1.0 / (N * T * A)), L.ptr(grads), L.ptr(ws), C.c_size_t(nbytes))
+    L.call("magpo_minibatch_grads", L.context(), L.stream_ptr(), C.byref(cnet), C.byref(csys), L.ptr(gflat), L.ptr(aflat), mbs, L.ptr(env_slot),
+           L.ptr(stats), C.c_float(1.0 / (N * T * A)), L.ptr(grads), 0, L.ptr(ws), C.c_size_t(nbytes))
     sync()
     gv = param_views(grads[:ng], gt)
     av = param_views(grads[ng:ng + na], at)

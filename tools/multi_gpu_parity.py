@@ -17,27 +17,31 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from magpo_b200 import init as minit  # noqa: E402
+from magpo_b200.comm import NcclComm  # noqa: E402
 from magpo_b200.learner import LbfVec, MagpoLearner, SystemConfig  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+dist.init_process_group("nccl", device_id=dev)  # harness only (gathering the ranks' results); the gradient exchange is NcclComm's
+comm = NcclComm.from_env(dev)
 E, T, UPDATES = 64, 32, 3
 env = LbfVec()
 
 
-def make(U, n_dev, r, allreduce):
+def make(U, n_dev, r, attach):
     sysc = SystemConfig(num_envs=E, update_batch_size=U, rollout_length=T)
-    lrn = MagpoLearner(env, sysc, device=dev, allreduce=allreduce, world_size=n_dev)
+    lrn = MagpoLearner(env, sysc, device=dev, world_size=n_dev)
+    if attach:
+        comm.attach(lrn)  # magpo_minibatch_grads all-reduces through the library's communicator
     lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, 0), minit.init_actor(env.obs_dim, env.action_dim, 1))
     env_keys, step_key, _ = minit.setup_keys(42, n_dev, U, E, dev)
     lrn.reset(env_keys[r], step_key)
     return lrn
 
 
-dp = make(1, world, rank, lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
-single = make(world, 1, 0, None) if rank == 0 else None
+dp = make(1, world, rank, True)
+single = make(world, 1, 0, False) if rank == 0 else None
 rows = []
 for upd in range(UPDATES):
     dp.update_step()
@@ -68,4 +72,5 @@ if rank == 0:
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "multi_gpu_parity.json"), "w"), indent=1)
     print(json.dumps(out))
 dist.barrier()
+comm.close()
 dist.destroy_process_group()
