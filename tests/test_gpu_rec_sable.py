@@ -10,6 +10,7 @@ from magpo_b200.config import compose
 from magpo_b200.learner import CoordSumVec, LbfVec, MagpoLearner, SystemConfig
 from oracle import coordsum as ocs
 from oracle import lbf as olbf
+from magpo_b200 import rec_magpo as rm
 from oracle import learner as olr
 from oracle import nets as onets
 from oracle import prng as oprng

@@ -54,9 +54,12 @@ for tag, tc, gru, scan in (("default", 1, 0, 0), ("tensor cores off", 0, 0, 0), 
     report(tag, param_views(g[:lrn.n_g], lrn.g_table), param_views(g[lrn.n_g:lrn.n_g + lrn.n_a], lrn.a_table))
 lib.magpo_set_tensor_cores(1); lib.magpo_debug_force_gru_stepwise(0); lib.magpo_debug_force_retention_scan(0)
 
-# every optimiser step of update 0: gradient of step k (CUDA vs the oracles), then the parameters after the update
-print("=== per optimiser step of update 0: worst |g_cuda - g_o32| / max|g| over the (guider, learner) tensors, and the tensor")
-_, _, _, _, lrn = baseline_case(env, dev)
+# every optimiser step of update 0: gradient of step k (CUDA vs the fp32 oracle's), then the parameters after the step against the
+# oracle's optimiser replayed on the oracle's recorded gradients from the same initial parameters
+print("=== per optimiser step of update 0")
+spec, ncfg, osys, state0, lrn = baseline_case(env, dev)
+o_params = {k: v.copy() for k, v in state0["actor_params"].items()}
+o_opt = olr.init_opt(o_params)
 lrn.rollout(); lrn.gae()
 k = 0
 for p_ in range(osys.ppo_epochs):
@@ -65,11 +68,20 @@ for p_ in range(osys.ppo_epochs):
         lrn.minibatch_grads(m_)
         torch.cuda.synchronize()
         g = lrn.grads.clone()
-        gv, av = param_views(g[:lrn.n_g], lrn.g_table), param_views(g[lrn.n_g:lrn.n_g + lrn.n_a], lrn.a_table)
-        out = []
-        for mine, ref in ((gv, rec32["grads"][k][0]), (av, rec32["grads"][k][1])):
-            worst = max(((float(np.abs(mine[n].cpu().numpy() - r).max()) / max(float(np.abs(r).max()), 1e-30), n) for n, r in ref.items()))
-            out.append("%.2e %s" % worst)
-        print(f"    step {k} (epoch {p_}, minibatch {m_}): guider {out[0]} | learner {out[1]}")
+        av = param_views(g[lrn.n_g:lrn.n_g + lrn.n_a], lrn.a_table)
+        ref = rec32["grads"][k][1]
+        rows = sorted(((float(np.abs(av[n].cpu().numpy() - r).max()) / max(float(np.abs(r).max()), 1e-30), float(np.abs(r).max()), n)
+                       for n, r in ref.items()), reverse=True)
         lrn.apply_grads()
+        torch.cuda.synchronize()
+        olr.clip_adam_step(o_params, ref, o_opt, osys.actor_lr, osys.max_grad_norm)
+        _, ap = lrn.get_params()
+        prow = sorted(((float(np.abs(ap[n].cpu().numpy() - r).max()) / osys.actor_lr, n) for n, r in o_params.items()), reverse=True)
+        print(f"  step {k}: grad dev (rel to max|g|, max|g|, tensor): " + "; ".join("%.1e %.1e %s" % r for r in rows[:3]))
+        print(f"          param dev in units of lr: " + "; ".join("%.3f %s" % r for r in prow[:3]))
+        n = prow[0][1]
+        d = np.abs(ap[n].cpu().numpy() - o_params[n])
+        idx = np.unravel_index(int(d.argmax()), d.shape)
+        print(f"          worst element {n}{list(idx)}: p_cuda {float(ap[n].cpu().numpy()[idx]):.9g} p_oracle {float(o_params[n][idx]):.9g} "
+              f"g_cuda {float(av[n].cpu().numpy()[idx]):.6g} g_oracle {float(ref[n][idx]):.6g} count {int(lrn.a_count.item())}")
         k += 1
