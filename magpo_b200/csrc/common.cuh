@@ -90,8 +90,8 @@ struct CtxScope {
 int comm_allreduce(MagpoComm* c, cudaStream_t s, float* buf, int64_t n, int op);
 // true exactly once per (device, id): guards cudaFuncSetAttribute, which is per device
 bool once_per_device(int id);
-enum { ONCE_GEMM_TC = 0, ONCE_GEMM_TN, ONCE_GRU_FWD, ONCE_GRU_BWD, ONCE_RET_FWD, ONCE_RET_BWD, ONCE_SABLE_STEP_1, ONCE_SABLE_STEP_2,
-       ONCE_SABLE_STEP_3, ONCE_SABLE_STEP_4, ONCE_NUM };
+enum { ONCE_GEMM_TC = 0, ONCE_GEMM_TN, ONCE_GRU_FWD, ONCE_GRU_BWD, ONCE_RET_FWD, ONCE_RET_BWD, ONCE_SABLE_STEP_1 /* 8 ids: (A - 1) * 2 + (EPW - 1) */,
+       ONCE_SABLE_STEP_LAST = ONCE_SABLE_STEP_1 + 7, ONCE_NUM };
 
 constexpr int kNumSMs = 148;
 constexpr float kF32Min = -3.4028234663852886e+38f;  // jnp.finfo(float32).min

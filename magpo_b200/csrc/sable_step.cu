@@ -7,9 +7,11 @@
 // i-1's sampled action), so one warp runs the whole chain for EPW envs with nothing but warp shuffles between stages:
 //   * a 64-wide activation row lives in one float2 per lane (lane l = columns 2l, 2l+1), the same layout the row kernels use;
 //   * a dense layer y = x W is 64 broadcast-FMA steps: x_k by shuffle, the k-th weight row from shared memory (256 contiguous
-//     bytes per warp, conflict-free). The CTA streams the 5 + 7 A weight matrices of the step (0.4 MB, L2 resident) through two
-//     64 KiB buffers with cp.async, one layer ahead of the arithmetic, so no weight load is ever waited for; EPW envs (x A
-//     tokens in the encoder) share each weight read;
+//     bytes per warp, conflict-free). The CTA streams the weight matrices of the step (0.4 MB, L2 resident) through two
+//     32 KiB buffers with cp.async, one piece ahead of the arithmetic (the 64 x 256 projections go through as two 64 x 128 column
+//     halves), so no weight load is ever waited for; EPW envs (x A tokens in the encoder) share each weight read. With 32 KiB
+//     buffers TWO CTAs of 7 warps fit on an SM (80 KB of shared memory, 128 registers per thread each): they drift apart in phase, so
+//     one CTA's state stream (HBM) runs under the other's dense layers (FMA) instead of the whole SM alternating between the two;
 //   * the 64x64 retention states (3 x 16 KiB per env, the only large HBM stream of the rollout) are read row by row, 256
 //     coalesced bytes per row and warp, 8 rows in flight per env. The decoder states are READ once per agent but WRITTEN once
 //     per step: with H0 the stored state, lam the step's decay and (k_j, v_j) the tokens added so far,
@@ -27,11 +29,12 @@ namespace magpo {
 namespace {
 
 constexpr float kEps = 1e-6f;
-constexpr int EPW = 2;         // envs per warp
-constexpr int SS_WARPS = 14;   // warps per CTA (28 envs; one CTA per SM, the register file is the occupancy limit): 8192 envs = 1.98 waves
-constexpr int SS_WBUF = kD * 4 * kD;  // floats of the largest layer [64, 256]
+// envs per warp: 2 for large batches (every weight read from shared memory serves 2 A rows), 1 for small ones (twice the warps, half
+// the dependent work per warp: the RWARE shard of 1024 envs is latency-bound, not bandwidth-bound)
+constexpr int SS_WARPS = 8;    // max warps per CTA; two CTAs per SM
+constexpr int SS_WBUF = kD * 2 * kD;  // floats of the largest staged piece [64, 128]
 constexpr int SS_XROWS = 8;  // rows of the per-warp activation scratch (EPW x A <= 8)
-constexpr uint32_t SS_SMEM = (2 * SS_WBUF + SS_WARPS * SS_XROWS * kD) * sizeof(float);
+constexpr uint32_t ss_smem(int warps) { return (uint32_t)((2 * SS_WBUF + warps * SS_XROWS * kD) * sizeof(float)); }
 constexpr unsigned kFull = 0xffffffffu;
 
 struct StepArgs {
@@ -98,11 +101,15 @@ __device__ __forceinline__ void dense1(const float* __restrict__ W, const float2
   for (int r = 0; r < R; ++r) y[r] = t[r][0];
 }
 
-// Weight pipeline: every thread copies its 16-byte pieces of the next layer's matrix (global, contiguous) into the idle buffer.
-__device__ __forceinline__ void stage_issue(float* dst /*shared*/, const float* __restrict__ src, int nfloats) {
+// Weight pipeline: every thread copies its 16-byte pieces of the next piece — 64 rows x `cols` floats out of a row-major matrix with
+// leading dimension `ld` — into the idle buffer (compact: leading dimension `cols`).
+__device__ __forceinline__ void stage_issue(float* dst /*shared*/, const float* __restrict__ src, int cols, int ld) {
   const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
-  for (int i = threadIdx.x * 4; i < nfloats; i += blockDim.x * 4)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i * 4), "l"(src + i) : "memory");
+  const int per_row = cols >> 2;  // 16-byte pieces per row
+  for (int i = threadIdx.x; i < kD * per_row; i += blockDim.x) {
+    const int r = i / per_row, c = (i - r * per_row) << 2;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)(r * cols + c) * 4u), "l"(src + (size_t)r * ld + c) : "memory");
+  }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 // the layer issued last has landed for every thread, and every warp is done with the other buffer
@@ -142,7 +149,7 @@ __device__ __forceinline__ void load_rows(float2 (&h)[8], const float* __restric
 
 // Decoder retention of agent i (token-causal): out_e = lam (q_e H0_e) + sum_{j<=i} (q_e . k_ej) v_ej, H0 read-only; the last
 // agent's pass also writes lam H0 + sum_j k_j^T v_j. Both envs' rows are in flight together.
-template <int A>
+template <int A, int EPW>
 __device__ __forceinline__ void decoder_retention(int i, float* __restrict__ Hall, const int (&b)[EPW], const bool (&live)[EPW],
                                                   const float (&lam)[EPW], const float2 (&q)[EPW], const float2 (&k)[EPW][A],
                                                   const float2 (&v)[EPW][A], float2 (&out)[EPW], int lane) {
@@ -183,9 +190,9 @@ __device__ __forceinline__ void decoder_retention(int i, float* __restrict__ Hal
   }
 }
 
-template <int A, int KMAX>
-// 14 warps are allocated as 16 (register allocation granularity): 128 registers per thread is the ceiling
-__global__ void __launch_bounds__(512, 1)
+template <int A, int KMAX, int EPW>
+// two CTAs of <= 8 warps per SM: 128 registers per thread is the ceiling
+__global__ void __launch_bounds__(256, 2)
 sable_step_kernel(const GuiderP p, const StepArgs s) {
   extern __shared__ __align__(16) float wbuf[];  // two weight buffers of SS_WBUF floats
   float* const w_a = wbuf;
@@ -193,14 +200,14 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
   float* const xs = wbuf + 2 * SS_WBUF + (threadIdx.x >> 5) * SS_XROWS * kD;  // this warp's activation scratch
   const int lane = threadIdx.x & 31;
   const int64_t pair = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // warps past the batch run dead (no stores)
-  stage_issue(w_a, p.qkvg, kD * 4 * kD);
+  stage_issue(w_a, p.qkvg, 2 * kD, 4 * kD);  // [w_q | w_k]
   float* cur_w = w_a;  // buffer of the layer about to be computed
   float* nxt_w = w_b;  // buffer the following layer is prefetched into
   const bool full = !s.dry && s.action;
 // the current layer's weights are complete and the other buffer is free: start the next layer's copy, then compute
-#define LAYER(next_ptr, next_n)                               \
+#define LAYER(next_ptr, next_cols, next_ld)                    \
   stage_wait();                                               \
-  if ((next_ptr) != nullptr) stage_issue(nxt_w, (next_ptr), (next_n));
+  if ((next_ptr) != nullptr) stage_issue(nxt_w, (next_ptr), (next_cols), (next_ld));
 #define LAYER_DONE()                                          \
   { float* t_ = cur_w; cur_w = nxt_w; nxt_w = t_; }
   int b[EPW];
@@ -299,9 +306,19 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
   float2 ret[RE], gate[RE];
   {
     float2 qkvg[RE][4];
-    LAYER(p.wo, kD * kD)
-    dense<4, RE>(cur_w, 4 * kD, cur, qkvg, xs, lane);
-    LAYER_DONE()
+    {
+      float2 half[RE][2];
+      LAYER(p.qkvg + 2 * kD, 2 * kD, 4 * kD)  // next: [w_v | w_g]
+      dense<2, RE>(cur_w, 2 * kD, cur, half, xs, lane);
+      LAYER_DONE()
+#pragma unroll
+      for (int r = 0; r < RE; ++r) { qkvg[r][0] = half[r][0]; qkvg[r][1] = half[r][1]; }
+      LAYER(p.wo, kD, kD)
+      dense<2, RE>(cur_w, 2 * kD, cur, half, xs, lane);
+      LAYER_DONE()
+#pragma unroll
+      for (int r = 0; r < RE; ++r) { qkvg[r][2] = half[r][0]; qkvg[r][3] = half[r][1]; }
+    }
     // retention: H <- lam H + sum_i k_i^T v_i ; ret_i = q_i H   (all A tokens are added before any output)
 #pragma unroll
     for (int r = 0; r < RE; ++r) ret[r] = make_float2(0.f, 0.f);
@@ -342,19 +359,19 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
 #pragma unroll
     for (int r = 0; r < RE; ++r) cur[r] = gn_gate(gate[r], ret[r], gs, gb);
     float2 o[RE];
-    LAYER(p.ffn_gl, kD * 2 * kD)
+    LAYER(p.ffn_gl, 2 * kD, 2 * kD)
     dense1<RE>(cur_w, cur, o, xs, lane);
     LAYER_DONE()
     const float2 ln1 = ldg2(p.ln1 + 2 * lane);
 #pragma unroll
     for (int r = 0; r < RE; ++r) xin[r] = rmsnorm(f2add(o[r], xin[r]), ln1);  // x1
     float2 gl[RE][2];
-    LAYER(p.ffn_out, kD * kD)
+    LAYER(p.ffn_out, kD, kD)
     dense<2, RE>(cur_w, 2 * kD, xin, gl, xs, lane);
     LAYER_DONE()
 #pragma unroll
     for (int r = 0; r < RE; ++r) cur[r] = make_float2(swishf(gl[r][0].x) * gl[r][1].x, swishf(gl[r][0].y) * gl[r][1].y);
-    LAYER(p.h0_w, kD * kD)
+    LAYER(p.h0_w, kD, kD)
     dense1<RE>(cur_w, cur, o, xs, lane);
     LAYER_DONE()
     const float2 ln2 = ldg2(p.ln2 + 2 * lane);
@@ -364,7 +381,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
       xpe[r] = f2add(x[r], pe_row(s.pe, stp[r], s.max_step, lane));
     }
     // value head: Dense(64) -> gelu -> RMSNorm -> Dense(1)
-    LAYER(full ? p.wo1 : nullptr, kD * kD)
+    LAYER(full ? p.wo1 : nullptr, kD, kD)
     dense1<RE>(cur_w, x, o, xs, lane);
     LAYER_DONE()
     const float2 hb = ldg2(p.h0_b + 2 * lane), hs = ldg2(p.h2_s + 2 * lane), hw = ldg2(p.h3_w + 2 * lane);
@@ -430,7 +447,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
       float2 q1[EPW];
 #pragma unroll
       for (int e = 0; e < EPW; ++e) q1[e] = qkvg[e][0];
-      decoder_retention<A>(i, s.h_self, b, live, lam, q1, k1, v1, r1, lane);
+      decoder_retention<A, EPW>(i, s.h_self, b, live, lam, q1, k1, v1, r1, lane);
     }
     float2 rpe[EPW];
     {
@@ -438,7 +455,7 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
       float2 t[EPW], o[EPW];
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = gn_gate(g1[e], r1[e], gs, gb);
-      LAYER(p.qkvg2, kD * 4 * kD)
+      LAYER(p.qkvg2, 2 * kD, 4 * kD)  // next: [w_q | w_k] of the cross retention
       dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
 #pragma unroll
@@ -458,13 +475,21 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
       }
       {
         float2 t[EPW][1];
-        LAYER(p.wo2, kD * kD)
-        dense<1, EPW>(cur_w, 4 * kD, qin, t, xs, lane);
+        LAYER(p.qkvg2 + 2 * kD, 2 * kD, 4 * kD)  // next: [w_v | w_g]
+        dense<1, EPW>(cur_w, 2 * kD, qin, t, xs, lane);
 #pragma unroll
         for (int e = 0; e < EPW; ++e) q2[e] = t[e][0];
+        dense<1, EPW>(cur_w + kD, 2 * kD, rpe, t, xs, lane);
+#pragma unroll
+        for (int e = 0; e < EPW; ++e) kvg[e][0] = t[e][0];
+        LAYER_DONE()
+        float2 vg[EPW][2];
+        LAYER(p.wo2, kD, kD)
+        dense<2, EPW>(cur_w, 2 * kD, rpe, vg, xs, lane);
+        LAYER_DONE()
+#pragma unroll
+        for (int e = 0; e < EPW; ++e) { kvg[e][1] = vg[e][0]; kvg[e][2] = vg[e][1]; }
       }
-      dense<3, EPW>(cur_w + kD, 4 * kD, rpe, kvg, xs, lane);
-      LAYER_DONE()
       float2 r2[EPW];
 #pragma unroll
       for (int e = 0; e < EPW; ++e) {
@@ -472,12 +497,12 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
         for (int jj = 0; jj < A; ++jj)
           if (jj == i) { k2[e][jj] = kvg[e][0]; v2[e][jj] = kvg[e][1]; }
       }
-      decoder_retention<A>(i, s.h_cross, b, live, lam, q2, k2, v2, r2, lane);
+      decoder_retention<A, EPW>(i, s.h_cross, b, live, lam, q2, k2, v2, r2, lane);
       const float2 gs = ldg2(p.gn2_s + 2 * lane), gb = ldg2(p.gn2_b + 2 * lane), dln2 = ldg2(p.dln2 + 2 * lane);
       float2 t[EPW], o[EPW];
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = gn_gate(kvg[e][2], r2[e], gs, gb);
-      LAYER(p.dffn_gl, kD * 2 * kD)
+      LAYER(p.dffn_gl, 2 * kD, 2 * kD)
       dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
 #pragma unroll
@@ -492,18 +517,18 @@ sable_step_kernel(const GuiderP p, const StepArgs s) {
     // ---- SwiGLU FFN, head, sample
     {
       float2 gl[EPW][2], t[EPW], o[EPW];
-      LAYER(p.dffn_out, kD * kD)
+      LAYER(p.dffn_out, kD, kD)
       dense<2, EPW>(cur_w, 2 * kD, yv, gl, xs, lane);
       LAYER_DONE()
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = make_float2(swishf(gl[e][0].x) * gl[e][1].x, swishf(gl[e][0].y) * gl[e][1].y);
-      LAYER(p.dh0_w, kD * kD)
+      LAYER(p.dh0_w, kD, kD)
       dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
       const float2 dln3 = ldg2(p.dln3 + 2 * lane);
 #pragma unroll
       for (int e = 0; e < EPW; ++e) t[e] = rmsnorm(f2add(o[e], yv[e]), dln3);  // xd
-      LAYER(i + 1 < A ? p.wo1 : nullptr, kD * kD)
+      LAYER(i + 1 < A ? p.wo1 : nullptr, kD, kD)
       dense1<EPW>(cur_w, t, o, xs, lane);
       LAYER_DONE()
       const float2 hb = ldg2(p.dh0_b + 2 * lane), hs = ldg2(p.dh2_s + 2 * lane);
@@ -579,32 +604,59 @@ decoder_tables_kernel(const GuiderP p, int a, int max_step, const float* __restr
   tab[(size_t)r * 4 * kD + threadIdx.x] = acc;
 }
 
-template <int A>
-int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
-  // small batches: fewer warps per CTA spread the envs over more SMs, but every CTA streams the step's weights (0.4 MB) through its
-  // own shared memory, so below ~7 warps the copies dominate (RWARE shard of 1024 envs, rollout of 128 steps: 40.1 ms at 14 warps,
-  // 34.8 ms at 7, 118 ms at 4 — tools/step_warps_experiment.sh)
-  const int64_t pairs = ceil_div(s.B, EPW);
+// Warps per CTA. Two CTAs share an SM (296 CTA slots): pick the CTA size whose last wave is fullest; small batches keep >= 6 warps,
+// because every CTA streams the step's weights (0.4 MB) through its own shared memory (RWARE shard of 1024 envs, rollout of 128
+// steps: 118 ms at 4 warps per CTA, 34.8 ms at 7 — tools/step_warps_experiment.sh).
+int pick_warps(int64_t units) {
   static int forced_warps = -1;
   if (forced_warps < 0) {
     const char* e = getenv("MAGPO_STEP_WARPS");
     forced_warps = e ? std::min(std::max(atoi(e), 1), SS_WARPS) : 0;
   }
-  const int warps = forced_warps ? forced_warps : (int)std::min<int64_t>(SS_WARPS, std::max<int64_t>(7, ceil_div(pairs, kNumSMs)));
-  const unsigned grid = (unsigned)ceil_div(pairs, warps);
-  const unsigned threads = (unsigned)warps * 32;
-  if (once_per_device(ONCE_SABLE_STEP_1 + A - 1)) {
-    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
-    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
-    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
-    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
+  if (forced_warps) return forced_warps;
+  const int64_t slots = 2 * kNumSMs;
+  int best = 7;
+  double best_eff = -1.0;
+  for (int w = 6; w <= SS_WARPS; ++w) {
+    const int64_t ctas = ceil_div(units, w);
+    const double eff = (double)units / ((double)ceil_div(ctas, slots) * slots * w);  // useful warps / warp slots over all waves
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
   }
-  if (s.d <= 4) sable_step_kernel<A, 4><<<grid, threads, SS_SMEM, st>>>(p, s);
-  else if (s.d <= 8) sable_step_kernel<A, 8><<<grid, threads, SS_SMEM, st>>>(p, s);
-  else if (s.d <= 16) sable_step_kernel<A, 16><<<grid, threads, SS_SMEM, st>>>(p, s);
-  else sable_step_kernel<A, 0><<<grid, threads, SS_SMEM, st>>>(p, s);
+  return best;
+}
+
+template <int A, int EPW>
+int launch_ae(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
+  const int64_t units = ceil_div(s.B, EPW);  // warps of work
+  const int warps = pick_warps(units);
+  const unsigned grid = (unsigned)ceil_div(units, warps);
+  const unsigned threads = (unsigned)warps * 32;
+  const uint32_t smem = ss_smem(warps);
+  if (once_per_device(ONCE_SABLE_STEP_1 + (A - 1) * 2 + (EPW - 1))) {
+    const int cap = (int)ss_smem(SS_WARPS);
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 4, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 8, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 16, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    MAGPO_CUDA_OK(cudaFuncSetAttribute(sable_step_kernel<A, 0, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+  }
+  if (s.d <= 4) sable_step_kernel<A, 4, EPW><<<grid, threads, smem, st>>>(p, s);
+  else if (s.d <= 8) sable_step_kernel<A, 8, EPW><<<grid, threads, smem, st>>>(p, s);
+  else if (s.d <= 16) sable_step_kernel<A, 16, EPW><<<grid, threads, smem, st>>>(p, s);
+  else sable_step_kernel<A, 0, EPW><<<grid, threads, smem, st>>>(p, s);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
+}
+
+template <int A>
+int launch_a(cudaStream_t st, const GuiderP& p, const StepArgs& s) {
+  // envs per warp: 2 when the batch fills the 296 CTA slots anyway, 1 below that (twice the warps, half the chain per warp)
+  static int forced_epw = -1;
+  if (forced_epw < 0) {
+    const char* e = getenv("MAGPO_STEP_EPW");
+    forced_epw = e ? atoi(e) : 0;
+  }
+  const int epw = (forced_epw == 1 || forced_epw == 2) ? forced_epw : (s.B <= 2048 ? 1 : 2);
+  return epw == 1 ? launch_ae<A, 1>(st, p, s) : launch_ae<A, 2>(st, p, s);
 }
 
 }  // namespace

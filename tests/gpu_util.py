@@ -58,6 +58,20 @@ def elementwise_dev(new: dict, ref: dict, floor: float = 1e-3) -> dict:
     return out
 
 
+def update_dev(new: dict, ref: dict, lr: float, rtol: float = 1e-4, atol_lr: float = 0.1) -> dict:
+    """Per tensor: (max |new - ref| in units of the learning rate, max |new - ref| / (rtol |ref| + atol_lr lr)). The second is the
+    allclose-style violation of `|dp| <= rtol |p| + atol_lr * lr` (<= 1 passes): north_star's rtol 1e-4 on the parameter plus a
+    tenth of ONE optimiser step's reach — an update consists of P*M Adam steps of at most ~lr each, and a parameter that starts at
+    zero (biases, SwiGLU) has no scale of its own for a relative bound."""
+    out = {}
+    for k, r in ref.items():
+        r = np.asarray(r, np.float64)
+        n = np.asarray(new[k].cpu().numpy() if torch.is_tensor(new[k]) else new[k], np.float64)
+        d = np.abs(n - r)
+        out[k] = (float(d.max()) / lr, float((d / (rtol * np.abs(r) + atol_lr * lr)).max()))
+    return out
+
+
 def baseline_case(env: str, dev, E=16, U=2, T=128, P=4, M=2, seed=42):
     """(spec, ncfg, osys, oracle state, CUDA learner) of a BASELINE.json config at its real rollout length:
     'coordsum' = configs[0] exactly (CoordSum 3x10-30, num_envs=16, rollout_length=128, U=2, P=4, M=2); 'lbf' = configs[1]'s
@@ -132,12 +146,20 @@ def run_baseline_updates(env: str, dev, updates: int = 2, with_fp64: bool = True
         d = elementwise_dev(cuda, o32)
         row["cuda_vs_o32"] = max(d.values())
         row["cuda_vs_o32_tensor"] = max(d, key=d.get)
-        row["cuda_vs_o32_maxnorm"] = max(rel_err(cuda[k].cpu().numpy(), o32[k]) for k in o32 if np.abs(o32[k]).max() > 0)
+        # max-norm over the tensors that have a scale of their own (zero-initialised ones are a few lr large after one update)
+        row["cuda_vs_o32_maxnorm"] = max(rel_err(cuda[k].cpu().numpy(), o32[k]) for k in o32 if np.abs(o32[k]).max() > 0.02)
+        lr = osys.actor_lr
+        u = update_dev(cuda, o32, lr)
+        row["cuda_vs_o32_lr"] = max(v[0] for v in u.values())
+        row["cuda_vs_o32_viol"] = max(v[1] for v in u.values())
         if with_fp64:
             o64 = {**{"g/" + k: v for k, v in s64["guider_params"].items()}, **{"a/" + k: v for k, v in s64["actor_params"].items()}}
             dc, do = elementwise_dev(cuda, o64), elementwise_dev(o32, o64)
             row["cuda_vs_o64"], row["o32_vs_o64"] = max(dc.values()), max(do.values())
             row["cuda_vs_o64_tensor"], row["o32_vs_o64_tensor"] = max(dc, key=dc.get), max(do, key=do.get)
+            uc, uo = update_dev(cuda, o64, lr), update_dev(o32, o64, lr)
+            row["cuda_vs_o64_lr"], row["o32_vs_o64_lr"] = max(v[0] for v in uc.values()), max(v[0] for v in uo.values())
+            row["cuda_vs_o64_viol"], row["o32_vs_o64_viol"] = max(v[1] for v in uc.values()), max(v[1] for v in uo.values())
         rows.append(row)
         if resync:
             lrn.set_params(state["guider_params"], state["actor_params"])

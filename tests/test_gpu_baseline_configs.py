@@ -4,12 +4,13 @@ P*M = 8 optimiser steps per update), and the envs of configs[1] (LBF 2s-8x8-2p-2
 num_envs=16 so that the oracle finishes in seconds. Sampled actions, rewards and observations must be identical; values / log-probs
 within 1e-4 and losses within 2e-4 of the oracle.
 
-Parameter tolerance (north_star: "rtol 1e-4 per update"): element-wise |dp| / max(|p|, 1e-3) is NOT bounded by 1e-4 for ANY fp32
-implementation, the fp32 oracle included — Adam normalises each gradient element by its own running magnitude, so an element whose
-gradient is at the fp32 noise floor moves by a noise-determined fraction of lr. The control makes that measurable: the same update in
-double precision from the identical state (oracle64) is the reference point, and the CUDA path's element-wise deviation from it must
-stay within 2x the fp32 oracle's own deviation from it (plus 1e-4, the stated rtol). In max-norm (|dp| relative to the tensor's largest
-entry) both stay below 1e-4. tools/tolerance_control.py writes the table (profiles/r2_tolerance_control.md)."""
+Parameter tolerance (north_star: "rtol 1e-4 per update"), as settled by the fp32-vs-fp64 control (tools/tolerance_control.py,
+profiles/r2_tolerance_control.md): after one update (P*M = 8 Adam steps) every parameter element satisfies
+    |p_cuda - p_oracle| <= 1e-4 |p_oracle| + 0.1 lr
+against the fp32 oracle and against the same update done in double precision from the identical state. The absolute term is a tenth
+of one optimiser step: zero-initialised tensors (biases, SwiGLU) are only a few lr large after an update and have no scale for a
+purely relative bound, and Adam turns a gradient element at the fp32 noise floor into a noise-determined fraction of lr in ANY fp32
+implementation. Measured: <= 0.01 lr on configs[0]. Tensors with a scale of their own stay within 1e-4 in max-norm."""
 import pytest
 
 from gpu_util import run_baseline_updates
@@ -26,5 +27,6 @@ def test_baseline_config_two_updates_at_T128(dev, env, with_fp64):
         assert r["value_rel"] < 1e-4 and r["logp_rel"] < 1e-4, r
         assert r["loss_dev"] <= 2e-4, r
         assert r["cuda_vs_o32_maxnorm"] <= 1e-4, r
+        assert r["cuda_vs_o32_viol"] <= 1.0, r
         if with_fp64:
-            assert r["cuda_vs_o64"] <= 2.0 * r["o32_vs_o64"] + 1e-4, r
+            assert r["cuda_vs_o64_viol"] <= 1.0 and r["o32_vs_o64_viol"] <= 1.0, r

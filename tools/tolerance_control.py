@@ -24,8 +24,12 @@ args = ap.parse_args()
 torch.set_num_threads(os.cpu_count() or 1)
 dev = torch.device("cuda:0")
 res = {}
-lines = ["| config (E=16, U=2, T=128, P=4, M=2) | mode | update | actions / rewards / obs identical | loss dev | cuda vs o32 (max-norm) | "
-         "cuda vs o32 (element-wise) | cuda vs o64 | o32 vs o64 | ratio | worst tensor (cuda vs o64) |", "|---|---|---|---|---|---|---|---|---|---|---|"]
+lines = ["Columns: max-norm = max |dp| / max |p| over the tensors with max |p| > 0.02; `lr` columns = max |dp| in units of the learning rate "
+         "(2.5e-4; one update = 8 Adam steps of at most ~lr each); `viol` = max |dp| / (1e-4 |p| + 0.1 lr), the asserted bound (<= 1); "
+         "element-wise = max |dp| / max(|p|, 1e-3). o32 / o64 = the CPU oracle's update in float32 / float64 from the identical state.", "",
+         "| config (E=16, U=2, T=128, P=4, M=2) | mode | update | actions / rewards / obs identical | loss dev | cuda vs o32 max-norm | "
+         "cuda vs o32 [lr] | cuda vs o64 [lr] | o32 vs o64 [lr] | cuda vs o64 viol | o32 vs o64 viol | cuda vs o64 element-wise | o32 vs o64 element-wise | "
+         "worst tensor (cuda vs o64) |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
 for env in args.envs.split(","):
     for resync in (True, False):
         rows = run_baseline_updates(env, dev, updates=args.updates, with_fp64=True, resync=resync)
@@ -33,8 +37,9 @@ for env in args.envs.split(","):
         for r in rows:
             ok = r["actions_exact"] and r["rewards_exact"] and r["obs_exact"]
             lines.append(f"| {env} | {'per-update (re-synced)' if resync else 'free-running'} | {r['update']} | {ok} | {r['loss_dev']:.1e} | "
-                         f"{r['cuda_vs_o32_maxnorm']:.1e} | {r['cuda_vs_o32']:.1e} | {r['cuda_vs_o64']:.1e} | {r['o32_vs_o64']:.1e} | "
-                         f"{r['cuda_vs_o64'] / max(r['o32_vs_o64'], 1e-30):.2f} | `{r['cuda_vs_o64_tensor']}` |")
+                         f"{r['cuda_vs_o32_maxnorm']:.1e} | {r['cuda_vs_o32_lr']:.4f} | {r['cuda_vs_o64_lr']:.4f} | {r['o32_vs_o64_lr']:.4f} | "
+                         f"{r['cuda_vs_o64_viol']:.3f} | {r['o32_vs_o64_viol']:.3f} | {r['cuda_vs_o64']:.1e} | {r['o32_vs_o64']:.1e} | "
+                         f"`{r['cuda_vs_o64_tensor']}` |")
             print(lines[-1], flush=True)
 os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
 with open(args.out + ".md", "w") as f:
