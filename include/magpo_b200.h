@@ -105,6 +105,12 @@ int magpo_prng_random_bits(magpo_stream_t s, const uint32_t* key, int64_t n, uin
 int magpo_prng_randint(magpo_stream_t s, const uint32_t* key, int64_t n, int32_t minval,
                        int32_t maxval, int32_t* out /*[n]*/);
 int magpo_prng_gumbel(magpo_stream_t s, const uint32_t* key, int64_t n, float* out /*[n]*/);
+/* jax.random.normal / truncated_normal(key, (n,), float32) — the draws behind flax's normal / lecun_normal / orthogonal initialisers
+ * (sable_network.py:97-107, retention.py:50-64, flax GRUCell): uniform from the threefry bits, sqrt(2) * erf_inv with XLA's
+ * single-precision expansion. fold_in is a host function (flax derives each parameter's key from the module path on the host). */
+int magpo_prng_normal(magpo_stream_t s, const uint32_t* key, int64_t n, float* out /*[n]*/);
+int magpo_prng_truncated_normal(magpo_stream_t s, const uint32_t* key, int64_t n, float lower, float upper, float* out /*[n]*/);
+int magpo_prng_fold_in_host(const uint32_t* key /*host [2]*/, uint32_t data, uint32_t* out /*host [2]*/);
 /* jax.random.permutation(key, n): rounds of stable sort by random bits. scratch: 2n uint32. */
 int magpo_prng_permutation(magpo_stream_t s, const uint32_t* key, int32_t n, int32_t* out,
                            uint32_t* scratch);

@@ -85,6 +85,41 @@ __global__ void iota_kernel(int n, int32_t* out) {
   if (i < n) out[i] = i;
 }
 
+
+// ---------------------------------------------------------------- jax.random.normal / truncated_normal (parameter initialisers)
+// jax 0.6.0 `_normal_real`: u = uniform(key, shape, f32, minval = nextafter(-1, 0), maxval = 1); sqrt(2) * erf_inv(u), and
+// `_truncated_normal`: u = uniform(key, minval = erf(lower / sqrt2), maxval = erf(upper / sqrt2)); clip(sqrt(2) * erf_inv(u), ...).
+// uniform: bits >> 9 | 0x3F800000 -> [1, 2) - 1 -> * (maxval - minval) + minval -> max(minval, .). erf_inv is XLA's single-precision
+// expansion (two degree-8 polynomials in w = -log1p(-x^2), Giles 2010), restated here; the libm log1pf / sqrtf may differ from XLA's
+// own in the last bit.
+__device__ __forceinline__ float xla_erf_inv_f32(float x) {
+  float w = -log1pf(-x * x);
+  const bool lt = w < 5.0f;
+  w = lt ? w - 2.5f : sqrtf(w) - 3.0f;
+  float p = lt ? 2.81022636e-08f : -0.000200214257f;
+  p = (lt ? 3.43273939e-07f : 0.000100950558f) + p * w;
+  p = (lt ? -3.5233877e-06f : 0.00134934322f) + p * w;
+  p = (lt ? -4.39150654e-06f : -0.00367342844f) + p * w;
+  p = (lt ? 0.00021858087f : 0.00573950773f) + p * w;
+  p = (lt ? -0.00125372503f : -0.0076224613f) + p * w;
+  p = (lt ? -0.00417768164f : 0.00943887047f) + p * w;
+  p = (lt ? 0.246640727f : 1.00167406f) + p * w;
+  p = (lt ? 1.50140941f : 2.83297682f) + p * w;
+  return fabsf(x) == 1.0f ? x * INFINITY : p * x;
+}
+__device__ __forceinline__ float uniform_range_from_bits(uint32_t bits, float minval, float maxval) {
+  const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  return fmaxf(minval, f * (maxval - minval) + minval);
+}
+__global__ void __launch_bounds__(256)
+normal_kernel(const uint32_t* __restrict__ key, int64_t n, float minval, float maxval, float clip_lo, float clip_hi, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float u = uniform_range_from_bits(prng_bits_i(key[0], key[1], (uint64_t)i), minval, maxval);
+  const float v = 1.41421356237309504880f * xla_erf_inv_f32(u);
+  out[i] = fminf(fmaxf(v, clip_lo), clip_hi);
+}
+
 }  // namespace magpo
 
 using namespace magpo;
@@ -148,6 +183,33 @@ int magpo_prng_permutation(magpo_stream_t s, const uint32_t* key, int32_t n, int
     src = bufs[cur];
     cur ^= 1;
   }
+  return MAGPO_OK;
+}
+
+// jax.random.normal(key, (n,), float32)
+int magpo_prng_normal(magpo_stream_t s, const uint32_t* key, int64_t n, float* out) {
+  if (!key || !out || n < 0) return MAGPO_ERR_ARG;
+  if (n == 0) return MAGPO_OK;
+  normal_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(s)>>>(key, n, nextafterf(-1.0f, 0.0f), 1.0f, -INFINITY, INFINITY, out);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+// jax.random.truncated_normal(key, lower, upper, (n,), float32)
+int magpo_prng_truncated_normal(magpo_stream_t s, const uint32_t* key, int64_t n, float lower, float upper, float* out) {
+  if (!key || !out || n < 0 || !(lower < upper)) return MAGPO_ERR_ARG;
+  if (n == 0) return MAGPO_OK;
+  const float sqrt2 = 1.41421356237309504880f;
+  normal_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(s)>>>(key, n, erff(lower / sqrt2), erff(upper / sqrt2),
+                                                                    nextafterf(lower, INFINITY), nextafterf(upper, -INFINITY), out);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+// jax.random.fold_in(key, data) = threefry2x32(key, (0, data)) — a host function (keys are host values while networks are initialised)
+int magpo_prng_fold_in_host(const uint32_t* key, uint32_t data, uint32_t* out) {
+  if (!key || !out) return MAGPO_ERR_ARG;
+  threefry2x32(key[0], key[1], 0u, data, out[0], out[1]);
   return MAGPO_OK;
 }
 

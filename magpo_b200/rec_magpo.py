@@ -415,10 +415,10 @@ def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, 
                        net=_network_config(config, env))
     if comm is not None:  # comm.NcclComm: magpo_minibatch_grads reduces the gradients itself (the pmean over "device", :399-409)
         comm.attach(lrn)
-    # parameters: flax's orthogonal/normal initialisers cannot be reproduced bit-for-bit without jax; same shapes, same
-    # gains, NumPy generator seeded from the net keys
-    lrn.set_params(minit.init_guider(env.num_agents, env.obs_dim, env.action_dim, int(np.asarray(net_key)[-1])),
-                   minit.init_actor(env.obs_dim, env.action_dim, int(np.asarray(actor_net_key)[-1])))
+    # parameters: flax's initialisers from the two net keys (rec_magpo.py:596-606) — per-parameter keys folded from the module path,
+    # jax.random.normal / truncated_normal draws from the library's threefry kernels, Householder QR for the orthogonal ones
+    lrn.set_params(minit.flax_init_guider(np.asarray(net_key, np.uint32), env.num_agents, env.obs_dim, env.action_dim, lrn.dev),
+                   minit.flax_init_actor(np.asarray(actor_net_key, np.uint32), env.obs_dim, env.action_dim, lrn.dev))
     U, E = lrn.sys.update_batch_size, lrn.sys.num_envs
     # key, *env_keys = split(key, Nd*U*E + 1); reset_key = split(key)[1] is the step key of every device and slot (:642-673)
     allk = minit.split(np.asarray(key, np.uint32), world_size * U * E + 1, device)

@@ -169,3 +169,51 @@ def randint_batched(keys, n: int, minval: int, maxval: int):
     with np.errstate(over="ignore"):
         off = ((hi % span) * mult + (lo % span)) % span
     return (np.int32(minval) + off.astype(np.int32)).astype(np.int32)
+
+
+# ---- jax.random.fold_in / normal / truncated_normal (parameter initialisers; checked against the library's kernels) ----
+def fold_in(key, data: int):
+    """jax.random.fold_in(key, data) = threefry2x32(key, threefry_seed(data)) with threefry_seed(uint32 d) = (0, d)."""
+    key = np.asarray(key, dtype=_U32)
+    o0, o1 = threefry2x32(key, np.zeros(1, _U32), np.array([data], _U32))
+    return np.array([o0[0], o1[0]], dtype=_U32)
+
+
+def erf_inv_f32(x):
+    """XLA's single-precision erf_inv expansion (two degree-8 polynomials in w = -log1p(-x^2))."""
+    f = np.float32
+    x = np.asarray(x, f)
+    w = (-np.log1p(-x * x)).astype(f)
+    lt = w < f(5.0)
+    w = np.where(lt, w - f(2.5), np.sqrt(w) - f(3.0)).astype(f)
+    lo = [2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503, -0.00417768164, 0.246640727, 1.50140941]
+    hi = [-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613, 0.00943887047, 1.00167406, 2.83297682]
+    p = np.where(lt, f(lo[0]), f(hi[0])).astype(f)
+    for a, b in zip(lo[1:], hi[1:]):
+        p = (np.where(lt, f(a), f(b)) + p * w).astype(f)
+    return (p * x).astype(f)
+
+
+def _uniform_range(key, shape, minval, maxval):
+    f = np.float32
+    bits = random_bits(key, shape)
+    u = ((bits >> _U32(9)) | _U32(0x3F800000)).view(f) - f(1.0)
+    return np.maximum(f(minval), (u * (f(maxval) - f(minval)) + f(minval)).astype(f))
+
+
+def normal(key, shape):
+    """jax.random.normal(key, shape, float32) (jax 0.6.0 `_normal_real`)."""
+    f = np.float32
+    u = _uniform_range(key, shape, np.nextafter(f(-1.0), f(0.0)), f(1.0))
+    return (f(np.sqrt(2.0)) * erf_inv_f32(u)).astype(f)
+
+
+def truncated_normal(key, lower, upper, shape):
+    """jax.random.truncated_normal(key, lower, upper, shape, float32)."""
+    import math
+
+    f = np.float32
+    s2 = f(np.sqrt(2.0))
+    a, b = f(math.erf(float(f(lower) / s2))), f(math.erf(float(f(upper) / s2)))
+    out = (s2 * erf_inv_f32(_uniform_range(key, shape, a, b))).astype(f)
+    return np.clip(out, np.nextafter(f(lower), f(np.inf)), np.nextafter(f(upper), f(-np.inf)))

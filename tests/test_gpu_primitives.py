@@ -309,3 +309,40 @@ def test_thin_n_layers(dev, R, N):
     assert rel_err(dbx.cpu().numpy(), ((dY.astype(np.float64) @ W.T) * (X > 0)).sum(0) + 0.125) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
     assert rel_err(dW.cpu().numpy(), X.astype(np.float64).T @ dY + 0.5) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
     assert rel_err(db.cpu().numpy(), dY.astype(np.float64).sum(0) - 0.25) < 3e-6 * max(1.0, (R / 1000) ** 0.5)
+
+
+def test_prng_normal_and_flax_shaped_init(dev):
+    """jax.random.normal / truncated_normal kernels against the NumPy restatement (same threefry bits, same erf_inv expansion; libm
+    log1p may differ in the last bits), and the flax-shaped initialisers built on them: orthogonal kernels are orthogonal with the
+    right gain, every parameter gets its own key, the result is a pure function of the net key."""
+    from magpo_b200 import init as minit
+    from oracle import prng as oprng
+
+    key = oprng.split(oprng.prng_key(42), 4)[3]
+    got = minit._draw(key, 5000, dev)
+    ref = oprng.normal(key, (5000,))
+    assert np.abs(got - ref).max() <= 4e-6 * max(1.0, float(np.abs(ref).max()))
+    got_t = minit._draw(key, 5000, dev, truncated=True)
+    ref_t = oprng.truncated_normal(key, -2.0, 2.0, (5000,))
+    assert np.abs(got_t - ref_t).max() <= 4e-6 and float(np.abs(got_t).max()) < 2.0
+    gp = minit.flax_init_guider(key, 3, 7, 5, dev)
+    gp2 = minit.flax_init_guider(key, 3, 7, 5, dev)
+    other = minit.flax_init_guider(oprng.split(key)[0], 3, 7, 5, dev)
+    for name, v in gp.items():
+        assert v.dtype == np.float32 and (v == gp2[name]).all(), name
+    w = gp["encoder/head/layers_0/kernel"]
+    assert np.abs(w.T @ w - 2.0 * np.eye(64)).max() < 1e-4  # orthogonal(sqrt 2)
+    w = gp["encoder/obs_encoder/layers_1/kernel"]  # rows < cols: orthonormal rows
+    assert np.abs(w @ w.T - 2.0 * np.eye(7)).max() < 1e-4
+    w = gp["decoder/head/layers_3/kernel"]
+    assert np.abs(w.T @ w - 1e-4 * np.eye(5)).max() < 1e-8
+    wq, wk = gp["encoder/encoder_block_0/retn/retention_heads_0/w_q"], gp["encoder/encoder_block_0/retn/retention_heads_0/w_k"]
+    assert abs(float(wq.std()) - 1 / 64) < 2e-3 and not np.allclose(wq, wk)
+    assert not np.allclose(wq, gp["decoder/decoder_block_0/retn1/retention_heads_0/w_q"])
+    assert not np.allclose(wq, other["encoder/encoder_block_0/retn/retention_heads_0/w_q"])
+    assert (gp["encoder/encoder_block_0/ffn/W_gate"] == 0).all() and (gp["encoder/ln/scale"] == 1).all()
+    ap = minit.flax_init_actor(key, 7, 5, dev)
+    wh = ap["ScannedRNN_0/GRUCell_0/hr/kernel"]
+    assert np.abs(wh.T @ wh - np.eye(128)).max() < 1e-4
+    wi = ap["ScannedRNN_0/GRUCell_0/ir/kernel"]
+    assert abs(float(wi.std()) - 1 / np.sqrt(128)) < 5e-3 and float(np.abs(wi).max()) <= 2.0 / np.sqrt(128) / 0.8796 + 1e-6

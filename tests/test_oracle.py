@@ -317,3 +317,28 @@ def test_param_table_matches_oracle_param_names():
                 assert not covered[sl].any(), name  # no overlap between tensors
                 covered[sl] = True
         assert covered.sum() == sum(v.size for v in ref.values())
+
+
+def test_fold_in_and_normal_restatements():
+    """fold_in(key, i) == split(key, n)[i] under the partitionable threefry scheme (both are threefry(key, (0, i))), the library's host
+    fold_in agrees with the oracle's, and the normal draws have the right moments / tails (erf_inv against scipy in float64)."""
+    import ctypes as C
+
+    from scipy.special import erfinv
+
+    from magpo_b200 import _lib as L
+
+    key = prng.prng_key(7)
+    ks = prng.split(key, 6)
+    for i in range(6):
+        assert (prng.fold_in(key, i) == ks[i]).all()
+    out = (C.c_uint32 * 2)()
+    kk = (C.c_uint32 * 2)(int(key[0]), int(key[1]))
+    assert L.lib().magpo_prng_fold_in_host(kk, C.c_uint32(0xDEADBEEF), out) == 0
+    assert (np.array([out[0], out[1]], np.uint32) == prng.fold_in(key, 0xDEADBEEF)).all()
+    x = np.linspace(-0.999999, 0.999999, 20001).astype(np.float32)
+    assert np.abs(prng.erf_inv_f32(x) - erfinv(x.astype(np.float64))).max() < 3e-6 * 3.5
+    z = prng.normal(key, (200_000,))
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01 and np.isfinite(z).all()
+    t = prng.truncated_normal(key, -2.0, 2.0, (100_000,))
+    assert float(t.min()) > -2.0 and float(t.max()) < 2.0 and abs(float(t.std()) - 0.8796) < 0.01
