@@ -62,7 +62,13 @@ struct ActorP {
 
 inline int check_net(const MagpoNetCfg* n) {
   if (!n) return MAGPO_ERR_ARG;
-  if (n->embed_dim != kD || n->n_head != 1 || n->n_block != 1 || n->hidden != kH) return MAGPO_ERR_UNSUPPORTED;
+  if (n->hidden != kH) return MAGPO_ERR_UNSUPPORTED;
+  {  // guider shapes: the default (64, 1, 1) on the specialised kernels, the others on the general path (generic.cuh: net_shape_ok)
+    const int D = n->embed_dim, nh = n->n_head, nb = n->n_block;
+    if (D != 32 && D != 64 && D != 128) return MAGPO_ERR_UNSUPPORTED;
+    if (nh != 1 && nh != 2 && nh != 4) return MAGPO_ERR_UNSUPPORTED;
+    if (nb < 1 || nb > 3 || D % nh || (D / nh) % nh) return MAGPO_ERR_UNSUPPORTED;
+  }
   if (n->n_agents < 1 || n->n_agents > kMaxAgents) return MAGPO_ERR_UNSUPPORTED;
   if (n->action_dim < 1 || n->action_dim > kMaxActions) return MAGPO_ERR_UNSUPPORTED;
   if (n->obs_dim < 1 || n->obs_dim > 128) return MAGPO_ERR_UNSUPPORTED;

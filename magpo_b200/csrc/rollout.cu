@@ -6,6 +6,7 @@
 // by one tiny kernel up front (rec_magpo.py:135,202; decode.py:140).
 #include "actor.cuh"
 #include "envs.cuh"
+#include "generic.cuh"
 #include "prng.cuh"
 #include "sable.cuh"
 #include "update.cuh"
@@ -103,12 +104,12 @@ sample_kernel(int64_t B, int A, int i, int a, int gumbel_rows, const float* __re
   prev_action[b] = best_j;
 }
 
-// dst[b] = done[b] ? 0 : src[b]  for [B, 64*64] states
-__global__ void copy_zero_done_kernel(int64_t B, const float* __restrict__ src, const uint8_t* __restrict__ done,
-                                      float* __restrict__ dst) {
+// dst[b] = done[b] ? 0 : src[b]  for [B, n_head, n_block, hs, hs] states
+__global__ void copy_zero_done_kernel(int64_t B, int64_t quads /* float4 per env state */, const float* __restrict__ src,
+                                      const uint8_t* __restrict__ done, float* __restrict__ dst) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * (kD * kD / 4)) return;
-  const int64_t b = idx / (kD * kD / 4);
+  if (idx >= B * quads) return;
+  const int64_t b = idx / quads;
   float4 v = reinterpret_cast<const float4*>(src)[idx];
   if (done && done[b]) v = make_float4(0.f, 0.f, 0.f, 0.f);
   reinterpret_cast<float4*>(dst)[idx] = v;
@@ -124,12 +125,24 @@ struct RolloutWs {
   float *pe, *dec_tab, *xrep_i, *xrep_pe_i, *logits_i;
   int32_t *step_i, *prev_action;
   uint32_t* sample_keys;
+  void* gws;  // general guider shapes (generic.cuh): the step workspace of sable_g_get_actions instead of the default path's buffers
+  size_t gws_bytes;
   void plan(Arena& ar, const MagpoNetCfg* net, int B, int T) {
     const int64_t R = (int64_t)B * net->n_agents;
-    sa.plan(ar, R, B, net->obs_dim, false);
     aa.plan(ar, R, R, net->action_dim, false);
-    gt.plan(ar, net->obs_dim);
     at.plan(ar, net->action_dim);
+    sample_keys = ar.get<uint32_t>((size_t)(T + 1) * net->n_agents * 2);
+    gws = nullptr; gws_bytes = 0;
+    const NetShape shape = NetShape::of(net);
+    if (!shape.is_default()) {
+      gws_bytes = sable_g_step_workspace_bytes(shape, B);
+      gws = ar.get<char>(gws_bytes);
+      pe = dec_tab = xrep_i = xrep_pe_i = logits_i = nullptr;
+      step_i = prev_action = nullptr;
+      return;
+    }
+    sa.plan(ar, R, B, net->obs_dim, false);
+    gt.plan(ar, net->obs_dim);
     pe = ar.get<float>((size_t)(net->max_step_count + 1) * kD);
     dec_tab = ar.get<float>(sable_step_table_floats(net));
     xrep_i = ar.get<float>((size_t)B * kD);
@@ -137,7 +150,6 @@ struct RolloutWs {
     logits_i = ar.get<float>((size_t)B * net->action_dim);
     step_i = ar.get<int32_t>(B);
     prev_action = ar.get<int32_t>(B);
-    sample_keys = ar.get<uint32_t>((size_t)(T + 1) * net->n_agents * 2);
   }
 };
 
@@ -147,6 +159,9 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
                 const uint8_t* prev_done, const uint32_t* sample_keys, MagpoSableHState hs, bool dry,
                 int32_t* action, float* log_prob, float* value, float* masked_logits, const RolloutWs& w) {
   const int A = net->n_agents, d = net->obs_dim, a = net->action_dim, ms = net->max_step_count;
+  if (w.gws)  // general (embed_dim, n_head, n_block): layer by layer (the caller prepared the workspace once: sable_g_prepare)
+    return sable_g_get_actions(s, net, B, gumbel_rows, gp.obs_scale, agents_view, action_mask, step_count, prev_done, sample_keys, hs, dry,
+                               action, log_prob, value, masked_logits, w.gws, w.gws_bytes, false);
   if (!g_force_unfused && sable_step_supported(A, d, a))
     return sable_step(s, net, B, gumbel_rows, gp, kappa, agents_view, action_mask, step_count, prev_done, sample_keys, w.pe, w.dec_tab,
                       hs, dry, action, log_prob, value, masked_logits);
@@ -178,6 +193,14 @@ int get_actions(cudaStream_t s, const MagpoNetCfg* net, int B, int gumbel_rows, 
 }
 
 }  // namespace
+
+int sample_agent(cudaStream_t s, int64_t B, int A, int i, int a, int gumbel_rows, const float* logits, const uint8_t* mask, const uint32_t* key,
+                 int32_t* action, float* log_prob, int32_t* prev_action, float* masked_logits) {
+  ProfScope ps(PROF_SAMPLE, s, (double)B * (5.0 * a + 12.0));
+  sample_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, A, i, a, gumbel_rows, logits, mask, key, action, log_prob, prev_action, masked_logits);
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
 }  // namespace magpo
 
 using namespace magpo;
@@ -211,6 +234,9 @@ int magpo_sable_get_actions(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNe
   RolloutWs w;
   w.plan(ar, net, B, 0);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
+  if (w.gws)
+    return sable_g_get_actions(s, net, B, gumbel_rows, guider, agents_view, action_mask, step_count, prev_done, sample_keys, hs, false, action,
+                               log_prob, value, logits, w.gws, w.gws_bytes, true);
   MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
   if (!g_force_unfused && sable_step_supported(net->n_agents, net->obs_dim, net->action_dim))
     MAGPO_TRY(sable_step_tables(s, net, GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim), w.pe, w.dec_tab));
@@ -251,20 +277,29 @@ int magpo_rollout(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net,
   RolloutWs w;
   w.plan(ar, net, B, T);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
-  const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), d, a);
+  const NetShape shape = NetShape::of(net);
+  GuiderP gp = GuiderP::bind(const_cast<float*>(guider), d, a);
   const ActorP ap = ActorP::bind(const_cast<float*>(actor), d, a);
   const float kappa = net_kappa(net);
-
-  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
-  if (!g_force_unfused && sable_step_supported(net->n_agents, net->obs_dim, net->action_dim))
-    MAGPO_TRY(sable_step_tables(s, net, GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim), w.pe, w.dec_tab));
   const GuiderT* gtp = nullptr;
   const ActorT* atp = nullptr;
-  if (tc_enabled()) {  // parameters are constant during the rollout: one transpose + TF32 split up front
-    MAGPO_TRY(guider_transpose(s, gp, w.gt, d));
-    MAGPO_TRY(actor_transpose(s, ap, w.at, a));
-    gtp = &w.gt;
-    atp = &w.at;
+  if (w.gws) {  // general guider shape: PE table, transposed weights and their TF32 images once per rollout
+    gp.obs_scale = const_cast<float*>(guider);  // get_actions hands the flat buffer to the general path
+    MAGPO_TRY(sable_g_prepare(s, net, B, guider, w.gws, w.gws_bytes));
+    if (tc_enabled()) {
+      MAGPO_TRY(actor_transpose(s, ap, w.at, a));
+      atp = &w.at;
+    }
+  } else {
+    MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
+    if (!g_force_unfused && sable_step_supported(net->n_agents, net->obs_dim, net->action_dim))
+      MAGPO_TRY(sable_step_tables(s, net, GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim), w.pe, w.dec_tab));
+    if (tc_enabled()) {  // parameters are constant during the rollout: one transpose + TF32 split up front
+      MAGPO_TRY(guider_transpose(s, gp, w.gt, d));
+      MAGPO_TRY(actor_transpose(s, ap, w.at, a));
+      gtp = &w.gt;
+      atp = &w.at;
+    }
   }
   if (carry_over) {  // LearnerState.timestep of the previous call becomes observation slot 0
     MAGPO_CUDA_OK(cudaMemcpyAsync(traj.done, traj.done + (size_t)T * B, B, cudaMemcpyDeviceToDevice, s));
@@ -277,12 +312,13 @@ int magpo_rollout(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net,
   }
   // hidden states the update will start from (rec_magpo.py:190-192, 244-248)
   MAGPO_CUDA_OK(cudaMemcpyAsync(traj.policy_h0, policy_h, BA * kH * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  const unsigned gz = g256((int64_t)B * (kD * kD / 4));
-  copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, hs.encoder, traj.done, traj.sable_h0.encoder);
+  const int64_t quads = shape.state_elems() / 4;
+  const unsigned gz = g256((int64_t)B * quads);
+  copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, quads, hs.encoder, traj.done, traj.sable_h0.encoder);
   MAGPO_LAUNCH_OK();
-  copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, hs.decoder_self, traj.done, traj.sable_h0.decoder_self);
+  copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, quads, hs.decoder_self, traj.done, traj.sable_h0.decoder_self);
   MAGPO_LAUNCH_OK();
-  copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, hs.decoder_cross, traj.done, traj.sable_h0.decoder_cross);
+  copy_zero_done_kernel<<<gz, 256, 0, s>>>(B, quads, hs.decoder_cross, traj.done, traj.sable_h0.decoder_cross);
   MAGPO_LAUNCH_OK();
   rollout_keys_kernel<<<1, 32, 0, s>>>(key, T + 1, A, w.sample_keys);
   MAGPO_LAUNCH_OK();

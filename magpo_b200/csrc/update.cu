@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "actor.cuh"
+#include "generic.cuh"
 #include "prng.cuh"
 #include "sable.cuh"
 
@@ -110,7 +111,7 @@ pack_rows_narrow_kernel(int T, int B, int A, int d, int a, int n_env, MagpoTraje
 }
 
 __global__ void __launch_bounds__(256)
-pack_hidden_kernel(int A, int n_env, const float* __restrict__ policy_h0, const float* __restrict__ h_enc,
+pack_hidden_kernel(int A, int n_env, int quads /* float4 per env state */, const float* __restrict__ policy_h0, const float* __restrict__ h_enc,
                    const float* __restrict__ h_self, const float* __restrict__ h_cross,
                    const int32_t* __restrict__ env_index, const int32_t* __restrict__ hs_index,
                    const int32_t* __restrict__ agent_perm, float* __restrict__ o_h0, float* __restrict__ o_enc,
@@ -121,13 +122,13 @@ pack_hidden_kernel(int A, int n_env, const float* __restrict__ policy_h0, const 
     const int i = idx / kH, c = idx % kH;
     o_h0[((int64_t)n * A + i) * kH + c] = policy_h0[((int64_t)b * A + agent_perm[i]) * kH + c];
   }
-  const float4* se = reinterpret_cast<const float4*>(h_enc + (int64_t)hb * kD * kD);
-  const float4* ss = reinterpret_cast<const float4*>(h_self + (int64_t)hb * kD * kD);
-  const float4* sc = reinterpret_cast<const float4*>(h_cross + (int64_t)hb * kD * kD);
-  float4* de = reinterpret_cast<float4*>(o_enc + (int64_t)n * kD * kD);
-  float4* ds = reinterpret_cast<float4*>(o_self + (int64_t)n * kD * kD);
-  float4* dc = reinterpret_cast<float4*>(o_cross + (int64_t)n * kD * kD);
-  for (int idx = threadIdx.x; idx < kD * kD / 4; idx += blockDim.x) {
+  const float4* se = reinterpret_cast<const float4*>(h_enc) + (int64_t)hb * quads;
+  const float4* ss = reinterpret_cast<const float4*>(h_self) + (int64_t)hb * quads;
+  const float4* sc = reinterpret_cast<const float4*>(h_cross) + (int64_t)hb * quads;
+  float4* de = reinterpret_cast<float4*>(o_enc) + (int64_t)n * quads;
+  float4* ds = reinterpret_cast<float4*>(o_self) + (int64_t)n * quads;
+  float4* dc = reinterpret_cast<float4*>(o_cross) + (int64_t)n * quads;
+  for (int idx = threadIdx.x; idx < quads; idx += blockDim.x) {
     de[idx] = se[idx];
     ds[idx] = ss[idx];
     dc[idx] = sc[idx];
@@ -141,16 +142,27 @@ struct UpdateWs {
   ActorActs aa;
   float *pe, *lg, *ll, *value, *dlg, *dll, *dvalue;
   float *g_hi, *g_lo, *a_hi, *a_lo;  // TF32 hi/lo images of the two flat parameter buffers (dX operands)
+  void* gws;  // general guider shapes (generic.cuh): the workspace of sable_g_train_forward / backward
+  size_t gws_bytes;
   void plan(Arena& ar, const MagpoNetCfg* net, int T, int N, bool with_backward) {
     const int A = net->n_agents, a = net->action_dim, d = net->obs_dim;
     const int64_t Rs = (int64_t)N * A, R = Rs * T;
-    gt.plan(ar, d);
+    const NetShape shape = NetShape::of(net);
+    gws = nullptr; gws_bytes = 0;
     at.plan(ar, a);
-    const int64_t n_g = GuiderP::bind(nullptr, d, a).total, n_a = ActorP::bind(nullptr, d, a).total;
-    g_hi = ar.get<float>((size_t)n_g); g_lo = ar.get<float>((size_t)n_g);
+    const int64_t n_a = ActorP::bind(nullptr, d, a).total;
     a_hi = ar.get<float>((size_t)n_a); a_lo = ar.get<float>((size_t)n_a);
-    sa.plan(ar, R, (int64_t)T * N, d, with_backward);
     aa.plan(ar, R, Rs, a, with_backward);
+    if (shape.is_default()) {
+      gt.plan(ar, d);
+      const int64_t n_g = GuiderP::bind(nullptr, d, a).total;
+      g_hi = ar.get<float>((size_t)n_g); g_lo = ar.get<float>((size_t)n_g);
+      sa.plan(ar, R, (int64_t)T * N, d, with_backward);
+    } else {
+      g_hi = g_lo = nullptr;
+      gws_bytes = sable_g_workspace_bytes(shape, T, N, with_backward);
+      gws = ar.get<char>(gws_bytes);
+    }
     pe = ar.get<float>((size_t)(net->max_step_count + 1) * kD);
     lg = ar.get<float>((size_t)R * a);
     ll = ar.get<float>((size_t)R * a);
@@ -243,7 +255,7 @@ int magpo_pack_minibatch(magpo_stream_t s_, const MagpoNetCfg* net, const MagpoS
       const_cast<uint8_t*>(out.done), const_cast<int32_t*>(out.action), const_cast<float*>(out.value),
       const_cast<float*>(out.log_prob), const_cast<float*>(out.advantages), const_cast<float*>(out.targets));
   MAGPO_LAUNCH_OK();
-  pack_hidden_kernel<<<n_env, 256, 0, s>>>(A, n_env, traj.policy_h0, traj.sable_h0.encoder, traj.sable_h0.decoder_self,
+  pack_hidden_kernel<<<n_env, 256, 0, s>>>(A, n_env, (int)(NetShape::of(net).state_elems() / 4), traj.policy_h0, traj.sable_h0.encoder, traj.sable_h0.decoder_self,
                                            traj.sable_h0.decoder_cross, env_index, hs_index, agent_perm,
                                            const_cast<float*>(out.policy_h0), out.sable_h0.encoder,
                                            out.sable_h0.decoder_self, out.sable_h0.decoder_cross);
@@ -293,16 +305,21 @@ int magpo_minibatch_grads(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetC
   UpdateWs w;
   w.plan(ar, net, T, N, true);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
-  const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), d, a);
+  const NetShape shape = NetShape::of(net);
+  const bool general = !shape.is_default();
+  GuiderP gp = GuiderP::bind(const_cast<float*>(guider), d, a);
+  if (general) gp.total = GuiderG::bind(nullptr, shape).total;  // the general layout's length; the default structs are not used then
   const ActorP ap = ActorP::bind(const_cast<float*>(actor), d, a);
   const GuiderP gg = GuiderP::bind(grads, d, a);
   const ActorP ag = ActorP::bind(grads + gp.total, d, a);
   float* loss_sums = grads + gp.total + ap.total;
-  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
-  MAGPO_TRY(guider_transpose(s, gp, w.gt, d));
   MAGPO_TRY(actor_transpose(s, ap, w.at, a));
+  if (!general) {
+    MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
+    MAGPO_TRY(guider_transpose(s, gp, w.gt, d));
+  }
   if (tc_enabled()) {
-    MAGPO_TRY(tc_prepare_region(s, guider, gp.total, w.g_hi, w.g_lo));
+    if (!general) MAGPO_TRY(tc_prepare_region(s, guider, gp.total, w.g_hi, w.g_lo));
     MAGPO_TRY(tc_prepare_region(s, actor, ap.total, w.a_hi, w.a_lo));
   }
   const SableBatch b = make_batch(net, mb, w.pe);
@@ -320,7 +337,13 @@ int magpo_minibatch_grads(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetC
   if (sable_only) skip_learner = true;
   if (!(skip & 2) && !skip_learner)
     MAGPO_TRY(actor_forward(s2, ap, &w.at, T, N, A, d, a, mb.agents_view, mb.done, mb.policy_h0, w.aa, w.ll, nullptr));
-  if (!(skip & 1)) MAGPO_TRY(sable_train_forward(sg, gp, &w.gt, b, w.sa, w.value, w.lg, true));
+  if (!(skip & 1)) {
+    if (general)
+      MAGPO_TRY(sable_g_train_forward(sg, net, guider, T, N, mb.agents_view, mb.step_count, mb.done, mb.action, mb.sable_h0.encoder,
+                                      mb.sable_h0.decoder_self, mb.sable_h0.decoder_cross, w.value, w.lg, w.gws, w.gws_bytes, true));
+    else
+      MAGPO_TRY(sable_train_forward(sg, gp, &w.gt, b, w.sa, w.value, w.lg, true));
+  }
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_side.join, g_side.s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_side.join, 0));
@@ -340,7 +363,13 @@ int magpo_minibatch_grads(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetC
   // guider's half at the end. Every rank issues the two all-reduces in this order.
   MagpoComm* comm = reduce_grads ? ctx().comm : nullptr;
   if (comm) MAGPO_TRY(comm_allreduce(comm, s2, grads + gp.total, ap.total + 8, 0));
-  if (!(skip & 5)) MAGPO_TRY(sable_train_backward(sg, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
+  if (!(skip & 5)) {
+    if (general)
+      MAGPO_TRY(sable_g_train_backward(sg, net, guider, T, N, mb.agents_view, mb.step_count, mb.done, mb.action, mb.sable_h0.encoder,
+                                       mb.sable_h0.decoder_self, mb.sable_h0.decoder_cross, w.dlg, w.dvalue, grads, w.gws, w.gws_bytes));
+    else
+      MAGPO_TRY(sable_train_backward(sg, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
+  }
   if (comm) MAGPO_TRY(comm_allreduce(comm, sg, grads, gp.total, 0));
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_side.join, g_side.s));
@@ -360,10 +389,15 @@ int magpo_guider_forward(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCf
   UpdateWs w;
   w.plan(ar, net, mb.T, mb.N, false);
   if (ar.overflow) return MAGPO_ERR_WORKSPACE;
-  const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim);
-  MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
-  const SableBatch b = make_batch(net, mb, w.pe);
-  MAGPO_TRY(sable_train_forward(s, gp, nullptr, b, w.sa, value, logits, false));
+  if (w.gws) {
+    MAGPO_TRY(sable_g_train_forward(s, net, guider, mb.T, mb.N, mb.agents_view, mb.step_count, mb.done, mb.action, mb.sable_h0.encoder,
+                                    mb.sable_h0.decoder_self, mb.sable_h0.decoder_cross, value, logits, w.gws, w.gws_bytes, false));
+  } else {
+    const GuiderP gp = GuiderP::bind(const_cast<float*>(guider), net->obs_dim, net->action_dim);
+    MAGPO_TRY(build_pe_table(s, net->max_step_count, w.pe, net->timestep_pe != 0));
+    const SableBatch b = make_batch(net, mb, w.pe);
+    MAGPO_TRY(sable_train_forward(s, gp, nullptr, b, w.sa, value, logits, false));
+  }
   const int64_t n = (int64_t)mb.T * mb.N * net->n_agents * net->action_dim;
   mask_logits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(n, mb.action_mask, logits);
   MAGPO_LAUNCH_OK();
@@ -399,7 +433,7 @@ int magpo_debug_set_skip(int mask) {
 // Test hook: byte offset inside the update workspace of a saved activation (same plan as magpo_minibatch_grads),
 // so that parity tests can compare intermediates with the oracle after a call. Returns -1 for unknown names.
 int64_t magpo_debug_buffer_offset(const MagpoNetCfg* net, int32_t T, int32_t N, const char* name) {
-  if (check_net(net) != MAGPO_OK || !name) return -1;
+  if (check_net(net) != MAGPO_OK || !name || !NetShape::of(net).is_default()) return -1;
   Arena ar(nullptr, SIZE_MAX);
   UpdateWs w;
   w.plan(ar, net, T, N, true);
@@ -512,20 +546,37 @@ static int actor_table(const MagpoNetCfg* net, ParamEntry* out) {
   return n;
 }
 
+// the general guider's table (generic.cuh); names live in a per-thread cache so that the returned pointers stay valid
+static const std::vector<ParamEntryG>& general_table(const MagpoNetCfg* net) {
+  static thread_local std::vector<ParamEntryG> tab;
+  tab.clear();
+  guider_table_g(NetShape::of(net), &tab);
+  return tab;
+}
+
 int64_t magpo_param_count(const MagpoNetCfg* net, int which) {
   if (check_net(net) != MAGPO_OK) return -1;
+  if (which == 0 && !NetShape::of(net).is_default()) return GuiderG::bind(nullptr, NetShape::of(net)).total;
   return which == 0 ? GuiderP::bind(nullptr, net->obs_dim, net->action_dim).total
                     : ActorP::bind(nullptr, net->obs_dim, net->action_dim).total;
 }
 
 int32_t magpo_param_num_tensors(const MagpoNetCfg* net, int which) {
   if (check_net(net) != MAGPO_OK) return -1;
+  if (which == 0 && !NetShape::of(net).is_default()) return (int32_t)general_table(net).size();
   return which == 0 ? guider_table(net, nullptr) : actor_table(net, nullptr);
 }
 
 int magpo_param_tensor(const MagpoNetCfg* net, int which, int32_t index, const char** name, int64_t* offset,
                        int32_t* dim0, int32_t* dim1, int32_t* ld) {
   MAGPO_TRY(check_net(net));
+  if (which == 0 && !NetShape::of(net).is_default()) {
+    const std::vector<ParamEntryG>& t = general_table(net);
+    if (index < 0 || index >= (int32_t)t.size() || !name || !offset || !dim0 || !dim1 || !ld) return MAGPO_ERR_ARG;
+    *name = t[index].name;  // valid until the next table query on this thread
+    *offset = t[index].offset; *dim0 = t[index].dim0; *dim1 = t[index].dim1; *ld = t[index].ld;
+    return MAGPO_OK;
+  }
   ParamEntry tab[64];
   const int n = which == 0 ? guider_table(net, tab) : actor_table(net, tab);
   if (index < 0 || index >= n || !name || !offset || !dim0 || !dim1 || !ld) return MAGPO_ERR_ARG;

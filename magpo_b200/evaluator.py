@@ -51,7 +51,7 @@ def get_eval_fn(env, actor_network, config, absolute_metric: bool, n_devices: in
     mb = dict(agents_view=ts["agents_view"].view(1, n, A, d), action_mask=ts["action_mask"].view(1, n, A, a),
               step_count=ts["step_count"].view(1, n, A), done=z(1, n, dt=torch.uint8), action=z(1, n, A, dt=torch.int32),
               value=z(1, n, A), log_prob=z(1, n, A), advantages=z(1, n, A), targets=z(1, n, A), policy_h0=z(n, A, net.hidden))
-    dummy_h = {k: z(1, 64, 64) for k in ("encoder", "decoder_self", "decoder_cross")}
+    dummy_h = {k: z(1, *net.state_shape) for k in ("encoder", "decoder_self", "decoder_cross")}
     mbs = L.struct_of(L.Minibatch, **mb)
     mbs.sable_h0 = L.struct_of(L.SableHState, **dummy_h)
     mbs.T, mbs.N = 1, n
@@ -121,7 +121,7 @@ def get_sable_eval_fn(env, lrn, config, absolute_metric: bool, n_devices: int = 
     nbytes = int(lib.magpo_rollout_workspace_bytes(C.byref(lrn.c_net), n, 1))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
-    hs = {k: z(n, 64, 64) for k in ("encoder", "decoder_self", "decoder_cross")}
+    hs = {k: z(n, *net.state_shape) for k in ("encoder", "decoder_self", "decoder_cross")}
     action, log_prob, value = z(n, A, dt=torch.int32), z(n, A), z(n, A)
 
     def eval_fn(guider_flat: torch.Tensor, key) -> dict:

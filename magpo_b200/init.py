@@ -31,8 +31,9 @@ def _normal(rng, rows, cols, std):
     return (rng.standard_normal((rows, cols)) * std).astype(np.float32)
 
 
-def init_guider(n_agents: int, obs_dim: int, action_dim: int, seed: int = 0, D: int = 64) -> dict:
+def init_guider(n_agents: int, obs_dim: int, action_dim: int, seed: int = 0, D: int = 64, n_head: int = 1, n_block: int = 1) -> dict:
     rng = np.random.default_rng(seed)
+    hs = D // n_head
     ones, zeros = (lambda n: np.ones(n, np.float32)), (lambda *s: np.zeros(s, np.float32))
     p = {"encoder/obs_encoder/layers_0/scale": ones(obs_dim),
          "encoder/obs_encoder/layers_1/kernel": _orthogonal(rng, obs_dim, D, math.sqrt(2)),
@@ -40,9 +41,10 @@ def init_guider(n_agents: int, obs_dim: int, action_dim: int, seed: int = 0, D: 
 
     def retn(pre):
         p[f"{pre}/w_g"], p[f"{pre}/w_o"] = _normal(rng, D, D, 1 / D), _normal(rng, D, D, 1 / D)
-        p[f"{pre}/group_norm/scale"], p[f"{pre}/group_norm/bias"] = ones(D), zeros(D)
-        for w in ("w_q", "w_k", "w_v"):
-            p[f"{pre}/retention_heads_0/{w}"] = _normal(rng, D, D, 1 / D)
+        p[f"{pre}/group_norm/scale"], p[f"{pre}/group_norm/bias"] = ones(hs), zeros(hs)
+        for h in range(n_head):
+            for w in ("w_q", "w_k", "w_v"):
+                p[f"{pre}/retention_heads_{h}/{w}"] = _normal(rng, D, hs, 1 / D)
 
     def ffn(pre):
         for w in ("W_linear", "W_gate", "W_output"):
@@ -53,19 +55,21 @@ def init_guider(n_agents: int, obs_dim: int, action_dim: int, seed: int = 0, D: 
         p[f"{pre}/layers_2/scale"] = ones(D)
         p[f"{pre}/layers_3/kernel"], p[f"{pre}/layers_3/bias"] = _orthogonal(rng, D, nout, 0.01), zeros(nout)
 
-    eb = "encoder/encoder_block_0"
-    p[f"{eb}/ln1/scale"], p[f"{eb}/ln2/scale"] = ones(D), ones(D)
-    retn(f"{eb}/retn")
-    ffn(f"{eb}/ffn")
+    for b in range(n_block):
+        eb = f"encoder/encoder_block_{b}"
+        p[f"{eb}/ln1/scale"], p[f"{eb}/ln2/scale"] = ones(D), ones(D)
+        retn(f"{eb}/retn")
+        ffn(f"{eb}/ffn")
     head("encoder/head", 1)
     p["decoder/action_encoder/layers_0/kernel"] = _orthogonal(rng, action_dim + 1, D, math.sqrt(2))
     p["decoder/ln/scale"] = ones(D)
-    db = "decoder/decoder_block_0"
-    for ln in ("ln1", "ln2", "ln3"):
-        p[f"{db}/{ln}/scale"] = ones(D)
-    retn(f"{db}/retn1")
-    retn(f"{db}/retn2")
-    ffn(f"{db}/ffn")
+    for b in range(n_block):
+        db = f"decoder/decoder_block_{b}"
+        for ln in ("ln1", "ln2", "ln3"):
+            p[f"{db}/{ln}/scale"] = ones(D)
+        retn(f"{db}/retn1")
+        retn(f"{db}/retn2")
+        ffn(f"{db}/ffn")
     head("decoder/head", action_dim)
     return p
 
@@ -164,12 +168,14 @@ def _flax_lecun_normal(key, shape, device):
     return (_draw(key, int(np.prod(shape)), device, truncated=True).reshape(shape) * std).astype(np.float32)
 
 
-def flax_init_guider(net_key, n_agents: int, obs_dim: int, action_dim: int, device="cuda:0", D: int = 64) -> dict:
+def flax_init_guider(net_key, n_agents: int, obs_dim: int, action_dim: int, device="cuda:0", D: int = 64, n_head: int = 1,
+                     n_block: int = 1) -> dict:
     """SableNetwork.init(net_key, ...) (rec_magpo.py:596-601): the parameter tree of networks/sable_network.py with flax's own
     per-parameter keys and initialisers (orthogonal(sqrt 2) encoders / head hidden layers, orthogonal(0.01) output layers, normal(1 / D)
     retention weights, zeros SwiGLU, ones norms)."""
-    p = init_guider(n_agents, obs_dim, action_dim, 0, D)  # shapes + the constant (ones / zeros) tensors
+    p = init_guider(n_agents, obs_dim, action_dim, 0, D, n_head, n_block)  # shapes + the constant (ones / zeros) tensors
     sq2 = np.sqrt(np.float32(2.0))
+    hs = D // n_head
 
     def orth(path, shape, scale):  # a Dense kernel is its scope's first parameter
         return _flax_orthogonal(_flax_param_key(net_key, path, 0), shape, scale, device)
@@ -179,12 +185,16 @@ def flax_init_guider(net_key, n_agents: int, obs_dim: int, action_dim: int, devi
     for side, nout in (("encoder", 1), ("decoder", action_dim)):
         p[f"{side}/head/layers_0/kernel"] = orth((side, "head", "layers_0"), (D, D), sq2)
         p[f"{side}/head/layers_3/kernel"] = orth((side, "head", "layers_3"), (D, nout), 0.01)
-    for retn in ("encoder/encoder_block_0/retn", "decoder/decoder_block_0/retn1", "decoder/decoder_block_0/retn2"):
+    retns = [f"encoder/encoder_block_{b}/retn" for b in range(n_block)]
+    retns += [f"decoder/decoder_block_{b}/{r}" for b in range(n_block) for r in ("retn1", "retn2")]
+    for retn in retns:
         path = tuple(retn.split("/"))
         for i, w in enumerate(("w_g", "w_o")):  # MultiScaleRetention.setup: w_g, w_o, then the submodules (retention.py:237-246)
             p[f"{retn}/{w}"] = _flax_normal(_flax_param_key(net_key, path, i), (D, D), 1.0 / D, device)
-        for i, w in enumerate(("w_q", "w_k", "w_v")):  # SimpleRetention.setup (retention.py:47-64)
-            p[f"{retn}/retention_heads_0/{w}"] = _flax_normal(_flax_param_key(net_key, path + ("retention_heads_0",), i), (D, D), 1.0 / D, device)
+        for h in range(n_head):
+            for i, w in enumerate(("w_q", "w_k", "w_v")):  # SimpleRetention.setup (retention.py:47-64)
+                p[f"{retn}/retention_heads_{h}/{w}"] = _flax_normal(_flax_param_key(net_key, path + (f"retention_heads_{h}",), i), (D, hs),
+                                                                    1.0 / D, device)
     return p
 
 

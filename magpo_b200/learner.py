@@ -59,6 +59,12 @@ class NetworkConfig:
     timestep_pe: bool = True
     decay_scaling_factor: float = 0.8
 
+    @property
+    def state_shape(self) -> tuple:
+        """One env's Sable hidden state: [n_head, n_block, head_size, head_size] (get_init_hstates.py:20-43)."""
+        hs = self.embed_dim // self.n_head
+        return (self.n_head, self.n_block, hs, hs)
+
     def c_struct(self) -> L.NetCfg:
         return L.NetCfg(self.n_agents, self.obs_dim, self.action_dim, self.embed_dim, self.n_head, self.n_block,
                         self.hidden, int(self.timestep_pe), self.decay_scaling_factor, self.max_step_count)
@@ -253,12 +259,13 @@ class MagpoLearner:
         self.key = z(2, dt=i32)
         self.env_state = env.alloc_state(B, dev)
         self.ts = alloc_timestep(B, A, d, a, dev)
-        self.hs = dict(encoder=z(B, 64, 64), decoder_self=z(B, 64, 64), decoder_cross=z(B, 64, 64))
+        ss = self.net.state_shape
+        self.hs = dict(encoder=z(B, *ss), decoder_self=z(B, *ss), decoder_cross=z(B, *ss))
         self.policy_h = z(B, A, 128)
         self.traj = dict(done=z(T + 1, B, dt=u8), agents_view=z(T + 1, B, A, d), action_mask=z(T + 1, B, A, a, dt=u8),
                          step_count=z(T + 1, B, A, dt=i32), action=z(T, B, A, dt=i32), value=z(T, B, A), reward=z(T, B, A),
                          log_prob=z(T, B, A), policy_h0=z(B, A, 128),
-                         sable_h0=dict(encoder=z(B, 64, 64), decoder_self=z(B, 64, 64), decoder_cross=z(B, 64, 64)),
+                         sable_h0=dict(encoder=z(B, *ss), decoder_self=z(B, *ss), decoder_cross=z(B, *ss)),
                          episode_return=z(T, B), episode_length=z(T, B, dt=i32), is_terminal_step=z(T, B, dt=u8),
                          last_value=z(B, A))
         self.adv, self.targets = z(T, B, A), z(T, B, A)
@@ -269,7 +276,7 @@ class MagpoLearner:
         self.mb = dict(agents_view=z(T, n, A, d), action_mask=z(T, n, A, a, dt=u8), step_count=z(T, n, A, dt=i32),
                        done=z(T, n, dt=u8), action=z(T, n, A, dt=i32), value=z(T, n, A), log_prob=z(T, n, A),
                        advantages=z(T, n, A), targets=z(T, n, A), policy_h0=z(n, A, 128),
-                       sable_h0=dict(encoder=z(n, 64, 64), decoder_self=z(n, 64, 64), decoder_cross=z(n, 64, 64)))
+                       sable_h0=dict(encoder=z(n, *ss), decoder_self=z(n, *ss), decoder_cross=z(n, *ss)))
         self.hs_perm, self.batch_perm, self.agent_perm = z(E, dt=i32), z(E, dt=i32), z(A, dt=i32)
         self.env_index, self.hs_index, self.env_slot = z(M * Nmb, dt=i32), z(M * Nmb, dt=i32), z(M * Nmb, dt=i32)
         self.idx_scratch = z(4 + 2 * max(E, A) + E + 16, dt=i32)
@@ -444,5 +451,5 @@ class MagpoLearner:
 
     def sable_hidden_state(self) -> dict:
         """LearnerState.hstates.sable_hidden_state: reset where the last step was terminal (rec_magpo.py:165-169)."""
-        done = self.traj["done"][self.sys.rollout_length].bool()[:, None, None]
+        done = self.traj["done"][self.sys.rollout_length].bool().view(-1, 1, 1, 1, 1)
         return {k: torch.where(done, torch.zeros_like(v), v) for k, v in self.hs.items()}

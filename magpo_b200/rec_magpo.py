@@ -175,8 +175,8 @@ def _network_config(config: Config, env) -> NetworkConfig:
                         decay_scaling_factor=float(mc.get("decay_scaling_factor", 0.8)))
     c = net.c_struct()
     if L.lib().magpo_param_count(C.byref(c), 0) < 0:
-        raise NotImplementedError(f"network configuration outside what the kernels implement: {net} "
-                                  "(built: embed_dim=64, n_head=1, n_block=1, hidden_state_dim=128, timestep PE on, <= 8 agents)")
+        raise NotImplementedError(f"network configuration outside what the kernels implement: {net} (built: embed_dim 32 / 64 / 128, "
+                                  "n_head 1 / 2 / 4 with head_size divisible by n_head, n_block 1..3, hidden_state_dim=128, <= 8 agents)")
     return net
 
 
@@ -216,7 +216,7 @@ class ActorNetwork:
                   action=z(T, N, A, dt=torch.int32), value=z(T, N, A), log_prob=z(T, N, A), advantages=z(T, N, A),
                   targets=z(T, N, A), policy_h0=hstate.to(torch.float32).contiguous())
         s = L.struct_of(L.Minibatch, **mb)
-        s.sable_h0 = L.struct_of(L.SableHState, **{k: z(N, 64, 64) for k in ("encoder", "decoder_self", "decoder_cross")})
+        s.sable_h0 = L.struct_of(L.SableHState, **{k: z(N, *lrn.net.state_shape) for k in ("encoder", "decoder_self", "decoder_cross")})
         s.T, s.N = T, N
         lib = L.lib()
         lib.magpo_update_workspace_bytes.restype = C.c_size_t
@@ -286,7 +286,7 @@ def _state_views(lrn: MagpoLearner) -> GPOLearnerState:
     sable = lrn.sable_hidden_state() if not lrn.first_rollout else lrn.hs
     for name in ("encoder", "decoder_self", "decoder_cross"):
         exported["sable/" + name] = sable[name]
-    hs = HiddenStates(SableHiddenStates(*(lead(sable[n_]).reshape(1, U, E, 1, 1, 64, 64)
+    hs = HiddenStates(SableHiddenStates(*(lead(sable[n_]).reshape(1, U, E, *lrn.net.state_shape)
                                           for n_ in ("encoder", "decoder_self", "decoder_cross"))), lead(lrn.policy_h))
     lrn._exported = exported
     return GPOLearnerState(params, opt, key, {k_: lead(v) for k_, v in lrn.env_state.items()}, ts, dones, hs)
@@ -356,7 +356,7 @@ def _adopt(lrn: MagpoLearner, state: GPOLearnerState) -> None:
     for name, src in (("encoder", sh.encoder), ("decoder_self", sh.decoder_self_retn), ("decoder_cross", sh.decoder_cross_retn)):
         ex = exported.get("sable/" + name)
         if (ex is None or src.data_ptr() != ex.data_ptr()) and src.data_ptr() != lrn.hs[name].data_ptr():
-            lrn.hs[name].copy_(src.reshape(U * E, 64, 64).to(torch.float32))
+            lrn.hs[name].copy_(src.reshape(U * E, *lrn.net.state_shape).to(torch.float32))
     take(lrn.policy_h, state.hstates.policy_hidden_state)
 
 
@@ -417,7 +417,8 @@ def learner_setup(env: CoordSumVec, keys: Tuple[Any, Any, Any], config: Config, 
         comm.attach(lrn)
     # parameters: flax's initialisers from the two net keys (rec_magpo.py:596-606) — per-parameter keys folded from the module path,
     # jax.random.normal / truncated_normal draws from the library's threefry kernels, Householder QR for the orthogonal ones
-    lrn.set_params(minit.flax_init_guider(np.asarray(net_key, np.uint32), env.num_agents, env.obs_dim, env.action_dim, lrn.dev),
+    lrn.set_params(minit.flax_init_guider(np.asarray(net_key, np.uint32), env.num_agents, env.obs_dim, env.action_dim, lrn.dev,
+                                          lrn.net.embed_dim, lrn.net.n_head, lrn.net.n_block),
                    minit.flax_init_actor(np.asarray(actor_net_key, np.uint32), env.obs_dim, env.action_dim, lrn.dev))
     U, E = lrn.sys.update_batch_size, lrn.sys.num_envs
     # key, *env_keys = split(key, Nd*U*E + 1); reset_key = split(key)[1] is the step key of every device and slot (:642-673)

@@ -79,7 +79,8 @@ def learner_setup(env, keys: Tuple[Any, Any], config: Config, device=None, allre
                        net=rm._network_config(config, env))
     if comm is not None:
         comm.attach(lrn)
-    lrn.set_params(minit.flax_init_guider(np.asarray(net_key, np.uint32), env.num_agents, env.obs_dim, env.action_dim, lrn.dev),
+    lrn.set_params(minit.flax_init_guider(np.asarray(net_key, np.uint32), env.num_agents, env.obs_dim, env.action_dim, lrn.dev,
+                                          lrn.net.embed_dim, lrn.net.n_head, lrn.net.n_block),
                    minit.init_actor(env.obs_dim, env.action_dim, 0))  # the learner buffers exist but are never touched
     U, E = sysc.update_batch_size, sysc.num_envs
     allk = minit.split(np.asarray(key, np.uint32), world_size * U * E + 1, lrn.dev)

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def make_case(seed, U, Ns, T, A, d, a, mask_p=0.85):
+def make_case(seed, U, Ns, T, A, d, a, mask_p=0.85, shape=(64, 1, 1)):
     """Random minibatch in the oracle's layout [N, T*A, ...] for U slots of Ns envs each."""
     rng = np.random.default_rng(seed)
     N, C_ = U * Ns, T * A
@@ -33,7 +33,8 @@ def make_case(seed, U, Ns, T, A, d, a, mask_p=0.85):
                 log_prob=(-np.abs(rng.standard_normal((N, C_))) - 1.0).astype(np.float32),
                 adv=rng.standard_normal((N, C_)).astype(np.float32), targets=rng.standard_normal((N, C_)).astype(np.float32),
                 policy_h0=(rng.standard_normal((N, A, 128)) * 0.3).astype(np.float32),
-                prev_hstates=tuple((rng.standard_normal((N, 1, 1, 64, 64)) * 0.05).astype(np.float32) for _ in range(3)))
+                prev_hstates=tuple((rng.standard_normal((N, shape[1], shape[2], shape[0] // shape[1], shape[0] // shape[1])) * 0.05).astype(np.float32)
+                                   for _ in range(3)))
 
 
 def device_minibatch(mb, T, A, dev):
@@ -44,21 +45,21 @@ def device_minibatch(mb, T, A, dev):
              action=dt(to_time_major(mb["action"], T, A), dev), value=dt(to_time_major(mb["value"], T, A), dev),
              log_prob=dt(to_time_major(mb["log_prob"], T, A), dev), advantages=dt(to_time_major(mb["adv"], T, A), dev),
              targets=dt(to_time_major(mb["targets"], T, A), dev), policy_h0=dt(mb["policy_h0"], dev))
-    hs = {k: dt(h.reshape(N, 64, 64), dev) for k, h in zip(("encoder", "decoder_self", "decoder_cross"), mb["prev_hstates"])}
+    hs = {k: dt(h, dev) for k, h in zip(("encoder", "decoder_self", "decoder_cross"), mb["prev_hstates"])}
     s = L.struct_of(L.Minibatch, **t)
     s.sable_h0 = L.struct_of(L.SableHState, **hs)
     s.T, s.N = T, N
     return s, (t, hs)
 
 
-def setup_nets(A, d, a, dev, ffn_zero=False, seed=0):
-    cfg = onets.NetCfg(A, d, a)
+def setup_nets(A, d, a, dev, ffn_zero=False, seed=0, shape=(64, 1, 1)):
+    cfg = onets.NetCfg(A, d, a, embed_dim=shape[0], n_head=shape[1], n_block=shape[2])
     gp, ap = onets.init_guider_params(cfg, seed, ffn_zero=ffn_zero), onets.init_actor_params(cfg, seed + 1)
     rng = np.random.default_rng(seed + 7)
     # move every tensor off its special init value (ones / zeros) so that all gradient paths are exercised
     gp = {k: (v + 0.05 * rng.standard_normal(v.shape)).astype(np.float32) for k, v in gp.items()}
     ap = {k: (v + 0.05 * rng.standard_normal(v.shape)).astype(np.float32) for k, v in ap.items()}
-    net = NetworkConfig(A, d, a, 100)
+    net = NetworkConfig(A, d, a, 100, embed_dim=shape[0], n_head=shape[1], n_block=shape[2])
     gt, ng = param_table(net, 0)
     at, na = param_table(net, 1)
     gflat, aflat = torch.zeros(ng, device=dev), torch.zeros(na, device=dev)
@@ -133,10 +134,10 @@ def test_guider_and_actor_forward(dev, A, d, a, T, N):
 # against the fp64 oracle there (tools/diag_grads.py), so that case is held to 2e-3; well-conditioned cases sit at ~5e-6.
 @pytest.mark.parametrize("A,d,a,T,Ns,U,tol", [(3, 4, 10, 12, 5, 2, 2e-4), (4, 75, 5, 6, 3, 1, 2e-4), (3, 4, 10, 9, 50, 2, 2e-3),
                                               (3, 4, 10, 9, 100, 2, 2e-4), (2, 14, 6, 7, 40, 1, 2e-4)])
-def test_minibatch_grads(dev, A, d, a, T, Ns, U, tol):
-    cfg, net, gp, ap, (gt, ng, gflat), (at, na, aflat) = setup_nets(A, d, a, dev)
+def test_minibatch_grads(dev, A, d, a, T, Ns, U, tol, shape=(64, 1, 1)):
+    cfg, net, gp, ap, (gt, ng, gflat), (at, na, aflat) = setup_nets(A, d, a, dev, shape=shape)
     sysc = olr.SysCfg(num_envs=Ns, update_batch_size=U, rollout_length=T, num_minibatches=1)
-    mb = make_case(2, U, Ns, T, A, d, a)
+    mb = make_case(2, U, Ns, T, A, d, a, shape=shape)
     N = U * Ns
     # oracle: per-slot value_and_grad, then the mean over slots (pmean over "batch")
     gsum = asum = None

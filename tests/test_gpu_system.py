@@ -170,7 +170,8 @@ def test_network_config_is_read_from_the_config(dev):
     cfg, env, (learn, net, state) = _setup(dev, extra=["network.memory_config.decay_scaling_factor=0.5",
                                                         "network.memory_config.timestep_positional_encoding=False"])
     assert abs(net.lrn.net.decay_scaling_factor - 0.5) < 1e-9 and net.lrn.net.timestep_pe is False
-    for bad in (["network.net_config.n_block=2"], ["network.net_config.embed_dim=128"], ["network.net_config.n_head=2"],
+    for bad in (["network.net_config.n_block=4"], ["network.net_config.embed_dim=96"], ["network.net_config.n_head=3"],
+                ["network.net_config.embed_dim=32", "network.net_config.n_head=4", "network.net_config.n_block=1", "network.hidden_state_dim=64"],
                 ["network.hidden_state_dim=64"], ["network.actor_network.pre_torso.layer_sizes=[64,64]"], ["system.add_agent_id=False"]):
         with pytest.raises(NotImplementedError):
             _setup(dev, extra=bad)
