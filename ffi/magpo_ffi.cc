@@ -190,6 +190,23 @@ ffi::Error PrngGumbel(cudaStream_t s, Args a, Rets r, int64_t n) {
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(magpo_ffi_prng_gumbel, PrngGumbel, ffi::Ffi::Bind() STREAM_ARGS_RETS.Attr<int64_t>("n"));
 
+// jax.random.normal / truncated_normal(key, (n,)) — the parameter initialisers' draws. operands: key; results: out f32[n]
+ffi::Error PrngNormal(cudaStream_t s, Args a, Rets r, int64_t n) {
+  Unpack u(a, r, s);
+  const uint32_t* key = u.in<uint32_t>();
+  float* out = u.out<float>();
+  return u.ok ? status(magpo_prng_normal(s, key, n, out), "magpo_prng_normal") : u.bad();
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(magpo_ffi_prng_normal, PrngNormal, ffi::Ffi::Bind() STREAM_ARGS_RETS.Attr<int64_t>("n"));
+ffi::Error PrngTruncatedNormal(cudaStream_t s, Args a, Rets r, int64_t n, float lower, float upper) {
+  Unpack u(a, r, s);
+  const uint32_t* key = u.in<uint32_t>();
+  float* out = u.out<float>();
+  return u.ok ? status(magpo_prng_truncated_normal(s, key, n, lower, upper, out), "magpo_prng_truncated_normal") : u.bad();
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(magpo_ffi_prng_truncated_normal, PrngTruncatedNormal,
+                              ffi::Ffi::Bind() STREAM_ARGS_RETS.Attr<int64_t>("n").Attr<float>("lower").Attr<float>("upper"));
+
 // operands: key; results: out i32[n], scratch u32[2n]
 ffi::Error PrngPermutation(cudaStream_t s, Args a, Rets r, int32_t n) {
   Unpack u(a, r, s);

@@ -210,7 +210,7 @@ def test_ffi_shim_declares_a_handler_for_every_entry_point_and_compiles():
     host_only = {"magpo_version", "magpo_last_cuda_error", "magpo_context_create", "magpo_context_destroy", "magpo_context_set_comm",
                  "magpo_param_count", "magpo_param_num_tensors", "magpo_param_tensor", "magpo_rware_num_shelves",
                  "magpo_rollout_workspace_bytes", "magpo_update_workspace_bytes", "magpo_comm_available", "magpo_comm_version",
-                 "magpo_comm_unique_id", "magpo_comm_init", "magpo_comm_destroy", "magpo_comm_allreduce_max",
+                 "magpo_comm_unique_id", "magpo_comm_init", "magpo_comm_destroy", "magpo_comm_allreduce_max", "magpo_prng_fold_in_host",
                  "magpo_clip_adam"}  # magpo_clip_adam is magpo_clip_adam_sched with decay_period 0: one handler serves both
     called = set(re.findall(r"\b(magpo_\w+)\(", shim))
     missing = sorted(n for n in declared - host_only if n not in called)
