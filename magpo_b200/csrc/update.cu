@@ -149,16 +149,19 @@ struct UpdateWs {
     const int64_t Rs = (int64_t)N * A, R = Rs * T;
     const NetShape shape = NetShape::of(net);
     gws = nullptr; gws_bytes = 0;
-    at.plan(ar, a);
     const int64_t n_a = ActorP::bind(nullptr, d, a).total;
-    a_hi = ar.get<float>((size_t)n_a); a_lo = ar.get<float>((size_t)n_a);
-    aa.plan(ar, R, Rs, a, with_backward);
-    if (shape.is_default()) {
+    if (shape.is_default()) {  // (the forward-only and the backward plan agree on every offset up to the backward-only buffers)
       gt.plan(ar, d);
+      at.plan(ar, a);
       const int64_t n_g = GuiderP::bind(nullptr, d, a).total;
       g_hi = ar.get<float>((size_t)n_g); g_lo = ar.get<float>((size_t)n_g);
+      a_hi = ar.get<float>((size_t)n_a); a_lo = ar.get<float>((size_t)n_a);
       sa.plan(ar, R, (int64_t)T * N, d, with_backward);
+      aa.plan(ar, R, Rs, a, with_backward);
     } else {
+      at.plan(ar, a);
+      a_hi = ar.get<float>((size_t)n_a); a_lo = ar.get<float>((size_t)n_a);
+      aa.plan(ar, R, Rs, a, with_backward);
       g_hi = g_lo = nullptr;
       gws_bytes = sable_g_workspace_bytes(shape, T, N, with_backward);
       gws = ar.get<char>(gws_bytes);

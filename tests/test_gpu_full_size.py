@@ -74,8 +74,9 @@ def test_full_size_determinism_graph_replay_and_invariants(dev):
     a2, b2 = _make(dev, chunk=1024), _make(dev, chunk=1024)
     a2.update_step(); b2.update_step()
     torch.cuda.synchronize()
-    assert torch.equal(a2.guider, b2.guider) or float((a2.guider - b2.guider).abs().max()) <= 1e-7  # atomics: order of float adds
-    assert float((a2.actor - b2.actor).abs().max()) <= 1e-7
+    # cross-CTA fp32 reductions (atomics, TMA reduce-adds) add in a run-dependent order: last bits only
+    assert torch.equal(a2.guider, b2.guider) or float((a2.guider - b2.guider).abs().max()) <= 1e-6
+    assert float((a2.actor - b2.actor).abs().max()) <= 1e-6
     assert torch.equal(a2.key, b2.key)
     del a2, b2
     torch.cuda.empty_cache()
