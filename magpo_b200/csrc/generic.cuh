@@ -37,10 +37,11 @@ inline bool net_shape_ok(const MagpoNetCfg* n) {
 
 // decay kappa of head h (retention.py:231-234): (1 - exp(linspace(log(1/32), log(1/512), n_head)[h])) * decay_scaling_factor, float32
 inline float head_kappa(const MagpoNetCfg* n, int h) {
-  const double lo = (double)logf(1.0f / 32.0f), hi = (double)logf(1.0f / 512.0f);
-  double x = lo;
-  if (n->n_head > 1) x = (h == n->n_head - 1) ? hi : lo + (double)h * ((hi - lo) / (double)(n->n_head - 1));
-  return (1.0f - expf((float)x)) * n->decay_scaling_factor;
+  // jnp.linspace in float32: start + i * ((stop - start) / (num - 1)), the last point set to stop
+  const float lo = logf(1.0f / 32.0f), hi = logf(1.0f / 512.0f);
+  float x = lo;
+  if (n->n_head > 1) x = (h == n->n_head - 1) ? hi : lo + (float)h * ((hi - lo) / (float)(n->n_head - 1));
+  return (1.0f - expf(x)) * n->decay_scaling_factor;
 }
 
 // Flat parameter layout of the general guider: the default layout of params.cuh with the per-block groups repeated n_block times
