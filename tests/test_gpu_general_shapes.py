@@ -60,7 +60,7 @@ def test_general_guider_forward(dev, shape):
 @pytest.mark.parametrize("shape,Ns", [((128, 2, 3), 4), ((32, 4, 2), 6), ((64, 2, 2), 5), ((64, 1, 2), 40), ((128, 4, 1), 40)])
 def test_general_minibatch_grads(dev, shape, Ns):
     """every gradient tensor (per block, per head) against the fp64 oracle; Ns = 40: >= 256 token rows, the tensor-core GEMMs engage"""
-    tgn.test_minibatch_grads(dev, 3, 9, 7, 8, Ns, 2, 5e-3 if _ill_conditioned(shape) else 2e-4, shape=shape)
+    tgn.test_minibatch_grads(dev, 3, 9, 7, 8, Ns, 2, 5e-3 if _ill_conditioned(shape) else 2e-4, shape=shape, yardstick=_ill_conditioned(shape))
 
 
 def _build(dev, kind, shape, E, U, T, P, M, seed=42):

@@ -134,17 +134,23 @@ def test_guider_and_actor_forward(dev, A, d, a, T, N):
 # against the fp64 oracle there (tools/diag_grads.py), so that case is held to 2e-3; well-conditioned cases sit at ~5e-6.
 @pytest.mark.parametrize("A,d,a,T,Ns,U,tol", [(3, 4, 10, 12, 5, 2, 2e-4), (4, 75, 5, 6, 3, 1, 2e-4), (3, 4, 10, 9, 50, 2, 2e-3),
                                               (3, 4, 10, 9, 100, 2, 2e-4), (2, 14, 6, 7, 40, 1, 2e-4)])
-def test_minibatch_grads(dev, A, d, a, T, Ns, U, tol, shape=(64, 1, 1)):
+def test_minibatch_grads(dev, A, d, a, T, Ns, U, tol, shape=(64, 1, 1), yardstick=False):
+    """yardstick: also run the oracle in fp32 and allow the CUDA path twice the fp32 oracle's own worst deviation from the fp64 oracle
+    (ill-conditioned shapes, where ANY fp32 implementation is far from fp64)"""
     cfg, net, gp, ap, (gt, ng, gflat), (at, na, aflat) = setup_nets(A, d, a, dev, shape=shape)
     sysc = olr.SysCfg(num_envs=Ns, update_batch_size=U, rollout_length=T, num_minibatches=1)
     mb = make_case(2, U, Ns, T, A, d, a, shape=shape)
     N = U * Ns
     # oracle: per-slot value_and_grad, then the mean over slots (pmean over "batch")
-    gsum = asum = None
+    gsum = asum = g32 = None
     infos = []
     for u in range(U):
         sl = slice(u * Ns, (u + 1) * Ns)
         part = {k: (tuple(h[sl] for h in v) if k == "prev_hstates" else v[sl]) for k, v in mb.items()}
+        if yardstick:
+            gg, ga, _, _ = olr.minibatch_losses_and_grads(gp, ap, part, cfg, sysc, dtype=torch.float32)
+            gg.update(ga)
+            g32 = gg if g32 is None else {k: g32[k] + gg[k] for k in gg}
         # fp64 oracle: the comparison then measures the CUDA path's own rounding, not the sum of two fp32 roundings
         gg, ga, info, _ = olr.minibatch_losses_and_grads(gp, ap, part, cfg, sysc, dtype=torch.float64)
         gsum = gg if gsum is None else {k: gsum[k] + gg[k] for k in gg}
@@ -185,4 +191,11 @@ def test_minibatch_grads(dev, A, d, a, T, Ns, U, tol, shape=(64, 1, 1)):
     print("\n".join(lines))
     for k, v in loss_pairs:
         assert abs(v - info_ref[k]) <= 1e-4 * max(1.0, abs(info_ref[k])), (k, v, info_ref[k])
-    assert worst < tol, worst
+    if yardstick:
+        ref_all = dict(g_ref)
+        ref_all.update(a_ref)
+        worst32 = max(rel_err(g32[k] / U, ref_all[k]) for k in ref_all)
+        print(f"worst deviation from the fp64 oracle: cuda {worst:.3e}, fp32 oracle {worst32:.3e}")
+        assert worst < max(tol, 2 * worst32), (worst, worst32)
+    else:
+        assert worst < tol, worst
