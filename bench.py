@@ -41,7 +41,7 @@ WORKLOADS = {
 }
 METRIC, UNIT = "end_to_end_training_agent_env_steps_per_sec", "agent-steps/s"
 PROF_CATS = ["gemm_nn", "gemm_tn", "colsum", "rowops", "retention_fwd", "retention_bwd", "gru_pointwise", "loss", "pack",
-             "optim", "env_step", "sample", "gae", "misc", "gemm_rollout"]
+             "optim", "env_step", "sample", "gae", "misc", "gemm_rollout", "chain"]
 
 
 def parse():

@@ -32,7 +32,7 @@ void note_launch();
 // roofline numbers and the per-kernel breakdown. Off by default; zero cost when off.
 enum ProfCat {
   PROF_GEMM_NN = 0, PROF_GEMM_TN, PROF_COLSUM, PROF_ROWOPS, PROF_RET_FWD, PROF_RET_BWD, PROF_GRU, PROF_LOSS, PROF_PACK,
-  PROF_OPTIM, PROF_ENV, PROF_SAMPLE, PROF_GAE, PROF_MISC, PROF_GEMM_SMALL /* M < 64 Ki rows: the rollout */, PROF_NUM
+  PROF_OPTIM, PROF_ENV, PROF_SAMPLE, PROF_GAE, PROF_MISC, PROF_GEMM_SMALL /* M < 64 Ki rows: the rollout */, PROF_CHAIN /* fused row chains */, PROF_NUM
 };
 struct ProfScope {
   int idx;
@@ -91,7 +91,8 @@ int comm_allreduce(MagpoComm* c, cudaStream_t s, float* buf, int64_t n, int op);
 // true exactly once per (device, id): guards cudaFuncSetAttribute, which is per device
 bool once_per_device(int id);
 enum { ONCE_GEMM_TC = 0, ONCE_GEMM_TN, ONCE_GRU_FWD, ONCE_GRU_BWD, ONCE_RET_FWD, ONCE_RET_BWD, ONCE_SABLE_STEP_1 /* 8 ids: (A - 1) * 2 + (EPW - 1) */,
-       ONCE_SABLE_STEP_LAST = ONCE_SABLE_STEP_1 + 7, ONCE_NUM };
+       ONCE_SABLE_STEP_LAST = ONCE_SABLE_STEP_1 + 7, ONCE_CHAIN_GATE, ONCE_CHAIN_GATE_FFN, ONCE_CHAIN_TAIL, ONCE_CHAIN_BWD_A, ONCE_CHAIN_BWD_B,
+       ONCE_NUM };
 
 constexpr int kNumSMs = 148;
 constexpr float kF32Min = -3.4028234663852886e+38f;  // jnp.finfo(float32).min

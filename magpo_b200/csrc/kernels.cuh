@@ -40,6 +40,20 @@ int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx,
 bool tc_make_map(void* tensor_map, const float* ptr, int64_t rows, int cols, int ld, int box_rows);
 int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW,
             int ldw);
+// ---- chain_fwd.cu: fused row chains of the guider's training forward (persistent tcgen05 kernels, A operands in tensor memory)
+void chain_set_enabled(bool on);
+bool chain_supported(int64_t R);
+// gated = swish(g) * GroupNorm(ret); o = gated W1; y = RMSNorm(o + res) * ln_s; ype = y + pe[step] (y / ype optional);
+// with W2T: gl = y W2 [R,128]; hmid = swish(gl[:, :64]) * gl[:, 64:].  W1T [64,64], W2T [128,64]: transposed weights with registered images
+int chain_gate_fwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float* ret, const float* res, const float* gn_s,
+                   const float* gn_b, const float* ln_s, const float* pe, const int32_t* step, int max_step, const float* W1T,
+                   const float* W2T, float* gated, float* o, float* y, float* ype, float* gl, float* hmid);
+// f = hmid W1; x = RMSNorm(f + res) * ln_s; xpe = x + pe[step] (optional); q = xpe Wq (optional, row stride ldq); zh = x Wh + h_bias;
+// out[R,nout] = RMSNorm(gelu(zh)) * h2_s @ W3 + b3
+int chain_tail_fwd(cudaStream_t s, int64_t R, const float* hmid, const float* res, const float* ln_s, const float* pe,
+                   const int32_t* step, int max_step, const float* W1T, const float* WqT, int ldwq, const float* WhT, const float* h_bias,
+                   const float* h2_s, const float* W3, const float* b3, int nout, float* f, float* x, float* xpe, float* q, int ldq,
+                   float* zh, float* out);
 // ---- gru_scan.cu: persistent tcgen05 GRU scans over T steps (one CTA per 128 rows, W_h streamed through a TMA ring)
 int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const float* WhT_hi, const float* WhT_lo, const float* bhn,
                  const uint8_t* done, float* rzn, float* ghn, float* Y, float* HU);

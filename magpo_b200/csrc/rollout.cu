@@ -16,7 +16,8 @@ namespace magpo {
 // sable.cu
 int sable_encoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int A, int d, int max_step,
                           const float* agents_view, const int32_t* step, const uint8_t* done, const float* H0,
-                          float kappa, const float* pe, const SableActs& w, float* value, float* Hsave, float* Hout);
+                          float kappa, const float* pe, const SableActs& w, float* value, float* Hsave, float* Hout, bool chain = false,
+                          float* dec_q = nullptr);
 int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int ret_A, int embed_A, int a,
                           int max_step, const int32_t* action, const float* x_rep, const float* x_rep_pe,
                           const int32_t* step, const uint8_t* done, const float* Hself0, const float* Hcross0,

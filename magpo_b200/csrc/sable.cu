@@ -75,7 +75,7 @@ void SableActs::plan(Arena& ar, int64_t R, int64_t TN, int d, bool with_backward
 // Encoder over R = T*N*A rows (Encoder.__call__/recurrent, sable_network.py:121-156).
 int sable_encoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int A, int d, int max_step,
                           const float* agents_view, const int32_t* step, const uint8_t* done, const float* H0,
-                          float kappa, const float* pe, const SableActs& w, float* value, float* Hsave, float* Hout) {
+                          float kappa, const float* pe, const SableActs& w, float* value, float* Hsave, float* Hout, bool chain, float* dec_q) {
   const int64_t R = (int64_t)T * N * A;
   if (obs_embed_ok(d)) {
     MAGPO_TRY(obs_embed_fwd(s, R, d, agents_view, p.obs_scale, p.Wobs, p.ln, pe, step, max_step, w.on, w.z0, w.xin, w.kqv));
@@ -87,6 +87,15 @@ int sable_encoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
   MAGPO_TRY(gemm_nn(s, R, 4 * kD, kD, w.kqv, kD, wref(p.qkvg, 4 * kD, pt ? pt->qkvgT : nullptr, kD), nullptr, w.qkvg, 4 * kD, 0));
   MAGPO_TRY(retention_fwd(s, T, N, A, kappa, false, w.qkvg, w.qkvg + kD, w.qkvg + 2 * kD, 4 * kD, H0, done, w.ret,
                           Hsave, Hout));
+  if (chain && pt && chain_supported(R)) {
+    // the two row chains after the retention, one persistent kernel each (chain_fwd.cu); dec_q: the decoder's cross-retention query
+    MAGPO_TRY(chain_gate_fwd(s, R, w.qkvg + 3 * kD, 4 * kD, w.ret, w.xin, p.gn_s, p.gn_b, p.ln1, nullptr, nullptr, 0, pt->woT, pt->ffn_glT,
+                             w.gated, w.o, w.x1, nullptr, w.gl, w.hmid));
+    MAGPO_TRY(chain_tail_fwd(s, R, w.hmid, w.x1, p.ln2, pe, step, max_step, pt->ffn_outT, dec_q ? pt->qkvg2T : nullptr, kD, pt->h0T, p.h0_b,
+                             p.h2_s, p.h3_w, p.h3_b, 1, w.f, w.x, w.xpe, dec_q, 4 * kD, w.zh, value));
+    return MAGPO_OK;
+  }
+  if (dec_q) return MAGPO_ERR_ARG;
   MAGPO_TRY(gn_gate_fwd(s, R, w.qkvg + 3 * kD, 4 * kD, w.ret, p.gn_s, p.gn_b, w.gated));
   MAGPO_TRY(gemm_nn(s, R, kD, kD, w.gated, kD, wref(p.wo, kD, pt ? pt->woT : nullptr, kD), nullptr, w.o, kD, 0));
   MAGPO_TRY(act_rms_fwd(s, R, w.o, w.xin, p.ln1, 0, nullptr, nullptr, 0, w.x1, nullptr));
@@ -104,27 +113,40 @@ int sable_encoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
 // `ret_A`: tokens per timestep seen by the retention scans. x_rep / x_rep_pe: encoder output (+PE) rows.
 // phase 1: the part that does not depend on the encoder (token embedding, self retention, the key / value / gate projections of the
 // cross retention); phase 2: the rest; phase 0: both.
-static int decoder_forward_phase(int phase, cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int ret_A, int embed_A, int a,
+static int decoder_forward_phase(int phase, bool q_done, cudaStream_t s, const GuiderP& p, const GuiderT* pt, int T, int N, int ret_A, int embed_A, int a,
                                  int max_step, const int32_t* action, const float* x_rep, const float* x_rep_pe,
                                  const int32_t* step, const uint8_t* done, const float* Hself0, const float* Hcross0,
                                  float kappa, const float* pe, const SableActs& w, float* logits, float* Hs_self,
                                  float* Hs_cross, float* Hself_out, float* Hcross_out) {
   const int64_t R = (int64_t)T * N * ret_A;
+  const bool chained = pt && embed_A > 0 && !Hself_out && chain_supported(R);  // training forward only: the rollout keeps its kernels
   if (phase != 2) {
     MAGPO_TRY(embed_fwd(s, R, embed_A, action, p.Wa, p.dln, pe, step, max_step, w.xD, w.xpeD));
     MAGPO_TRY(gemm_nn(s, R, 4 * kD, kD, w.xpeD, kD, wref(p.qkvg1, 4 * kD, pt ? pt->qkvg1T : nullptr, kD), nullptr, w.qkvg1, 4 * kD, 0));
     MAGPO_TRY(retention_fwd(s, T, N, ret_A, kappa, true, w.qkvg1, w.qkvg1 + kD, w.qkvg1 + 2 * kD, 4 * kD, Hself0, done,
                             w.ret1, Hs_self, Hself_out));
-    MAGPO_TRY(gn_gate_fwd(s, R, w.qkvg1 + 3 * kD, 4 * kD, w.ret1, p.gn1_s, p.gn1_b, w.gated1));
-    MAGPO_TRY(gemm_nn(s, R, kD, kD, w.gated1, kD, wref(p.wo1, kD, pt ? pt->wo1T : nullptr, kD), nullptr, w.o1, kD, 0));
-    MAGPO_TRY(act_rms_fwd(s, R, w.o1, w.xD, p.dln1, 0, pe, step, max_step, nullptr, w.rpe));
+    if (chained) {
+      MAGPO_TRY(chain_gate_fwd(s, R, w.qkvg1 + 3 * kD, 4 * kD, w.ret1, w.xD, p.gn1_s, p.gn1_b, p.dln1, pe, step, max_step, pt->wo1T, nullptr,
+                               w.gated1, w.o1, nullptr, w.rpe, nullptr, nullptr));
+    } else {
+      MAGPO_TRY(gn_gate_fwd(s, R, w.qkvg1 + 3 * kD, 4 * kD, w.ret1, p.gn1_s, p.gn1_b, w.gated1));
+      MAGPO_TRY(gemm_nn(s, R, kD, kD, w.gated1, kD, wref(p.wo1, kD, pt ? pt->wo1T : nullptr, kD), nullptr, w.o1, kD, 0));
+      MAGPO_TRY(act_rms_fwd(s, R, w.o1, w.xD, p.dln1, 0, pe, step, max_step, nullptr, w.rpe));
+    }
     // cross retention: key = value = r (+PE), query = obs_rep (+PE); gate input is the PE-added key
     MAGPO_TRY(gemm_nn(s, R, 3 * kD, kD, w.rpe, kD, wref(p.qkvg2 + kD, 4 * kD, pt ? pt->qkvg2T + kD * kD : nullptr, kD), nullptr, w.qkvg2 + kD, 4 * kD, 0));
   }
   if (phase == 1) return MAGPO_OK;
-  MAGPO_TRY(gemm_nn(s, R, kD, kD, x_rep_pe, kD, wref(p.qkvg2, 4 * kD, pt ? pt->qkvg2T : nullptr, kD), nullptr, w.qkvg2, 4 * kD, 0));
+  if (!q_done) MAGPO_TRY(gemm_nn(s, R, kD, kD, x_rep_pe, kD, wref(p.qkvg2, 4 * kD, pt ? pt->qkvg2T : nullptr, kD), nullptr, w.qkvg2, 4 * kD, 0));
   MAGPO_TRY(retention_fwd(s, T, N, ret_A, kappa, true, w.qkvg2, w.qkvg2 + kD, w.qkvg2 + 2 * kD, 4 * kD, Hcross0, done,
                           w.ret2, Hs_cross, Hcross_out));
+  if (chained) {
+    MAGPO_TRY(chain_gate_fwd(s, R, w.qkvg2 + 3 * kD, 4 * kD, w.ret2, x_rep, p.gn2_s, p.gn2_b, p.dln2, nullptr, nullptr, 0, pt->wo2T, pt->dffn_glT,
+                             w.gated2, w.o2, w.y, nullptr, w.glD, w.hmidD));
+    MAGPO_TRY(chain_tail_fwd(s, R, w.hmidD, w.y, p.dln3, nullptr, nullptr, 0, pt->dffn_outT, nullptr, 0, pt->dh0T, p.dh0_b, p.dh2_s, p.dh3_w,
+                             p.dh3_b, a, w.fD, w.xd, nullptr, nullptr, 0, w.zhD, logits));
+    return MAGPO_OK;
+  }
   MAGPO_TRY(gn_gate_fwd(s, R, w.qkvg2 + 3 * kD, 4 * kD, w.ret2, p.gn2_s, p.gn2_b, w.gated2));
   MAGPO_TRY(gemm_nn(s, R, kD, kD, w.gated2, kD, wref(p.wo2, kD, pt ? pt->wo2T : nullptr, kD), nullptr, w.o2, kD, 0));
   MAGPO_TRY(act_rms_fwd(s, R, w.o2, x_rep, p.dln2, 0, nullptr, nullptr, 0, w.y, nullptr));
@@ -142,7 +164,7 @@ int sable_decoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
                           const int32_t* step, const uint8_t* done, const float* Hself0, const float* Hcross0,
                           float kappa, const float* pe, const SableActs& w, float* logits, float* Hs_self,
                           float* Hs_cross, float* Hself_out, float* Hcross_out) {
-  return decoder_forward_phase(0, s, p, pt, T, N, ret_A, embed_A, a, max_step, action, x_rep, x_rep_pe, step, done, Hself0, Hcross0,
+  return decoder_forward_phase(0, false, s, p, pt, T, N, ret_A, embed_A, a, max_step, action, x_rep, x_rep_pe, step, done, Hself0, Hcross0,
                                kappa, pe, w, logits, Hs_self, Hs_cross, Hself_out, Hcross_out);
 }
 
@@ -162,16 +184,18 @@ int sable_train_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, con
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_dec.fork, s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(g_dec.s, g_dec.fork, 0));
-    MAGPO_TRY(decoder_forward_phase(1, g_dec.s, p, pt, b.T, b.N, b.A, b.A, b.a, b.max_step, b.action, w.x, w.xpe, b.step_count,
+    MAGPO_TRY(decoder_forward_phase(1, false, g_dec.s, p, pt, b.T, b.N, b.A, b.A, b.a, b.max_step, b.action, w.x, w.xpe, b.step_count,
                                     b.done, b.h_self, b.h_cross, b.kappa, b.pe, w, logits, hs_self, hs_cross, nullptr, nullptr));
   }
+  // with the fused chains the encoder's tail kernel also projects the decoder's cross-retention query (q = (x + PE) W_q of retn2)
+  const bool fuse_q = pt && chain_supported((int64_t)b.T * b.N * b.A);
   MAGPO_TRY(sable_encoder_forward(s, p, pt, b.T, b.N, b.A, b.d, b.max_step, b.agents_view, b.step_count, b.done, b.h_enc,
-                                  b.kappa, b.pe, w, value, save_states ? w.Hs_enc : nullptr, nullptr));
+                                  b.kappa, b.pe, w, value, save_states ? w.Hs_enc : nullptr, nullptr, true, fuse_q ? w.qkvg2 : nullptr));
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_dec.join, g_dec.s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_dec.join, 0));
   }
-  MAGPO_TRY(decoder_forward_phase(overlap ? 2 : 0, s, p, pt, b.T, b.N, b.A, b.A, b.a, b.max_step, b.action, w.x, w.xpe, b.step_count,
+  MAGPO_TRY(decoder_forward_phase(overlap ? 2 : 0, fuse_q, s, p, pt, b.T, b.N, b.A, b.A, b.a, b.max_step, b.action, w.x, w.xpe, b.step_count,
                                   b.done, b.h_self, b.h_cross, b.kappa, b.pe, w, logits, hs_self, hs_cross, nullptr, nullptr));
   return MAGPO_OK;
 }

@@ -199,3 +199,51 @@ def test_minibatch_grads(dev, A, d, a, T, Ns, U, tol, shape=(64, 1, 1), yardstic
         assert worst < max(tol, 2 * worst32), (worst, worst32)
     else:
         assert worst < tol, worst
+
+
+CHAIN_BUFFERS = ("gated", "o", "x1", "hmid", "f", "x", "xpe", "zh", "gated1", "o1", "rpe", "gated2", "o2", "y", "hmidD", "fD", "xd", "zhD")
+
+
+@pytest.mark.parametrize("A,d,a,T,N", [(2, 14, 6, 16, 64), (3, 4, 10, 7, 41), (4, 75, 5, 9, 8), (2, 14, 6, 16, 1500)])
+def test_chain_kernels_match_layer_path(dev, A, d, a, T, N):
+    """The fused row-chain kernels of the update (csrc/chain_fwd.cu, chain_bwd.cu: tcgen05 with the A operands in tensor memory) against the
+    layer-by-layer kernels they replace: every saved activation of the forward, the values, the logits and the whole gradient, on full
+    and ragged (R % 128 != 0) tile counts."""
+    cfg, net, gp, ap, (gt, ng, gflat), (at, na, aflat) = setup_nets(A, d, a, dev)
+    mb = make_case(3, 1, N, T, A, d, a)
+    mbs, keep = device_minibatch(mb, T, A, dev)
+    adv = mb["adv"].reshape(1, -1)
+    stats = dt(np.stack([adv.mean(1), adv.std(1)], 1).astype(np.float32), dev)
+    env_slot = dt(np.zeros(N, np.int32), dev)
+    from magpo_b200.learner import SystemConfig
+    csys = SystemConfig(num_envs=N, update_batch_size=1, rollout_length=T, num_minibatches=1).c_struct()
+    cnet = net.c_struct()
+    lib = L.lib()
+    got = {}
+    for on in (0, 1):
+        lib.magpo_set_chain_kernels(on)
+        try:
+            ws, nbytes = workspace(net, T, N, dev)
+            grads = torch.zeros(ng + na + 8, device=dev)
+            L.call("magpo_minibatch_grads", L.context(), L.stream_ptr(), C.byref(cnet), C.byref(csys), L.ptr(gflat), L.ptr(aflat), mbs,
+                   L.ptr(env_slot), L.ptr(stats), C.c_float(1.0 / (N * T * A)), L.ptr(grads), 0, L.ptr(ws), C.c_size_t(nbytes))
+            sync()
+            got[on] = {k: ws_buffer(ws, net, T, N, k, (T, N, A, 64)) for k in CHAIN_BUFFERS}
+            for k, w in (("gl", 128), ("glD", 128), ("qkvg2", 256)):
+                got[on][k] = ws_buffer(ws, net, T, N, k, (T, N, A, w))
+            got[on]["value"] = ws_buffer(ws, net, T, N, "value", (T, N, A))
+            got[on]["logits"] = ws_buffer(ws, net, T, N, "lg", (T, N, A, a))
+            gv = param_views(grads[:ng], gt)
+            got[on].update({"grad/" + k: v.cpu().numpy() for k, v in gv.items()})
+        finally:
+            lib.magpo_set_chain_kernels(1)
+    legal = to_time_major(mb["action_mask"], T, A)
+    differs = 0
+    for k in got[0]:
+        a0, a1 = got[0][k], got[1][k]
+        if k == "logits":
+            a0, a1 = a0[legal], a1[legal]
+        e = rel_err(a1, a0)
+        differs += e > 0
+        assert e < (2e-4 if k.startswith("grad/") else 2e-4), (k, e)
+    assert differs > 10, "the fused kernels did not run (results are bit-identical to the layer path)"
