@@ -53,6 +53,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] . B[smem]   (kind::tf32, A-from-TMEM form: lane = row, one column per K element)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -150,12 +162,14 @@ __device__ __forceinline__ void wait_D(RowCtx& c) {
 }
 template <int COL>
 __device__ __forceinline__ void ld_D64(const RowCtx& c, float (&x)[64]) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32_nowait(c.tm + CH_TM_D + COL, v0);
+  tmem_ld32_nowait(c.tm + CH_TM_D + COL + 32, v1);
+  tmem_ld_wait();
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t v[32];
-    tmem_ld32(c.tm + CH_TM_D + COL + 32 * h, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x[32 * h + j] = __uint_as_float(v[j]);
+  for (int j = 0; j < 32; ++j) {
+    x[j] = __uint_as_float(v0[j]);
+    x[32 + j] = __uint_as_float(v1[j]);
   }
 }
 __device__ __forceinline__ void ld_D32(const RowCtx& c, int col, float (&x)[32]) {
@@ -191,18 +205,20 @@ __device__ __forceinline__ void add_D64(const RowCtx& c, float (&x)[64]) {
   }
 }
 
-// this thread's 64-wide row -> columns [col0, col0 + 64) of an output tensor, rows [row0, row0 + 128) (TMA store of the group's buffer)
+// this thread's 64-wide row -> columns [col0, col0 + 64) of an output tensor, rows [row0, row0 + 128). Every warp stages and stores its
+// own 32 rows ([32 x 32 floats] TMA boxes out of the warp's 8 KiB of the group's buffer): no barrier between the warps of a group.
 __device__ __forceinline__ void out_store64(RowCtx& c, const CUtensorMap* tm, int col0, int row0, const float (&x)[64]) {
-  const bool leader = (c.rt == 0);
-  if (leader) bulk_wait_read<0>();  // the store that last used this buffer has finished reading it
-  named_bar_sync(1 + c.group, 128);
-  slot_write<0>(c.obuf, c.rt, x);
-  slot_write<32>(c.obuf + CH_SLOT, c.rt, x);
+  const int wrow = c.rt & ~31;
+  uint8_t* buf = c.obuf + (size_t)wrow * 256;  // 2 x [32 rows x 128 B] per warp
+  if (c.lane == 0) bulk_wait_read<0>();  // the stores that last used this buffer have finished reading it
+  __syncwarp();
+  slot_write<0>(buf, c.lane, x);
+  slot_write<32>(buf + 32 * 128, c.lane, x);
   fence_proxy_async();
-  named_bar_sync(1 + c.group, 128);
-  if (leader) {
-    tma_store_2d(tm, c.obuf, col0, row0);
-    tma_store_2d(tm, c.obuf + CH_SLOT, col0 + 32, row0);
+  __syncwarp();
+  if (c.lane == 0) {
+    tma_store_2d(tm, buf, col0, row0 + wrow);
+    tma_store_2d(tm, buf + 32 * 128, col0 + 32, row0 + wrow);
     bulk_commit();
   }
 }

@@ -153,7 +153,15 @@ __device__ __forceinline__ RowCtx row_ctx(const Carve& c, const ChainCommon& cc,
   return r;
 }
 
-__device__ __forceinline__ float swishf(float x) { return x * sigmoid_precise(x); }
+// The update needs fp32-faithful, not bit-identical, activations (the rollout, whose sampled actions must not move, never runs these
+// kernels): ex2.approx / rcp.approx forms, absolute error ~1e-7, a third of the instructions of expf + IEEE division. A row thread has
+// one warp per scheduler pair to hide latency behind, so the instruction count of the activation is what bounds these kernels.
+__device__ __forceinline__ float swishf(float x) { return x * __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
+  return 0.5f * x * (1.0f + t);
+}
 
 // x <- RMSNorm(x) * scale (scale: 64 floats in shared memory)
 __device__ __forceinline__ void rms64(float (&x)[64], const float* scale) {
@@ -262,7 +270,7 @@ chain_gate_kernel(const __grid_constant__ ChainMaps maps, const GateParams p) {
         out_store64(r, &maps.out[GO_H], 0, row0, x);
       }
     }
-    if (r.rt == 0) bulk_wait_all();
+    if (r.lane == 0) bulk_wait_all();
   }
   chain_teardown(tmem_base);
 }
@@ -337,7 +345,7 @@ chain_tail_kernel(const __grid_constant__ ChainMaps maps, const TailParams p) {
       out_store64(r, &maps.out[TO_ZH], 0, row0, x);
       // ---- head: out = RMSNorm(gelu(zh)) * scale @ W3 + b3
 #pragma unroll
-      for (int j = 0; j < 64; ++j) x[j] = gelu_tanh(x[j]);
+      for (int j = 0; j < 64; ++j) x[j] = gelu_fast(x[j]);
       rms64(x, h2);
       if (row < p.cc.R) {
         for (int jb = 0; jb < NP; jb += 4) {
@@ -361,7 +369,7 @@ chain_tail_kernel(const __grid_constant__ ChainMaps maps, const TailParams p) {
         out_store64(r, &maps.out[TO_Q], 0, row0, x);
       }
     }
-    if (r.rt == 0) bulk_wait_all();
+    if (r.lane == 0) bulk_wait_all();
   }
   chain_teardown(tmem_base);
 }
@@ -373,6 +381,8 @@ bool g_chain_enabled = [] {
 }();
 
 bool act_map(CUtensorMap* tm, const float* ptr, int64_t R, int cols, int ld) { return tc_make_map(tm, ptr, R, cols, ld, 128); }
+// outputs leave per warp: boxes of 32 rows
+bool out_map(CUtensorMap* tm, const float* ptr, int64_t R, int cols, int ld) { return tc_make_map(tm, ptr, R, cols, ld, 32); }
 
 // B operand images of a [N, 64] transposed weight registered with tc_prepare_region
 bool weight_maps(ChainMaps* m, int i, const float* wt, int N, int ld) {
@@ -424,10 +434,10 @@ int chain_gate_fwd(cudaStream_t s, int64_t R, const float* g, int ldg, const flo
   uint32_t smem;
   if (!finish_plan(&p.cc, R, &smem)) return MAGPO_ERR_UNSUPPORTED;
   bool ok = act_map(&m.in[0], ret, R, 64, 64) && act_map(&m.in[1], g, R, 64, ldg) && act_map(&m.in[2], res, R, 64, 64) &&
-            act_map(&m.out[GO_GATED], gated, R, 64, 64) && act_map(&m.out[GO_O], o, R, 64, 64) && weight_maps(&m, 0, W1T, 64, 64);
-  if (y) ok = ok && act_map(&m.out[GO_Y], y, R, 64, 64);
-  if (ype) ok = ok && act_map(&m.out[GO_YPE], ype, R, 64, 64);
-  if (ffn) ok = ok && act_map(&m.out[GO_GL], gl, R, 128, 128) && act_map(&m.out[GO_H], hmid, R, 64, 64) && weight_maps(&m, 1, W2T, 128, 64);
+            out_map(&m.out[GO_GATED], gated, R, 64, 64) && out_map(&m.out[GO_O], o, R, 64, 64) && weight_maps(&m, 0, W1T, 64, 64);
+  if (y) ok = ok && out_map(&m.out[GO_Y], y, R, 64, 64);
+  if (ype) ok = ok && out_map(&m.out[GO_YPE], ype, R, 64, 64);
+  if (ffn) ok = ok && out_map(&m.out[GO_GL], gl, R, 128, 128) && out_map(&m.out[GO_H], hmid, R, 64, 64) && weight_maps(&m, 1, W2T, 128, 64);
   if (!ok) return MAGPO_ERR_ARG;
   p.gn_s = gn_s; p.gn_b = gn_b; p.ln_s = ln_s; p.pe = pe; p.step = step; p.max_step = max_step;
   p.store_y = y != nullptr;
@@ -462,11 +472,11 @@ int chain_tail_fwd(cudaStream_t s, int64_t R, const float* hmid, const float* re
   if (q) add_gemm(&p.cc, 64, 64);  // q
   uint32_t smem;
   if (!finish_plan(&p.cc, R, &smem)) return MAGPO_ERR_UNSUPPORTED;
-  bool ok = act_map(&m.in[0], hmid, R, 64, 64) && act_map(&m.in[1], res, R, 64, 64) && act_map(&m.out[TO_F], f, R, 64, 64) &&
-            act_map(&m.out[TO_X], x, R, 64, 64) && act_map(&m.out[TO_ZH], zh, R, 64, 64) && weight_maps(&m, 0, W1T, 64, 64);
-  if (xpe) ok = ok && act_map(&m.out[TO_XPE], xpe, R, 64, 64);
+  bool ok = act_map(&m.in[0], hmid, R, 64, 64) && act_map(&m.in[1], res, R, 64, 64) && out_map(&m.out[TO_F], f, R, 64, 64) &&
+            out_map(&m.out[TO_X], x, R, 64, 64) && out_map(&m.out[TO_ZH], zh, R, 64, 64) && weight_maps(&m, 0, W1T, 64, 64);
+  if (xpe) ok = ok && out_map(&m.out[TO_XPE], xpe, R, 64, 64);
   ok = ok && weight_maps(&m, 1, WhT, 64, 64);
-  if (q) ok = ok && xpe && act_map(&m.out[TO_Q], q, R, 64, ldq) && weight_maps(&m, 2, WqT, 64, ldwq);
+  if (q) ok = ok && xpe && out_map(&m.out[TO_Q], q, R, 64, ldq) && weight_maps(&m, 2, WqT, 64, ldwq);
   if (!ok) return MAGPO_ERR_ARG;
   p.ln_s = ln_s; p.pe = pe; p.step = step; p.max_step = max_step; p.h_bias = h_bias; p.h2_s = h2_s; p.W3 = W3; p.b3 = b3;
   p.nout = nout; p.with_q = q != nullptr; p.store_xpe = xpe != nullptr; p.out = out;

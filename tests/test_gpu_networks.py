@@ -245,5 +245,5 @@ def test_chain_kernels_match_layer_path(dev, A, d, a, T, N):
             a0, a1 = a0[legal], a1[legal]
         e = rel_err(a1, a0)
         differs += e > 0
-        assert e < (2e-4 if k.startswith("grad/") else 2e-4), (k, e)
+        assert e < (1e-3 if k.startswith("grad/") else 2e-4), (k, e)
     assert differs > 10, "the fused kernels did not run (results are bit-identical to the layer path)"
