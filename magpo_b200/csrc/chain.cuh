@@ -38,8 +38,10 @@ struct ChainCommon {
   int n_gemm;                    // GEMMs per tile, in issue order
   int g_N[CH_MAX_GEMM];
   int g_dcol[CH_MAX_GEMM];        // first accumulator column of the GEMM's result
+  int g_wrow[CH_MAX_GEMM];       // first row of the GEMM's B operand inside its weight map
   uint32_t g_boff[CH_MAX_GEMM];  // byte offset of the hi image inside the weight area; the lo image follows it
   int ring_slots;
+  int par_floats;                // size of the kernel's small-parameter area
   uint32_t w_bytes;              // whole weight area
 };
 
@@ -150,6 +152,13 @@ __device__ __forceinline__ void put_A(RowCtx& c, const float (&x)[64]) {
     tmem_st32(c.tm + CH_TM_ALO + 32 * h, lo);
   }
   tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(c.a_ready);
+  ++c.a_uses;
+}
+// the A operand stays as it is: hand it to the next GEMM of the program (after this thread has drained the accumulator it overwrites)
+__device__ __forceinline__ void rearm_A(RowCtx& c) {
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(c.a_ready);

@@ -24,7 +24,6 @@ struct Carve {
   uint64_t *in_full, *in_empty, *a_ready, *d_ready, *in_done, *b_ready;
   uint32_t* tmem_ptr;
 };
-constexpr int CH_PAR_FLOATS = 64 * 36 + 64;  // up to: 4 scale vectors + W3 [64 x 32] + b3
 
 __device__ __forceinline__ Carve carve_smem(uint8_t* smem_raw, const ChainCommon& cc) {
   Carve c;
@@ -33,7 +32,7 @@ __device__ __forceinline__ Carve carve_smem(uint8_t* smem_raw, const ChainCommon
   c.ring = c.sW + cc.w_bytes;
   c.obuf = c.ring + (size_t)cc.ring_slots * CH_SLOT;
   c.sPar = reinterpret_cast<float*>(c.obuf + 2 * 2 * CH_SLOT);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(c.sPar + CH_PAR_FLOATS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c.sPar + cc.par_floats);
   c.in_full = bars;
   c.in_empty = bars + CH_MAX_RING;
   c.a_ready = bars + 2 * CH_MAX_RING;
@@ -43,8 +42,8 @@ __device__ __forceinline__ Carve carve_smem(uint8_t* smem_raw, const ChainCommon
   c.tmem_ptr = reinterpret_cast<uint32_t*>(c.b_ready + 1);
   return c;
 }
-inline uint32_t chain_smem_bytes(uint32_t w_bytes, int ring_slots) {
-  return 1024 + w_bytes + (uint32_t)ring_slots * CH_SLOT + 4 * CH_SLOT + CH_PAR_FLOATS * 4 + (2 * CH_MAX_RING + 7) * 8 + 16;
+inline uint32_t chain_smem_bytes(uint32_t w_bytes, int ring_slots, int par_floats) {
+  return 1024 + w_bytes + (uint32_t)ring_slots * CH_SLOT + 4 * CH_SLOT + (uint32_t)par_floats * 4 + (2 * CH_MAX_RING + 7) * 8 + 16;
 }
 
 // barriers + TMEM allocation; every thread of the CTA calls this once
@@ -86,8 +85,8 @@ __device__ __forceinline__ void chain_producer(const Carve& c, const ChainCommon
   for (int i = 0; i < cc.n_gemm; ++i) {
     const uint32_t chunk = (uint32_t)cc.g_N[i] * 128u, image = 2 * chunk;
     for (int kc = 0; kc < 2; ++kc) {
-      tma_load_2d(c.sW + cc.g_boff[i] + kc * chunk, &m.w[2 * i], kc * 32, 0, c.b_ready);
-      tma_load_2d(c.sW + cc.g_boff[i] + image + kc * chunk, &m.w[2 * i + 1], kc * 32, 0, c.b_ready);
+      tma_load_2d(c.sW + cc.g_boff[i] + kc * chunk, &m.w[2 * i], kc * 32, cc.g_wrow[i], c.b_ready);
+      tma_load_2d(c.sW + cc.g_boff[i] + image + kc * chunk, &m.w[2 * i + 1], kc * 32, cc.g_wrow[i], c.b_ready);
     }
   }
   uint32_t it = 0;
@@ -191,9 +190,10 @@ struct GateParams {
   int max_step;
   int store_y, store_ype;
 };
-enum { GO_GATED = 0, GO_O, GO_Y, GO_YPE, GO_GL, GO_H };
+enum { GO_GATED = 0, GO_O, GO_Y, GO_YPE, GO_GL /* MODE 2: the projection's output */, GO_H };
 
-template <bool FFN>
+// MODE 0: ends after the norm; 1: + SwiGLU up-projection; 2: + a [64 -> 192] projection of ype (the decoder's cross-retention k | v | g)
+template <int MODE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chain_gate_kernel(const __grid_constant__ ChainMaps maps, const GateParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -251,7 +251,19 @@ chain_gate_kernel(const __grid_constant__ ChainMaps maps, const GateParams p) {
         add_pe64(x, p.pe + (size_t)st * 64);
         out_store64(r, &maps.out[GO_YPE], 0, row0, x);
       }
-      if (FFN) {
+      if (MODE == 2) {
+        put_A(r, x);
+        wait_D(r);
+        ld_D64<0>(r, x);
+        out_store64(r, &maps.out[GO_GL], 0, row0, x);
+        ld_D64<64>(r, x);
+        rearm_A(r);  // the last 64 columns run while the first 128 leave
+        out_store64(r, &maps.out[GO_GL], 64, row0, x);
+        wait_D(r);
+        ld_D64<0>(r, x);
+        out_store64(r, &maps.out[GO_GL], 128, row0, x);
+      }
+      if (MODE == 1) {
         // ---- gl = y [W_gate | W_linear] ; hmid = swish(gl_a) * gl_b
         put_A(r, x);
         wait_D(r);
@@ -374,6 +386,114 @@ chain_tail_kernel(const __grid_constant__ ChainMaps maps, const TailParams p) {
   chain_teardown(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------------ front chain
+// The rows entering the first retention of each network:
+//   OBS   on = RMSNorm_d(obs) * obs_scale -> z0 = on W_obs -> x = RMSNorm(gelu(z0)) * ln -> xpe = x + PE -> qkvg = xpe [w_q|w_k|w_v|w_g]
+//   !OBS  token = shifted action -> x = RMSNorm(gelu(W_a[token])) * ln (a per-CTA table) -> xpe = x + PE -> qkvg = xpe [w_q|w_k|w_v|w_g]
+struct FrontParams {
+  ChainCommon cc;
+  int d, A, a, max_step;
+  const float *obs, *obs_scale, *Wobs, *Wa, *ln_s, *pe;
+  const int32_t *action, *step;
+};
+enum { FO_Z0 = 0, FO_X, FO_XPE, FO_Q };
+
+template <bool OBS>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chain_front_kernel(const __grid_constant__ ChainMaps maps, const FrontParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const Carve c = carve_smem(smem_raw, p.cc);
+  float *ls = c.sPar, *osc = c.sPar + 64, *tab = c.sPar + 80;  // tab: W_obs [d][64] or the token table [(a+1)][64]
+  for (int i = threadIdx.x; i < 64; i += CH_THREADS) ls[i] = p.ln_s[i];
+  if (OBS) {
+    for (int i = threadIdx.x; i < 16; i += CH_THREADS) osc[i] = i < p.d ? p.obs_scale[i] : 0.f;
+    for (int i = threadIdx.x; i < p.d * 64; i += CH_THREADS) tab[i] = p.Wobs[i];
+  }
+  __syncthreads();
+  if (!OBS && threadIdx.x <= p.a) {  // x of every token value, once per CTA
+    float v[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = gelu_fast(p.Wa[threadIdx.x * 64 + j]);
+    rms64(v, ls);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) tab[threadIdx.x * 64 + j] = v[j];
+  }
+  const uint32_t tmem_base = chain_setup(c, p.cc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (lane == 0) chain_producer(c, p.cc, maps);
+  } else if (warp == 1) {
+    if (lane == 0) chain_mma(c, p.cc, tmem_base);
+  } else if (warp >= 4) {
+    RowCtx r = row_ctx(c, p.cc, tmem_base);
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.cc.num_tiles; tile += gridDim.x, ++ti) {
+      if ((ti & 1) != r.group) continue;
+      const int row0 = tile * 128;
+      const int64_t row = (int64_t)row0 + r.rt;
+      const bool live = row < p.cc.R;
+      float x[64];
+      if (OBS) {
+        float ob[16];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          ob[k] = (live && k < p.d) ? __ldg(p.obs + row * p.d + k) : 0.f;
+          ss = fmaf(ob[k], ob[k], ss);
+        }
+        const float rstd0 = rsqrtf(ss / (float)p.d + kEps);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) x[j] = 0.f;
+        for (int k = 0; k < p.d; ++k) {
+          float okv = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) okv = kk == k ? ob[kk] : okv;
+          okv *= rstd0 * osc[k];
+          const float* wr = tab + k * 64;
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wr + j);
+            x[j] = fmaf(okv, w.x, x[j]); x[j + 1] = fmaf(okv, w.y, x[j + 1]);
+            x[j + 2] = fmaf(okv, w.z, x[j + 2]); x[j + 3] = fmaf(okv, w.w, x[j + 3]);
+          }
+        }
+        out_store64(r, &maps.out[FO_Z0], 0, row0, x);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) x[j] = gelu_fast(x[j]);
+        rms64(x, ls);
+      } else {
+        int tok = 0;
+        if (live && (row % p.A) != 0) tok = 1 + p.action[row - 1];
+        const float* tr = tab + tok * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(tr + j);
+          x[j] = t.x; x[j + 1] = t.y; x[j + 2] = t.z; x[j + 3] = t.w;
+        }
+      }
+      out_store64(r, &maps.out[FO_X], 0, row0, x);
+      const int st = live ? min(max(p.step[row], 0), p.max_step) : 0;
+      add_pe64(x, p.pe + (size_t)st * 64);
+      put_A(r, x);
+      out_store64(r, &maps.out[FO_XPE], 0, row0, x);
+      // ---- the four 64-wide projections, 128 columns per pass
+      wait_D(r);
+      ld_D64<0>(r, x);
+      out_store64(r, &maps.out[FO_Q], 0, row0, x);
+      ld_D64<64>(r, x);
+      rearm_A(r);
+      out_store64(r, &maps.out[FO_Q], 64, row0, x);
+      wait_D(r);
+      ld_D64<0>(r, x);
+      out_store64(r, &maps.out[FO_Q], 128, row0, x);
+      ld_D64<64>(r, x);
+      out_store64(r, &maps.out[FO_Q], 192, row0, x);
+    }
+    if (r.lane == 0) bulk_wait_all();
+  }
+  chain_teardown(tmem_base);
+}
+
 // ---------------------------------------------------------------- host side
 bool g_chain_enabled = [] {
   const char* e = getenv("MAGPO_CHAIN");  // "0": the layer-by-layer kernels everywhere
@@ -385,16 +505,18 @@ bool act_map(CUtensorMap* tm, const float* ptr, int64_t R, int cols, int ld) { r
 bool out_map(CUtensorMap* tm, const float* ptr, int64_t R, int cols, int ld) { return tc_make_map(tm, ptr, R, cols, ld, 32); }
 
 // B operand images of a [N, 64] transposed weight registered with tc_prepare_region
-bool weight_maps(ChainMaps* m, int i, const float* wt, int N, int ld) {
+bool weight_maps(ChainMaps* m, int i, const float* wt, int N, int ld, int box_rows = 0) {
   const float *hi, *lo;
   if (!tc_lookup(wt, &hi, &lo)) return false;
-  return tc_make_map(&m->w[2 * i], hi, N, 64, ld, N) && tc_make_map(&m->w[2 * i + 1], lo, N, 64, ld, N);
+  if (!box_rows) box_rows = N;
+  return tc_make_map(&m->w[2 * i], hi, N, 64, ld, box_rows) && tc_make_map(&m->w[2 * i + 1], lo, N, 64, ld, box_rows);
 }
 
-void add_gemm(ChainCommon* cc, int N, int dcol = 0) {
+void add_gemm(ChainCommon* cc, int N, int dcol = 0, int wrow = 0) {
   const int i = cc->n_gemm++;
   cc->g_N[i] = N;
   cc->g_dcol[i] = dcol;
+  cc->g_wrow[i] = wrow;
   cc->g_boff[i] = cc->w_bytes;
   cc->w_bytes += 2u * 2u * (uint32_t)N * 128u;  // hi + lo, two 32-wide k chunks each
 }
@@ -404,14 +526,15 @@ void add_input(ChainCommon* cc, int map) {
     cc->in_col[cc->n_in++] = 32 * h;
   }
 }
-bool finish_plan(ChainCommon* cc, int64_t R, uint32_t* smem) {
+bool finish_plan(ChainCommon* cc, int64_t R, int par_floats, uint32_t* smem) {
   cc->R = R;
   cc->num_tiles = (int)ceil_div(R, 128);
-  int slots = CH_MAX_RING;
-  while (slots >= 2 && chain_smem_bytes(cc->w_bytes, slots) > CH_SMEM_LIMIT) --slots;
-  if (slots < 2) return false;
+  cc->par_floats = par_floats;
+  int slots = cc->n_in ? CH_MAX_RING : 0;
+  while (slots >= 2 && chain_smem_bytes(cc->w_bytes, slots, par_floats) > CH_SMEM_LIMIT) --slots;
+  if (cc->n_in ? slots < 2 : chain_smem_bytes(cc->w_bytes, 0, par_floats) > CH_SMEM_LIMIT) return false;
   cc->ring_slots = slots;
-  *smem = chain_smem_bytes(cc->w_bytes, slots);
+  *smem = chain_smem_bytes(cc->w_bytes, slots, par_floats);
   return true;
 }
 
@@ -422,37 +545,75 @@ bool chain_supported(int64_t R) { return g_chain_enabled && tc_enabled() && R >=
 
 int chain_gate_fwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float* ret, const float* res, const float* gn_s,
                    const float* gn_b, const float* ln_s, const float* pe, const int32_t* step, int max_step, const float* W1T,
-                   const float* W2T, float* gated, float* o, float* y, float* ype, float* gl, float* hmid) {
+                   const float* W2T, const float* WpT, float* gated, float* o, float* y, float* ype, float* gl, float* hmid, float* proj,
+                   int ldproj) {
   ChainMaps m;
   GateParams p{};
-  const bool ffn = W2T != nullptr;
+  const int mode = W2T ? 1 : (WpT ? 2 : 0);
   add_input(&p.cc, 0);  // ret
   add_input(&p.cc, 1);  // g
   add_input(&p.cc, 2);  // res
   add_gemm(&p.cc, 64);
-  if (ffn) add_gemm(&p.cc, 128);
+  if (mode == 1) add_gemm(&p.cc, 128);
+  if (mode == 2) {
+    add_gemm(&p.cc, 128, 0, 0);
+    add_gemm(&p.cc, 64, 0, 128);
+  }
   uint32_t smem;
-  if (!finish_plan(&p.cc, R, &smem)) return MAGPO_ERR_UNSUPPORTED;
+  if (!finish_plan(&p.cc, R, 192, &smem)) return MAGPO_ERR_UNSUPPORTED;
   bool ok = act_map(&m.in[0], ret, R, 64, 64) && act_map(&m.in[1], g, R, 64, ldg) && act_map(&m.in[2], res, R, 64, 64) &&
             out_map(&m.out[GO_GATED], gated, R, 64, 64) && out_map(&m.out[GO_O], o, R, 64, 64) && weight_maps(&m, 0, W1T, 64, 64);
   if (y) ok = ok && out_map(&m.out[GO_Y], y, R, 64, 64);
   if (ype) ok = ok && out_map(&m.out[GO_YPE], ype, R, 64, 64);
-  if (ffn) ok = ok && out_map(&m.out[GO_GL], gl, R, 128, 128) && out_map(&m.out[GO_H], hmid, R, 64, 64) && weight_maps(&m, 1, W2T, 128, 64);
+  if (mode == 1) ok = ok && out_map(&m.out[GO_GL], gl, R, 128, 128) && out_map(&m.out[GO_H], hmid, R, 64, 64) && weight_maps(&m, 1, W2T, 128, 64);
+  if (mode == 2)
+    ok = ok && ype && out_map(&m.out[GO_GL], proj, R, 192, ldproj) && weight_maps(&m, 1, WpT, 192, 64, 128) && weight_maps(&m, 2, WpT, 192, 64, 64);
   if (!ok) return MAGPO_ERR_ARG;
   p.gn_s = gn_s; p.gn_b = gn_b; p.ln_s = ln_s; p.pe = pe; p.step = step; p.max_step = max_step;
   p.store_y = y != nullptr;
   p.store_ype = ype != nullptr;
   const unsigned grid = (unsigned)std::min(p.cc.num_tiles, kNumSMs);
-  const double units = 3 + 2 + (y ? 1 : 0) + (ype ? 1 : 0) + (ffn ? 3 : 0);
-  ProfScope ps(PROF_CHAIN, s, 2.0 * R * 64 * (64 + (ffn ? 128 : 0)), units * 256.0 * R);
-  if (ffn) {
-    if (once_per_device(ONCE_CHAIN_GATE_FFN))
-      MAGPO_CUDA_OK(cudaFuncSetAttribute(chain_gate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_LIMIT));
-    chain_gate_kernel<true><<<grid, CH_THREADS, smem, s>>>(m, p);
+  const double units = 3 + 2 + (y ? 1 : 0) + (ype ? 1 : 0) + (mode ? 3 : 0);
+  ProfScope ps(PROF_CHAIN, s, 2.0 * R * 64 * (64 + (mode == 1 ? 128 : mode == 2 ? 192 : 0)), units * 256.0 * R);
+#define LAUNCH_GATE(MODE, ONCE)                                                                                                    \
+  {                                                                                                                                \
+    if (once_per_device(ONCE))                                                                                                     \
+      MAGPO_CUDA_OK(cudaFuncSetAttribute(chain_gate_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_LIMIT)); \
+    chain_gate_kernel<MODE><<<grid, CH_THREADS, smem, s>>>(m, p);                                                                  \
+  }
+  if (mode == 1) LAUNCH_GATE(1, ONCE_CHAIN_GATE_FFN) else if (mode == 2) LAUNCH_GATE(2, ONCE_CHAIN_GATE_PROJ) else LAUNCH_GATE(0, ONCE_CHAIN_GATE)
+#undef LAUNCH_GATE
+  MAGPO_LAUNCH_OK();
+  return MAGPO_OK;
+}
+
+int chain_front_fwd(cudaStream_t s, int64_t R, int d, const float* obs, const float* obs_scale, const float* Wobs, int A, int a,
+                    const int32_t* action, const float* Wa, const float* ln_s, const float* pe, const int32_t* step, int max_step,
+                    const float* WqT, float* z0, float* x, float* xpe, float* qkvg) {
+  ChainMaps m;
+  FrontParams p{};
+  const bool obs_mode = obs != nullptr;
+  if (obs_mode ? (d < 1 || d > 16) : (a < 1 || a > 32)) return MAGPO_ERR_UNSUPPORTED;
+  add_gemm(&p.cc, 128, 0, 0);
+  add_gemm(&p.cc, 128, 0, 128);
+  uint32_t smem;
+  if (!finish_plan(&p.cc, R, 64 + 16 + 33 * 64, &smem)) return MAGPO_ERR_UNSUPPORTED;
+  bool ok = out_map(&m.out[FO_X], x, R, 64, 64) && out_map(&m.out[FO_XPE], xpe, R, 64, 64) && out_map(&m.out[FO_Q], qkvg, R, 256, 256) &&
+            weight_maps(&m, 0, WqT, 256, 64, 128) && weight_maps(&m, 1, WqT, 256, 64, 128);
+  if (obs_mode) ok = ok && out_map(&m.out[FO_Z0], z0, R, 64, 64);
+  if (!ok) return MAGPO_ERR_ARG;
+  p.d = d; p.obs = obs; p.obs_scale = obs_scale; p.Wobs = Wobs; p.A = A; p.a = a; p.action = action; p.Wa = Wa; p.ln_s = ln_s;
+  p.pe = pe; p.step = step; p.max_step = max_step;
+  const unsigned grid = (unsigned)std::min(p.cc.num_tiles, kNumSMs);
+  ProfScope ps(PROF_CHAIN, s, 2.0 * R * 64 * 256, ((obs_mode ? 7 : 6) * 256.0 + (obs_mode ? 4.0 * d : 4.0)) * R);
+  if (obs_mode) {
+    if (once_per_device(ONCE_CHAIN_FRONT_OBS))
+      MAGPO_CUDA_OK(cudaFuncSetAttribute(chain_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_LIMIT));
+    chain_front_kernel<true><<<grid, CH_THREADS, smem, s>>>(m, p);
   } else {
-    if (once_per_device(ONCE_CHAIN_GATE))
-      MAGPO_CUDA_OK(cudaFuncSetAttribute(chain_gate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_LIMIT));
-    chain_gate_kernel<false><<<grid, CH_THREADS, smem, s>>>(m, p);
+    if (once_per_device(ONCE_CHAIN_FRONT_EMB))
+      MAGPO_CUDA_OK(cudaFuncSetAttribute(chain_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_LIMIT));
+    chain_front_kernel<false><<<grid, CH_THREADS, smem, s>>>(m, p);
   }
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
@@ -471,7 +632,7 @@ int chain_tail_fwd(cudaStream_t s, int64_t R, const float* hmid, const float* re
   add_gemm(&p.cc, 64);          // h0
   if (q) add_gemm(&p.cc, 64, 64);  // q
   uint32_t smem;
-  if (!finish_plan(&p.cc, R, &smem)) return MAGPO_ERR_UNSUPPORTED;
+  if (!finish_plan(&p.cc, R, 192 + 64 * 32 + 32, &smem)) return MAGPO_ERR_UNSUPPORTED;
   bool ok = act_map(&m.in[0], hmid, R, 64, 64) && act_map(&m.in[1], res, R, 64, 64) && out_map(&m.out[TO_F], f, R, 64, 64) &&
             out_map(&m.out[TO_X], x, R, 64, 64) && out_map(&m.out[TO_ZH], zh, R, 64, 64) && weight_maps(&m, 0, W1T, 64, 64);
   if (xpe) ok = ok && out_map(&m.out[TO_XPE], xpe, R, 64, 64);

@@ -91,7 +91,7 @@ int comm_allreduce(MagpoComm* c, cudaStream_t s, float* buf, int64_t n, int op);
 // true exactly once per (device, id): guards cudaFuncSetAttribute, which is per device
 bool once_per_device(int id);
 enum { ONCE_GEMM_TC = 0, ONCE_GEMM_TN, ONCE_GRU_FWD, ONCE_GRU_BWD, ONCE_RET_FWD, ONCE_RET_BWD, ONCE_SABLE_STEP_1 /* 8 ids: (A - 1) * 2 + (EPW - 1) */,
-       ONCE_SABLE_STEP_LAST = ONCE_SABLE_STEP_1 + 7, ONCE_CHAIN_GATE, ONCE_CHAIN_GATE_FFN, ONCE_CHAIN_TAIL, ONCE_CHAIN_BWD_A, ONCE_CHAIN_BWD_B,
+       ONCE_SABLE_STEP_LAST = ONCE_SABLE_STEP_1 + 7, ONCE_CHAIN_GATE, ONCE_CHAIN_GATE_FFN, ONCE_CHAIN_GATE_PROJ, ONCE_CHAIN_TAIL, ONCE_CHAIN_FRONT_OBS, ONCE_CHAIN_FRONT_EMB, ONCE_CHAIN_BWD_A, ONCE_CHAIN_BWD_B,
        ONCE_NUM };
 
 constexpr int kNumSMs = 148;

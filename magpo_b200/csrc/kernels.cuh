@@ -47,7 +47,14 @@ bool chain_supported(int64_t R);
 // with W2T: gl = y W2 [R,128]; hmid = swish(gl[:, :64]) * gl[:, 64:].  W1T [64,64], W2T [128,64]: transposed weights with registered images
 int chain_gate_fwd(cudaStream_t s, int64_t R, const float* g, int ldg, const float* ret, const float* res, const float* gn_s,
                    const float* gn_b, const float* ln_s, const float* pe, const int32_t* step, int max_step, const float* W1T,
-                   const float* W2T, float* gated, float* o, float* y, float* ype, float* gl, float* hmid);
+                   const float* W2T, const float* WpT, float* gated, float* o, float* y, float* ype, float* gl, float* hmid, float* proj,
+                   int ldproj);
+// with WpT [192,64] (instead of W2T): proj[R,192] (row stride ldproj) = ype Wp
+// The rows entering the first retention: obs != null: z0 = (RMSNorm_d(obs) * obs_scale) Wobs (d <= 16), x = RMSNorm(gelu(z0)) * ln_s;
+// obs == null: x = RMSNorm(gelu(Wa[shifted action token])) * ln_s (A agents per timestep); then xpe = x + pe[step], qkvg[R,256] = xpe Wq
+int chain_front_fwd(cudaStream_t s, int64_t R, int d, const float* obs, const float* obs_scale, const float* Wobs, int A, int a,
+                    const int32_t* action, const float* Wa, const float* ln_s, const float* pe, const int32_t* step, int max_step,
+                    const float* WqT, float* z0, float* x, float* xpe, float* qkvg);
 // f = hmid W1; x = RMSNorm(f + res) * ln_s; xpe = x + pe[step] (optional); q = xpe Wq (optional, row stride ldq); zh = x Wh + h_bias;
 // out[R,nout] = RMSNorm(gelu(zh)) * h2_s @ W3 + b3
 int chain_tail_fwd(cudaStream_t s, int64_t R, const float* hmid, const float* res, const float* ln_s, const float* pe,

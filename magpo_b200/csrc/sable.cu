@@ -77,20 +77,25 @@ int sable_encoder_forward(cudaStream_t s, const GuiderP& p, const GuiderT* pt, i
                           const float* agents_view, const int32_t* step, const uint8_t* done, const float* H0,
                           float kappa, const float* pe, const SableActs& w, float* value, float* Hsave, float* Hout, bool chain, float* dec_q) {
   const int64_t R = (int64_t)T * N * A;
-  if (obs_embed_ok(d)) {
+  const bool chained = chain && pt && chain_supported(R);
+  if (chained && obs_embed_ok(d)) {
+    MAGPO_TRY(chain_front_fwd(s, R, d, agents_view, p.obs_scale, p.Wobs, A, 0, nullptr, nullptr, p.ln, pe, step, max_step, pt->qkvgT, w.z0,
+                              w.xin, w.kqv, w.qkvg));
+  } else if (obs_embed_ok(d)) {
     MAGPO_TRY(obs_embed_fwd(s, R, d, agents_view, p.obs_scale, p.Wobs, p.ln, pe, step, max_step, w.on, w.z0, w.xin, w.kqv));
   } else {
     MAGPO_TRY(rms_general_fwd(s, R, d, agents_view, p.obs_scale, w.on));
     MAGPO_TRY(gemm_nn(s, R, kD, d, w.on, d, wref(p.Wobs, kD), nullptr, w.z0, kD, 0));
     MAGPO_TRY(act_rms_fwd(s, R, w.z0, nullptr, p.ln, ROW_GELU, pe, step, max_step, w.xin, w.kqv));
   }
-  MAGPO_TRY(gemm_nn(s, R, 4 * kD, kD, w.kqv, kD, wref(p.qkvg, 4 * kD, pt ? pt->qkvgT : nullptr, kD), nullptr, w.qkvg, 4 * kD, 0));
+  if (!(chained && obs_embed_ok(d)))
+    MAGPO_TRY(gemm_nn(s, R, 4 * kD, kD, w.kqv, kD, wref(p.qkvg, 4 * kD, pt ? pt->qkvgT : nullptr, kD), nullptr, w.qkvg, 4 * kD, 0));
   MAGPO_TRY(retention_fwd(s, T, N, A, kappa, false, w.qkvg, w.qkvg + kD, w.qkvg + 2 * kD, 4 * kD, H0, done, w.ret,
                           Hsave, Hout));
-  if (chain && pt && chain_supported(R)) {
+  if (chained) {
     // the two row chains after the retention, one persistent kernel each (chain_fwd.cu); dec_q: the decoder's cross-retention query
     MAGPO_TRY(chain_gate_fwd(s, R, w.qkvg + 3 * kD, 4 * kD, w.ret, w.xin, p.gn_s, p.gn_b, p.ln1, nullptr, nullptr, 0, pt->woT, pt->ffn_glT,
-                             w.gated, w.o, w.x1, nullptr, w.gl, w.hmid));
+                             nullptr, w.gated, w.o, w.x1, nullptr, w.gl, w.hmid, nullptr, 0));
     MAGPO_TRY(chain_tail_fwd(s, R, w.hmid, w.x1, p.ln2, pe, step, max_step, pt->ffn_outT, dec_q ? pt->qkvg2T : nullptr, kD, pt->h0T, p.h0_b,
                              p.h2_s, p.h3_w, p.h3_b, 1, w.f, w.x, w.xpe, dec_q, 4 * kD, w.zh, value));
     return MAGPO_OK;
@@ -121,20 +126,26 @@ static int decoder_forward_phase(int phase, bool q_done, cudaStream_t s, const G
   const int64_t R = (int64_t)T * N * ret_A;
   const bool chained = pt && embed_A > 0 && !Hself_out && chain_supported(R);  // training forward only: the rollout keeps its kernels
   if (phase != 2) {
-    MAGPO_TRY(embed_fwd(s, R, embed_A, action, p.Wa, p.dln, pe, step, max_step, w.xD, w.xpeD));
-    MAGPO_TRY(gemm_nn(s, R, 4 * kD, kD, w.xpeD, kD, wref(p.qkvg1, 4 * kD, pt ? pt->qkvg1T : nullptr, kD), nullptr, w.qkvg1, 4 * kD, 0));
+    if (chained) {
+      MAGPO_TRY(chain_front_fwd(s, R, 0, nullptr, nullptr, nullptr, embed_A, a, action, p.Wa, p.dln, pe, step, max_step, pt->qkvg1T, nullptr,
+                                w.xD, w.xpeD, w.qkvg1));
+    } else {
+      MAGPO_TRY(embed_fwd(s, R, embed_A, action, p.Wa, p.dln, pe, step, max_step, w.xD, w.xpeD));
+      MAGPO_TRY(gemm_nn(s, R, 4 * kD, kD, w.xpeD, kD, wref(p.qkvg1, 4 * kD, pt ? pt->qkvg1T : nullptr, kD), nullptr, w.qkvg1, 4 * kD, 0));
+    }
     MAGPO_TRY(retention_fwd(s, T, N, ret_A, kappa, true, w.qkvg1, w.qkvg1 + kD, w.qkvg1 + 2 * kD, 4 * kD, Hself0, done,
                             w.ret1, Hs_self, Hself_out));
     if (chained) {
+      // ... and the key / value / gate projections of the cross retention in the same kernel
       MAGPO_TRY(chain_gate_fwd(s, R, w.qkvg1 + 3 * kD, 4 * kD, w.ret1, w.xD, p.gn1_s, p.gn1_b, p.dln1, pe, step, max_step, pt->wo1T, nullptr,
-                               w.gated1, w.o1, nullptr, w.rpe, nullptr, nullptr));
+                               pt->qkvg2T + kD * kD, w.gated1, w.o1, nullptr, w.rpe, nullptr, nullptr, w.qkvg2 + kD, 4 * kD));
     } else {
       MAGPO_TRY(gn_gate_fwd(s, R, w.qkvg1 + 3 * kD, 4 * kD, w.ret1, p.gn1_s, p.gn1_b, w.gated1));
       MAGPO_TRY(gemm_nn(s, R, kD, kD, w.gated1, kD, wref(p.wo1, kD, pt ? pt->wo1T : nullptr, kD), nullptr, w.o1, kD, 0));
       MAGPO_TRY(act_rms_fwd(s, R, w.o1, w.xD, p.dln1, 0, pe, step, max_step, nullptr, w.rpe));
     }
     // cross retention: key = value = r (+PE), query = obs_rep (+PE); gate input is the PE-added key
-    MAGPO_TRY(gemm_nn(s, R, 3 * kD, kD, w.rpe, kD, wref(p.qkvg2 + kD, 4 * kD, pt ? pt->qkvg2T + kD * kD : nullptr, kD), nullptr, w.qkvg2 + kD, 4 * kD, 0));
+    if (!chained) MAGPO_TRY(gemm_nn(s, R, 3 * kD, kD, w.rpe, kD, wref(p.qkvg2 + kD, 4 * kD, pt ? pt->qkvg2T + kD * kD : nullptr, kD), nullptr, w.qkvg2 + kD, 4 * kD, 0));
   }
   if (phase == 1) return MAGPO_OK;
   if (!q_done) MAGPO_TRY(gemm_nn(s, R, kD, kD, x_rep_pe, kD, wref(p.qkvg2, 4 * kD, pt ? pt->qkvg2T : nullptr, kD), nullptr, w.qkvg2, 4 * kD, 0));
@@ -142,7 +153,7 @@ static int decoder_forward_phase(int phase, bool q_done, cudaStream_t s, const G
                           w.ret2, Hs_cross, Hcross_out));
   if (chained) {
     MAGPO_TRY(chain_gate_fwd(s, R, w.qkvg2 + 3 * kD, 4 * kD, w.ret2, x_rep, p.gn2_s, p.gn2_b, p.dln2, nullptr, nullptr, 0, pt->wo2T, pt->dffn_glT,
-                             w.gated2, w.o2, w.y, nullptr, w.glD, w.hmidD));
+                             nullptr, w.gated2, w.o2, w.y, nullptr, w.glD, w.hmidD, nullptr, 0));
     MAGPO_TRY(chain_tail_fwd(s, R, w.hmidD, w.y, p.dln3, nullptr, nullptr, 0, pt->dffn_outT, nullptr, 0, pt->dh0T, p.dh0_b, p.dh2_s, p.dh3_w,
                              p.dh3_b, a, w.fD, w.xd, nullptr, nullptr, 0, w.zhD, logits));
     return MAGPO_OK;

@@ -201,7 +201,7 @@ def test_minibatch_grads(dev, A, d, a, T, Ns, U, tol, shape=(64, 1, 1), yardstic
         assert worst < tol, worst
 
 
-CHAIN_BUFFERS = ("gated", "o", "x1", "hmid", "f", "x", "xpe", "zh", "gated1", "o1", "rpe", "gated2", "o2", "y", "hmidD", "fD", "xd", "zhD")
+CHAIN_BUFFERS = ("z0", "xin", "kqv", "xD", "xpeD", "gated", "o", "x1", "hmid", "f", "x", "xpe", "zh", "gated1", "o1", "rpe", "gated2", "o2", "y", "hmidD", "fD", "xd", "zhD")
 
 
 @pytest.mark.parametrize("A,d,a,T,N", [(2, 14, 6, 16, 64), (3, 4, 10, 7, 41), (4, 75, 5, 9, 8), (2, 14, 6, 16, 1500)])
@@ -229,7 +229,7 @@ def test_chain_kernels_match_layer_path(dev, A, d, a, T, N):
                    L.ptr(env_slot), L.ptr(stats), C.c_float(1.0 / (N * T * A)), L.ptr(grads), 0, L.ptr(ws), C.c_size_t(nbytes))
             sync()
             got[on] = {k: ws_buffer(ws, net, T, N, k, (T, N, A, 64)) for k in CHAIN_BUFFERS}
-            for k, w in (("gl", 128), ("glD", 128), ("qkvg2", 256)):
+            for k, w in (("gl", 128), ("glD", 128), ("qkvg", 256), ("qkvg1", 256), ("qkvg2", 256)):
                 got[on][k] = ws_buffer(ws, net, T, N, k, (T, N, A, w))
             got[on]["value"] = ws_buffer(ws, net, T, N, "value", (T, N, A))
             got[on]["logits"] = ws_buffer(ws, net, T, N, "lg", (T, N, A, a))
