@@ -11,6 +11,11 @@
 //               tcgen05.commit releases the smem stage / publishes the accumulator
 //   warps 4-7   epilogue: tcgen05.ld (thread = row) -> bias/relu -> 128B-swizzled smem slab -> TMA store
 //               (or TMA reduce-add for Y += ...), double-buffered; TMEM accumulators are double-buffered too.
+// The tensor core re-reads its shared-memory operands on every K = 8 step, so with three MMAs per step the operand reads (not the
+// flops, not HBM) are what a narrow GEMM saturates first (measured: ~70 % of the shared-memory bandwidth at N = 64). For N tiles <= 128
+// the hi and lo images of B therefore sit side by side and the two products that share A_hi run as ONE MMA of width 2 BN:
+//     D[:, 0:BN] += A_hi B_hi,  D[:, BN:2BN] += A_hi B_lo   (one instruction),      D[:, 0:BN] += A_lo B_hi
+// and the epilogue adds the two halves. A is read twice per step instead of three times.
 // Every mbarrier wait is bounded and traps instead of hanging.
 #include <cuda.h>
 
@@ -34,7 +39,7 @@ constexpr int TC_MAX_STAGES = 6;
 constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
-  int M, N, K, BN, kchunks, stages, flags, num_row_tiles, tmem_cols;
+  int M, N, K, BN, kchunks, stages, flags, num_row_tiles, tmem_cols, stacked /* B hi | lo as one operand of width 2 BN */;
   const float* bias;
 };
 
@@ -47,9 +52,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   // carve (everything TMA touches is 1024-byte aligned)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_chunk_bytes = p.BN * 128;
-  uint8_t* sBh = base;
-  uint8_t* sBl = sBh + (size_t)p.kchunks * b_chunk_bytes;
-  uint8_t* sA = sBl + (size_t)p.kchunks * b_chunk_bytes;          // stages x {hi 16K, lo 16K}
+  uint8_t* sBh = base;                                             // per k chunk: [hi rows | lo rows]
+  uint8_t* sBl = sBh + b_chunk_bytes;
+  uint8_t* sA = sBh + (size_t)p.kchunks * 2 * b_chunk_bytes;       // stages x {hi 16K, lo 16K}
   uint8_t* sOut = sA + (size_t)p.stages * 2 * TC_CHUNK_BYTES;      // 2 x 16K
   float* sBias = reinterpret_cast<float*>(sOut + 2 * TC_CHUNK_BYTES);  // 256 floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
@@ -95,8 +100,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       mbar_expect_tx(b_ready, 2u * p.kchunks * b_chunk_bytes);
       for (int c = 0; c < p.kchunks; ++c) {
-        tma_load_2d(sBh + (size_t)c * b_chunk_bytes, &tmBh, c * TC_KC, n0, b_ready);
-        tma_load_2d(sBl + (size_t)c * b_chunk_bytes, &tmBl, c * TC_KC, n0, b_ready);
+        tma_load_2d(sBh + (size_t)c * 2 * b_chunk_bytes, &tmBh, c * TC_KC, n0, b_ready);
+        tma_load_2d(sBl + (size_t)c * 2 * b_chunk_bytes, &tmBl, c * TC_KC, n0, b_ready);
       }
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_row_tiles; tile += gridDim.x) {
@@ -111,28 +116,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(p.BN);
+      const uint32_t idesc = umma_idesc_tf32(p.BN), idesc2 = umma_idesc_tf32(2 * p.BN);
+      const int acc_cols = p.stacked ? 2 * p.BN : p.BN;
       mbar_wait(b_ready, 0);
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < p.num_row_tiles; tile += gridDim.x, ++ti) {
         const int acc = ti & 1;
         mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
         for (int c = 0; c < p.kchunks; ++c, ++it) {
           const int s = it % p.stages;
           mbar_wait(&full_conv[s], (it / p.stages) & 1);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(sA + (size_t)s * 2 * TC_CHUNK_BYTES);
           const uint32_t a_lo = a_hi + TC_CHUNK_BYTES;
-          const uint32_t b_hi = smem_u32(sBh + (size_t)c * b_chunk_bytes);
-          const uint32_t b_lo = smem_u32(sBl + (size_t)c * b_chunk_bytes);
+          const uint32_t b_hi = smem_u32(sBh + (size_t)c * 2 * b_chunk_bytes);
+          const uint32_t b_lo = smem_u32(sBl + (size_t)c * 2 * b_chunk_bytes);
 #pragma unroll
           for (int k = 0; k < TC_KC / 8; ++k) {
             const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes along K inside the swizzle atom
-            umma_tf32(tmem_d, umma_desc_k_sw128(a_lo + ko), umma_desc_k_sw128(b_hi + ko), idesc, (c | k) ? 1u : 0u);
-            umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_lo + ko), idesc, 1u);
-            umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_hi + ko), idesc, 1u);
+            if (p.stacked) {
+              umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_hi + ko), idesc2, (c | k) ? 1u : 0u);
+              umma_tf32(tmem_d, umma_desc_k_sw128(a_lo + ko), umma_desc_k_sw128(b_hi + ko), idesc, 1u);
+            } else {
+              umma_tf32(tmem_d, umma_desc_k_sw128(a_lo + ko), umma_desc_k_sw128(b_hi + ko), idesc, (c | k) ? 1u : 0u);
+              umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_lo + ko), idesc, 1u);
+              umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_hi + ko), idesc, 1u);
+            }
           }
           umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
         }
@@ -146,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int row = sub * 32 + lane;      // row of the tile this thread owns
     const bool relu = p.flags & GEMM_RELU, accumulate = p.flags & GEMM_ACCUMULATE;
     const int nslab = p.BN / 32;
+    const int acc_cols = p.stacked ? 2 * p.BN : p.BN;
     uint32_t ti = 0, slab_it = 0;
     for (int tile = blockIdx.x; tile < p.num_row_tiles; tile += gridDim.x, ++ti) {
       const int acc = ti & 1;
@@ -153,7 +165,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_after();
       for (int sl = 0; sl < nslab; ++sl, ++slab_it) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.BN + sl * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * acc_cols + sl * 32), v);
+        if (p.stacked) {  // + the A_hi B_lo half
+          uint32_t w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * acc_cols + p.BN + sl * 32), w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        }
         if (sl == nslab - 1) {  // accumulator fully read: hand it back to the MMA warp (one arrival per warp: hundreds of
           tc_fence_before();    // arrivals on one mbarrier serialise in shared memory and cost a large part of a microsecond)
           __syncwarp();
@@ -474,8 +492,9 @@ static bool tc_plan(int64_t M, int N, int K, TcParams* p, uint32_t* smem_bytes) 
     p->BN = bn;
     p->kchunks = K / TC_KC;
     p->stages = stages;
+    p->stacked = bn <= 128 ? 1 : 0;
     int cols = 32;
-    while (cols < 2 * bn) cols <<= 1;
+    while (cols < (p->stacked ? 4 : 2) * bn) cols <<= 1;
     p->tmem_cols = cols;
     *smem_bytes = fixed + (uint32_t)stages * 2 * TC_CHUNK_BYTES;
     return true;
