@@ -436,6 +436,19 @@ bool g_tc_enabled = env_tc_default();
 bool tc_make_map(void* tensor_map, const float* ptr, int64_t rows, int cols, int ld, int box_rows) {
   return make_map(static_cast<CUtensorMap*>(tensor_map), ptr, rows, cols, ld, box_rows);
 }
+// [T, rows, cols] fp32 tensor (contiguous), boxes of [1, box_rows, 32 floats], 128B swizzle: per-timestep slabs whose row tiles clip at
+// `rows` (the GRU scans' saved activations)
+bool tc_make_map3(void* tensor_map, const float* ptr, int64_t T, int64_t rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)T};
+  cuuint64_t gstride[2] = {(cuuint64_t)cols * 4, (cuuint64_t)rows * cols * 4};
+  cuuint32_t box[3] = {(cuuint32_t)TC_KC, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(static_cast<CUtensorMap*>(tensor_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 void tc_set_enabled(bool on) { g_tc_enabled = on; }
 bool tc_enabled() { return g_tc_enabled; }
 

@@ -2,9 +2,12 @@
 // GRUCell of SURVEY.md Appendix A8; BPTT per Appendix G).
 //
 // The recurrence is independent per (env, agent) row, so one CTA owns a tile of 128 rows for the whole sequence:
-//   * the hidden state never leaves the SM: it lives in registers (exact fp32) and, split into TF32 hi/lo images, in shared
-//     memory as the K-major 128B-swizzled A operand of tcgen05.mma;
-//   * W_h (hi/lo images, 384 KiB) does not fit beside it, so it is streamed from L2 every timestep through a TMA ring;
+//   * the hidden state never leaves the SM: it lives in registers (exact fp32) and, split into TF32 hi/lo images, in TENSOR MEMORY
+//     as the A operand of tcgen05.mma (A-from-TMEM form; round 2: it used to be a 128 KiB shared-memory operand — the tensor core
+//     re-read it on every K = 8 step, and publishing it cost an STS pass + fence.proxy.async per timestep). The gate threads write
+//     their 4 x 2 patches with tcgen05.st in the same 16x256b shape they read the accumulators with;
+//   * W_h (hi/lo images, 384 KiB) does not fit in shared memory, so it is streamed from L2 every timestep through a TMA ring
+//     (8 stages of the 16 pieces of a step now that the A operand is gone from shared memory);
 //   * accumulators live in tensor memory; the gate math runs straight out of tcgen05.ld registers, fused with the loads of
 //     the batched input-side pre-activations and the stores of everything the backward needs. The gate warps read TMEM with
 //     the 16x256b fragment shape (4 lanes = 32 consecutive bytes of a row), so each of their global accesses covers whole
@@ -28,7 +31,15 @@ constexpr int GS_GATE_WARPS = 16;
 constexpr int GS_GATE_THREADS = GS_GATE_WARPS * 32;
 constexpr int GS_THREADS = GS_GATE_THREADS + 128;  // + one warpgroup of service warps
 constexpr int GS_CHUNK = 128 * 128;            // bytes of one [128 rows x 32 floats] operand chunk
-constexpr int GS_STAGES = 4;
+constexpr int GS_STAGES = 4;       // backward ring
+constexpr int GS_FWD_STAGES = 3;   // forward ring (24 KiB pieces)
+constexpr int GS_IN_BOXES = 3;     // staging of one block's input pre-activations (r, z, n columns): 3 x [128 rows x 32 floats]
+constexpr int GS_OUT_BOXES = 6;    // staging of one block's saved activations: 6 x [128 rows x 32 floats]
+constexpr int GS_BWD_STAGES = 6;   // backward ring (32 KiB pieces)
+// forward TMEM columns: A hi [0,128), A lo [128,256), two accumulators of 96 at 256 / 352
+constexpr uint32_t GS_F_ALO = 128, GS_F_ACC = 256;
+// backward TMEM columns: A slots (gate r, z, n of a block) hi [0,96), lo [96,192), two carry accumulators of 128 at 192 / 320
+constexpr uint32_t GS_B_ALO = 96, GS_B_ACC = 192;
 constexpr int GS_FWD_STAGE = 2 * 96 * 128;     // [96 x 32] hi + lo
 constexpr int GS_BWD_STAGE = 2 * GS_CHUNK;     // [128 x 32] hi + lo
 constexpr uint32_t GS_SMEM = 227 * 1024;
@@ -42,6 +53,34 @@ __device__ __forceinline__ void tmem_ld_frag_nowait(uint32_t taddr, uint32_t* v)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the mirror image: thread values r[2h + e] -> (row l/4 + 8h, column 2(l%4) + e) of a 16-lane x 8-column patch
+__device__ __forceinline__ void tmem_st_frag(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// an 8-value patch as the TF32 hi / lo images of an A operand in tensor memory (hi = truncation, lo = exact remainder)
+__device__ __forceinline__ void tmem_st_patch_split(uint32_t taddr_hi, uint32_t taddr_lo, const float* v) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+    lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+  }
+  tmem_st_frag(taddr_hi, hi);
+  tmem_st_frag(taddr_hi + (16u << 16), hi + 4);
+  tmem_st_frag(taddr_lo, lo);
+  tmem_st_frag(taddr_lo + (16u << 16), lo + 4);
+}
+// D[tmem] (+)= A[tmem] . B[smem], kind::tf32
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 // both 16-lane halves of the warp's sub-partition: v[4 half + 2h + e]
 __device__ __forceinline__ void tmem_ld_patch_nowait(uint32_t taddr, uint32_t* v) {
   tmem_ld_frag_nowait(taddr, v);
@@ -84,6 +123,32 @@ __device__ __forceinline__ void store_patch(const float* v, float* slab, int wid
   for (int rr = 0; rr < 4; ++rr)
     if (gg.valid[rr])
       *reinterpret_cast<float2*>(slab + gg.grow[rr] * width + col + 2 * gg.m) = make_float2(v[vidx(rr, 0)], v[vidx(rr, 1)]);
+}
+// the patch into a 128B-swizzled [rows x 32 floats] staging box (c0 = first column of the warp's slab inside the box): the layout a TMA
+// store of the box expects. The gate warps' patches touch 8 rows x 32 B per global store instruction; staged, a block's six output
+// tensors leave as six bulk stores issued by one thread.
+__device__ __forceinline__ void stage_patch(uint8_t* box, int c0, const float* v, const GateGeom& gg) {
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr)
+    if (gg.valid[rr]) {
+      const int row = gg.row[rr];
+      const int unit = ((c0 >> 2) + (gg.m >> 1)) ^ (row & 7);
+      *reinterpret_cast<float2*>(box + row * 128 + unit * 16 + (gg.m & 1) * 8) = make_float2(v[vidx(rr, 0)], v[vidx(rr, 1)]);
+    }
+}
+// ... and back: the patch out of a staging box a TMA load filled
+__device__ __forceinline__ void unstage_patch(float* v, const uint8_t* box, int c0, const GateGeom& gg) {
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    float2 x = make_float2(0.f, 0.f);
+    if (gg.valid[rr]) {
+      const int row = gg.row[rr];
+      const int unit = ((c0 >> 2) + (gg.m >> 1)) ^ (row & 7);
+      x = *reinterpret_cast<const float2*>(box + row * 128 + unit * 16 + (gg.m & 1) * 8);
+    }
+    v[vidx(rr, 0)] = x.x;
+    v[vidx(rr, 1)] = x.y;
+  }
 }
 // the patch as TF32 hi / lo images in a 128B-swizzled K-major [128 rows x 32 floats] chunk (c0 = first column, multiple of 8)
 __device__ __forceinline__ void store_patch_split(uint8_t* chunk_hi, uint8_t* chunk_lo, int c0, const float* v, const GateGeom& gg) {
@@ -132,6 +197,10 @@ __device__ __forceinline__ uint64_t gtimer() {
     if (p.dbg && blockIdx.x == 0 && (idx) < 1024) p.dbg[(role) * 1024 + (idx)] = gtimer();      \
   } while (0)
 
+struct GruOutMaps {  // [T(+1), Rs, cols] tensors, boxes of [1, rpt, 32]
+  CUtensorMap gi, rzn, ghn, Y, HU;
+};
+
 struct GruFwdArgs {
   unsigned long long* dbg;
   int T, N, A;
@@ -147,35 +216,41 @@ struct GruFwdArgs {
 };
 
 __global__ void __launch_bounds__(GS_THREADS, 1)
-gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const GruFwdArgs p) {
+gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                    const __grid_constant__ GruOutMaps om, const GruFwdArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sAhi = base;                      // 4 chunks
-  uint8_t* sAlo = sAhi + 4 * GS_CHUNK;       // 4 chunks
-  uint8_t* sB = sAlo + 4 * GS_CHUNK;         // GS_STAGES x {hi 12K, lo 12K}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + GS_STAGES * GS_FWD_STAGE);
+  uint8_t* sB = base;                        // GS_FWD_STAGES x {hi 12K, lo 12K}
+  uint8_t* sOut = sB + GS_FWD_STAGES * GS_FWD_STAGE;  // 6 staging boxes (r, z, n, gh_n, y, h) of the block being finished (1 KiB-aligned)
+  uint8_t* sIn = sOut + GS_OUT_BOXES * GS_CHUNK;  // 3 staging boxes: the next block's gi columns, loaded while this block is computed
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + GS_IN_BOXES * GS_CHUNK);
   uint64_t* b_full = bars;
-  uint64_t* b_empty = bars + GS_STAGES;
-  uint64_t* acc_full = bars + 2 * GS_STAGES;  // 4
-  uint64_t* a_ready = acc_full + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 1);
-  volatile int* progress = reinterpret_cast<volatile int*>(tmem_ptr + 1);  // timesteps started by the gate warps (prefetch throttle)
+  uint64_t* b_empty = bars + GS_FWD_STAGES;
+  uint64_t* acc_full = bars + 2 * GS_FWD_STAGES;  // 2 accumulators
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* a_ready = acc_empty + 2;
+  uint64_t* in_full = a_ready + 1;
+  uint64_t* in_empty = in_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(in_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T;
   // a CTA owns p.rpt (32, 64 or 128) rows of its 128-row MMA tile: with few rows, spreading them over more SMs divides the
   // per-SM stream of saved activations; the unused rows of the tile are zero operands
   const int64_t tile_row0 = (int64_t)blockIdx.x * p.rpt;
-  const int64_t tile_rows = p.Rs - tile_row0 < p.rpt ? p.Rs - tile_row0 : p.rpt;
 
   if (warp == GS_GATE_WARPS + 1 && lane == 0) {
-    for (int i = 0; i < GS_STAGES; ++i) {
+    for (int i = 0; i < GS_FWD_STAGES; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], GS_GATE_WARPS);
+    }
     mbar_init(a_ready, GS_GATE_WARPS);
-    *progress = 0;
+    mbar_init(in_full, 1);
+    mbar_init(in_empty, GS_GATE_WARPS);
     fence_barrier_init();
   } else if (warp == GS_GATE_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
@@ -195,8 +270,8 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         for (int t = 0; t < T; ++t)
           for (int jb = 0; jb < 4; ++jb)
             for (int kc = 0; kc < 4; ++kc, ++it) {
-              const int s = it % GS_STAGES;
-              mbar_wait(&b_empty[s], ((it / GS_STAGES) & 1) ^ 1);
+              const int s = it % GS_FWD_STAGES;
+              mbar_wait(&b_empty[s], ((it / GS_FWD_STAGES) & 1) ^ 1);
               GS_STAMP(0, it);
               mbar_expect_tx(&b_full[s], GS_FWD_STAGE);
               uint8_t* st = sB + (size_t)s * GS_FWD_STAGE;
@@ -211,41 +286,50 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
       // ===================== MMA issuer =====================
       if (lane == 0) {
         const uint32_t idesc = idesc_tf32(96);
-        const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
         uint32_t it = 0;
         for (int t = 0; t < T; ++t) {
           mbar_wait(a_ready, t & 1);
           tc_fence_after();
           GS_STAMP(1, t * 16);
           for (int jb = 0; jb < 4; ++jb) {
-            const uint32_t tmem_d = tmem_base + (uint32_t)(jb * 96);
+            const int acc = jb & 1;
+            const uint32_t use = (uint32_t)t * 2 + (jb >> 1);  // uses of this accumulator so far
+            if (use > 0) {  // the gate warps have read the block that last occupied it
+              mbar_wait(&acc_empty[acc], (use - 1) & 1);
+              tc_fence_after();
+            }
+            const uint32_t tmem_d = tmem_base + GS_F_ACC + (uint32_t)(acc * 96);
             for (int kc = 0; kc < 4; ++kc, ++it) {
-              const int s = it % GS_STAGES;
-              mbar_wait(&b_full[s], (it / GS_STAGES) & 1);
+              const int s = it % GS_FWD_STAGES;
+              mbar_wait(&b_full[s], (it / GS_FWD_STAGES) & 1);
               tc_fence_after();
               if (kc == 0) GS_STAMP(1, t * 16 + 1 + jb * 2);
-              const uint32_t a_hi = a_hi0 + kc * GS_CHUNK, a_lo = a_lo0 + kc * GS_CHUNK;
+              const uint32_t a_hi = tmem_base + (uint32_t)(kc * 32), a_lo = a_hi + GS_F_ALO;
               const uint32_t b_hi = smem_u32(sB + (size_t)s * GS_FWD_STAGE), b_lo = b_hi + GS_FWD_STAGE / 2;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint32_t ko = k * 32;
-                umma_tf32(tmem_d, umma_desc_k_sw128(a_lo + ko), umma_desc_k_sw128(b_hi + ko), idesc, (kc | k) ? 1u : 0u);
-                umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_lo + ko), idesc, 1u);
-                umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_hi + ko), idesc, 1u);
+                umma_tf32_ts(tmem_d, a_lo + k * 8, umma_desc_k_sw128(b_hi + ko), idesc, (kc | k) ? 1u : 0u);
+                umma_tf32_ts(tmem_d, a_hi + k * 8, umma_desc_k_sw128(b_lo + ko), idesc, 1u);
+                umma_tf32_ts(tmem_d, a_hi + k * 8, umma_desc_k_sw128(b_hi + ko), idesc, 1u);
               }
               umma_commit(&b_empty[s]);
             }
-            umma_commit(&acc_full[jb]);
+            umma_commit(&acc_full[acc]);
             GS_STAMP(1, t * 16 + 2 + jb * 2);
           }
         }
       }
     } else if (warp == GS_GATE_WARPS + 2) {
-      // ============ L2 prefetch of the next timestep's input pre-activations (one contiguous block per tile) ============
-      l2_prefetch(p.gi + tile_row0 * (3 * kH), tile_rows * 3 * kH * 4, lane);
-      for (int t = 0; t + 1 < T; ++t) {
-        while (*progress < t + 1) __nanosleep(256);  // step t has started
-        l2_prefetch(p.gi + ((int64_t)(t + 1) * p.Rs + tile_row0) * (3 * kH), tile_rows * 3 * kH * 4, lane);
+      // ============ TMA loader of the input pre-activations: the gi columns of block (t, jb + 1) land while block (t, jb) is computed ====
+      if (lane == 0) {
+        for (int n = 0; n < 4 * T; ++n) {
+          const int t = n >> 2, jb = n & 3;
+          mbar_wait(in_empty, ((uint32_t)n & 1u) ^ 1u);
+          mbar_expect_tx(in_full, 3u * (uint32_t)p.rpt * 128u);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) tma_load_3d(sIn + g * GS_CHUNK, &om.gi, g * kH + 32 * jb, (int)tile_row0, t, in_full);
+        }
       }
     }
   } else {
@@ -259,38 +343,42 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {
       load_patch(&h[8 * jb], p.HU, kH, 32 * jb + 8 * cq, gg);
-      store_patch_split(sAhi + jb * GS_CHUNK, sAlo + jb * GS_CHUNK, 8 * cq, &h[8 * jb], gg);
+      tmem_st_patch_split(tmem_lane + (uint32_t)(32 * jb + 8 * cq), tmem_lane + GS_F_ALO + (uint32_t)(32 * jb + 8 * cq), &h[8 * jb]);
       bh[2 * jb] = p.bhn[32 * jb + 8 * cq + 2 * gg.m];
       bh[2 * jb + 1] = p.bhn[32 * jb + 8 * cq + 2 * gg.m + 1];
     }
-    fence_proxy_async();
+    tmem_st_wait();
+    tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(a_ready);
 
     for (int t = 0; t < T; ++t) {
-      if (threadIdx.x == 0) *progress = t + 1;
-      const int64_t slab = (int64_t)t * p.Rs;
       bool keep[4];  // row is live and not reset before the next step
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr)
         keep[rr] = gg.valid[rr] && !((t + 1 < T) && p.done[(int64_t)(t + 1) * p.N + gg.grow[rr] / p.A]);
 #pragma unroll
       for (int jb = 0; jb < 4; ++jb) {
-        const int j0 = 32 * jb + 8 * cq;
         float gi_r[8], gi_z[8], gi_n[8];
-        load_patch(gi_r, p.gi + slab * (3 * kH), 3 * kH, j0, gg);
-        load_patch(gi_z, p.gi + slab * (3 * kH), 3 * kH, kH + j0, gg);
-        load_patch(gi_n, p.gi + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
+        mbar_wait(in_full, (uint32_t)(t * 4 + jb) & 1u);
+        unstage_patch(gi_r, sIn + 0 * GS_CHUNK, 8 * cq, gg);
+        unstage_patch(gi_z, sIn + 1 * GS_CHUNK, 8 * cq, gg);
+        unstage_patch(gi_n, sIn + 2 * GS_CHUNK, 8 * cq, gg);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_empty);  // the loader may fetch the next block's columns
         if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 0);
-        mbar_wait(&acc_full[jb], t & 1);
+        mbar_wait(&acc_full[jb & 1], (uint32_t)(t * 2 + (jb >> 1)) & 1u);
         tc_fence_after();
         if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 1);
         uint32_t ar[8], az[8], an[8];
-        const uint32_t tcol = tmem_lane + (uint32_t)(jb * 96 + 8 * cq);
+        const uint32_t tcol = tmem_lane + GS_F_ACC + (uint32_t)((jb & 1) * 96 + 8 * cq);
         tmem_ld_patch_nowait(tcol, ar);
         tmem_ld_patch_nowait(tcol + 32, az);
         tmem_ld_patch_nowait(tcol + 64, an);
         tmem_ld_wait();
+        tc_fence_before();  // this warp's part of the accumulator is in registers: hand the buffer back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[jb & 1]);
         if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 2);
         float y_[8];
 #pragma unroll
@@ -309,19 +397,34 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             h[8 * jb + i] = keep[rr] ? hn : 0.0f;
           }
         if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 3);
-        store_patch(gi_r, p.rzn + slab * (3 * kH), 3 * kH, j0, gg);
-        store_patch(gi_z, p.rzn + slab * (3 * kH), 3 * kH, kH + j0, gg);
-        store_patch(gi_n, p.rzn + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
-        store_patch(reinterpret_cast<const float*>(ar), p.ghn + slab * kH, kH, j0, gg);
-        store_patch(y_, p.Y + slab * kH, kH, j0, gg);
-        store_patch(&h[8 * jb], p.HU + (slab + p.Rs) * kH, kH, j0, gg);
+        if (threadIdx.x == 0) bulk_wait_read<0>();  // the previous block's bulk stores have read the staging boxes
+        named_bar_sync(1, GS_GATE_THREADS);
+        stage_patch(sOut + 0 * GS_CHUNK, 8 * cq, gi_r, gg);
+        stage_patch(sOut + 1 * GS_CHUNK, 8 * cq, gi_z, gg);
+        stage_patch(sOut + 2 * GS_CHUNK, 8 * cq, gi_n, gg);
+        stage_patch(sOut + 3 * GS_CHUNK, 8 * cq, reinterpret_cast<const float*>(ar), gg);
+        stage_patch(sOut + 4 * GS_CHUNK, 8 * cq, y_, gg);
+        stage_patch(sOut + 5 * GS_CHUNK, 8 * cq, &h[8 * jb], gg);
+        fence_proxy_async();
+        named_bar_sync(1, GS_GATE_THREADS);
+        if (threadIdx.x == 0) {
+          const int r0 = (int)tile_row0;
+          tma_store_3d(&om.rzn, sOut + 0 * GS_CHUNK, 32 * jb, r0, t);
+          tma_store_3d(&om.rzn, sOut + 1 * GS_CHUNK, kH + 32 * jb, r0, t);
+          tma_store_3d(&om.rzn, sOut + 2 * GS_CHUNK, 2 * kH + 32 * jb, r0, t);
+          tma_store_3d(&om.ghn, sOut + 3 * GS_CHUNK, 32 * jb, r0, t);
+          tma_store_3d(&om.Y, sOut + 4 * GS_CHUNK, 32 * jb, r0, t);
+          tma_store_3d(&om.HU, sOut + 5 * GS_CHUNK, 32 * jb, r0, t + 1);
+          bulk_commit();
+        }
         if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 4);
       }
       if (t + 1 < T) {
-        // every MMA of this step has completed (acc_full[3] was observed): the A operand may be replaced
+        // every MMA of this step has completed (the last block's acc_full was observed): the A operand may be replaced
 #pragma unroll
-        for (int jb = 0; jb < 4; ++jb) store_patch_split(sAhi + jb * GS_CHUNK, sAlo + jb * GS_CHUNK, 8 * cq, &h[8 * jb], gg);
-        fence_proxy_async();
+        for (int jb = 0; jb < 4; ++jb)
+          tmem_st_patch_split(tmem_lane + (uint32_t)(32 * jb + 8 * cq), tmem_lane + GS_F_ALO + (uint32_t)(32 * jb + 8 * cq), &h[8 * jb]);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);  // one arrival per warp: 512 serialized shared-memory arrivals cost microseconds
@@ -329,6 +432,7 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
       }
     }
   }
+  if (threadIdx.x == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == GS_GATE_WARPS) {
@@ -562,10 +666,14 @@ int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const flo
   if (once_per_device(ONCE_GRU_FWD))
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
   const int rpt = gru_rows_per_tile(Rs);
+  GruOutMaps om;
+  if (!tc_make_map3(&om.gi, gi, T, Rs, 3 * kH, rpt) || !tc_make_map3(&om.rzn, rzn, T, Rs, 3 * kH, rpt) || !tc_make_map3(&om.ghn, ghn, T, Rs, kH, rpt) || !tc_make_map3(&om.Y, Y, T, Rs, kH, rpt) ||
+      !tc_make_map3(&om.HU, HU, T + 1, Rs, kH, rpt))
+    return MAGPO_ERR_ARG;
   GruFwdArgs a{g_gru_dbg, T, N, A, Rs, rpt, gi, bhn, done, rzn, ghn, Y, HU};
   // per row and step: 3xTF32 MMAs are the pipe work; bytes: gi 1536 read, rzn+ghn+Y+HU 3072 written
   ProfScope ps(PROF_GRU, s, 4608.0 * (double)Rs * T);
-  gru_scan_fwd_kernel<<<(unsigned)ceil_div(Rs, rpt), GS_THREADS, GS_SMEM, s>>>(tmh, tml, a);
+  gru_scan_fwd_kernel<<<(unsigned)ceil_div(Rs, rpt), GS_THREADS, GS_SMEM, s>>>(tmh, tml, om, a);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }

@@ -38,6 +38,8 @@ bool tc_tn_supported(int64_t M, int N, int K, const float* X, int ldx, const flo
 int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw);
 // TMA map (CUtensorMap*) of a row-major fp32 [rows, cols] matrix (leading dimension ld): boxes of [box_rows x 32 floats], 128B swizzle
 bool tc_make_map(void* tensor_map, const float* ptr, int64_t rows, int cols, int ld, int box_rows);
+// the same for a contiguous [T, rows, cols] tensor: boxes of [1, box_rows, 32 floats] that clip at `rows`
+bool tc_make_map3(void* tensor_map, const float* ptr, int64_t T, int64_t rows, int cols, int box_rows);
 int gemm_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, const float* dY, int ldy, float* dW,
             int ldw);
 // ---- chain_fwd.cu: fused row chains of the guider's training forward (persistent tcgen05 kernels, A operands in tensor memory)
