@@ -35,7 +35,6 @@ constexpr int GS_STAGES = 4;       // backward ring
 constexpr int GS_FWD_STAGES = 3;   // forward ring (24 KiB pieces)
 constexpr int GS_IN_BOXES = 3;     // staging of one block's input pre-activations (r, z, n columns): 3 x [128 rows x 32 floats]
 constexpr int GS_OUT_BOXES = 6;    // staging of one block's saved activations: 6 x [128 rows x 32 floats]
-constexpr int GS_BWD_STAGES = 6;   // backward ring (32 KiB pieces)
 // forward TMEM columns: A hi [0,128), A lo [128,256), two accumulators of 96 at 256 / 352
 constexpr uint32_t GS_F_ALO = 128, GS_F_ACC = 256;
 // backward TMEM columns: A slots (gate r, z, n of a block) hi [0,96), lo [96,192), two carry accumulators of 128 at 192 / 320
@@ -441,6 +440,10 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
   }
 }
 
+struct GruBwdMaps {  // [T(+1), Rs, cols] saved activations, boxes of [1, rpt, 32]
+  CUtensorMap dY, rzn, ghn, HU;
+};
+
 struct GruBwdArgs {
   int T, N, A;
   int64_t Rs;
@@ -455,26 +458,27 @@ struct GruBwdArgs {
 };
 
 __global__ void __launch_bounds__(GS_THREADS, 1)
-gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const GruBwdArgs p) {
+gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                    const __grid_constant__ GruBwdMaps im, const GruBwdArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = base;                         // 3 slots (gate r, z, n of the current block) x {hi 16K, lo 16K}
-  uint8_t* sB = sA + 3 * GS_BWD_STAGE;        // GS_STAGES x {hi 16K, lo 16K}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + GS_STAGES * GS_BWD_STAGE);
+  uint8_t* sB = base;                         // GS_STAGES x {hi 16K, lo 16K}
+  uint8_t* sIn = sB + GS_STAGES * GS_BWD_STAGE;  // 6 staging boxes: dY, r, z, n, gh_n, hu columns of the next block (TMA-loaded)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + 6 * GS_CHUNK);
   uint64_t* b_full = bars;
   uint64_t* b_empty = bars + GS_STAGES;
-  uint64_t* a_full = bars + 2 * GS_STAGES;   // the three slots of a block are handed over together
+  uint64_t* a_full = bars + 2 * GS_STAGES;   // the three A slots of a block (tensor memory) are handed over together
   uint64_t* a_empty = a_full + 1;
   uint64_t* acc_full = a_empty + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
-  volatile int* progress = reinterpret_cast<volatile int*>(tmem_ptr + 1);  // timesteps started by the gate warps (prefetch throttle)
+  uint64_t* in_full = acc_full + 1;
+  uint64_t* in_empty = in_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(in_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T;
   // a CTA owns p.rpt (32, 64 or 128) rows of its 128-row MMA tile: with few rows, spreading them over more SMs divides the
   // per-SM stream of saved activations; the unused rows of the tile are zero operands
   const int64_t tile_row0 = (int64_t)blockIdx.x * p.rpt;
-  const int64_t tile_rows = p.Rs - tile_row0 < p.rpt ? p.Rs - tile_row0 : p.rpt;
 
   if (warp == GS_GATE_WARPS + 1 && lane == 0) {
     for (int i = 0; i < GS_STAGES; ++i) {
@@ -484,10 +488,11 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     mbar_init(a_full, GS_GATE_WARPS);
     mbar_init(a_empty, 1);
     mbar_init(acc_full, 1);
-    *progress = 0;
+    mbar_init(in_full, 1);
+    mbar_init(in_empty, GS_GATE_WARPS);
     fence_barrier_init();
   } else if (warp == GS_GATE_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -518,7 +523,7 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         const uint32_t idesc = idesc_tf32(128);
         uint32_t it = 0;
         for (int si = 0; si + 1 < T; ++si) {
-          const uint32_t tmem_d = tmem_base + (uint32_t)((si & 1) * 128);
+          const uint32_t tmem_d = tmem_base + GS_B_ACC + (uint32_t)((si & 1) * 128);
           for (int jb = 0; jb < 4; ++jb) {
             const uint32_t n = (uint32_t)si * 4 + jb;
             mbar_wait(a_full, n & 1);
@@ -526,14 +531,14 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
               const int s = it % GS_STAGES;
               mbar_wait(&b_full[s], (it / GS_STAGES) & 1);
               tc_fence_after();
-              const uint32_t a_hi = smem_u32(sA + (size_t)g * GS_BWD_STAGE), a_lo = a_hi + GS_CHUNK;
+              const uint32_t a_hi = tmem_base + (uint32_t)(g * 32), a_lo = a_hi + GS_B_ALO;
               const uint32_t b_hi = smem_u32(sB + (size_t)s * GS_BWD_STAGE), b_lo = b_hi + GS_CHUNK;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint32_t ko = k * 32;
-                umma_tf32(tmem_d, umma_desc_k_sw128(a_lo + ko), umma_desc_k_sw128(b_hi + ko), idesc, (jb | g | k) ? 1u : 0u);
-                umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_lo + ko), idesc, 1u);
-                umma_tf32(tmem_d, umma_desc_k_sw128(a_hi + ko), umma_desc_k_sw128(b_hi + ko), idesc, 1u);
+                umma_tf32_ts(tmem_d, a_lo + k * 8, umma_desc_k_sw128(b_hi + ko), idesc, (jb | g | k) ? 1u : 0u);
+                umma_tf32_ts(tmem_d, a_hi + k * 8, umma_desc_k_sw128(b_lo + ko), idesc, 1u);
+                umma_tf32_ts(tmem_d, a_hi + k * 8, umma_desc_k_sw128(b_hi + ko), idesc, 1u);
               }
               umma_commit(&b_empty[s]);
             }
@@ -543,14 +548,20 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         }
       }
     } else if (warp == GS_GATE_WARPS + 2) {
-      // ===================== L2 prefetch of the saved activations, about one timestep ahead of the gates =====================
-      for (int si = 0; si < T; ++si) {
-        while (*progress < si) __nanosleep(256);  // step si-1 has started
-        const int64_t r0 = (int64_t)(T - 1 - si) * p.Rs + tile_row0;
-        l2_prefetch(p.dY + r0 * kH, tile_rows * kH * 4, lane);
-        l2_prefetch(p.rzn + r0 * (3 * kH), tile_rows * 3 * kH * 4, lane);
-        l2_prefetch(p.ghn + r0 * kH, tile_rows * kH * 4, lane);
-        l2_prefetch(p.HU + r0 * kH, tile_rows * kH * 4, lane);
+      // ============ TMA loader of the saved activations: the six column blocks of (step, jb + 1) land while (step, jb) is computed ======
+      if (lane == 0) {
+        for (int n = 0; n < 4 * T; ++n) {
+          const int t = T - 1 - (n >> 2), jb = n & 3;
+          mbar_wait(in_empty, ((uint32_t)n & 1u) ^ 1u);
+          mbar_expect_tx(in_full, 6u * (uint32_t)p.rpt * 128u);
+          const int r0 = (int)tile_row0;
+          tma_load_3d(sIn + 0 * GS_CHUNK, &im.dY, 32 * jb, r0, t, in_full);
+          tma_load_3d(sIn + 1 * GS_CHUNK, &im.rzn, 32 * jb, r0, t, in_full);
+          tma_load_3d(sIn + 2 * GS_CHUNK, &im.rzn, kH + 32 * jb, r0, t, in_full);
+          tma_load_3d(sIn + 3 * GS_CHUNK, &im.rzn, 2 * kH + 32 * jb, r0, t, in_full);
+          tma_load_3d(sIn + 4 * GS_CHUNK, &im.ghn, 32 * jb, r0, t, in_full);
+          tma_load_3d(sIn + 5 * GS_CHUNK, &im.HU, 32 * jb, r0, t, in_full);
+        }
       }
     }
   } else {
@@ -565,25 +576,27 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
 
     for (int si = 0; si < T; ++si) {
       const int t = T - 1 - si;
-      if (threadIdx.x == 0) *progress = si + 1;
       const int64_t slab = (int64_t)t * p.Rs;
       const bool has_carry = si > 0;
       bool use_carry[4];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr)
         use_carry[rr] = has_carry && gg.valid[rr] && !p.done[(int64_t)(t + 1) * p.N + gg.grow[rr] / p.A];
-      const uint32_t tmem_acc = tmem_lane + (uint32_t)(((si + 1) & 1) * 128);  // written by the MMAs of step si-1
+      const uint32_t tmem_acc = tmem_lane + GS_B_ACC + (uint32_t)(((si + 1) & 1) * 128);  // written by the MMAs of step si-1
       const bool feed = t > 0;  // the carry of step 0 goes nowhere
 #pragma unroll
       for (int jb = 0; jb < 4; ++jb) {
         const int j0 = 32 * jb + 8 * cq;
         float dy[8], r_[8], z_[8], n_[8], gh_[8], hu[8];
-        load_patch(dy, p.dY + slab * kH, kH, j0, gg);
-        load_patch(r_, p.rzn + slab * (3 * kH), 3 * kH, j0, gg);
-        load_patch(z_, p.rzn + slab * (3 * kH), 3 * kH, kH + j0, gg);
-        load_patch(n_, p.rzn + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
-        load_patch(gh_, p.ghn + slab * kH, kH, j0, gg);
-        load_patch(hu, p.HU + slab * kH, kH, j0, gg);
+        mbar_wait(in_full, (uint32_t)(si * 4 + jb) & 1u);
+        unstage_patch(dy, sIn + 0 * GS_CHUNK, 8 * cq, gg);
+        unstage_patch(r_, sIn + 1 * GS_CHUNK, 8 * cq, gg);
+        unstage_patch(z_, sIn + 2 * GS_CHUNK, 8 * cq, gg);
+        unstage_patch(n_, sIn + 3 * GS_CHUNK, 8 * cq, gg);
+        unstage_patch(gh_, sIn + 4 * GS_CHUNK, 8 * cq, gg);
+        unstage_patch(hu, sIn + 5 * GS_CHUNK, 8 * cq, gg);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_empty);  // the loader may fetch the next block's columns
         uint32_t acc[8];
         if (has_carry) {
           if (jb == 0) {
@@ -616,10 +629,11 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         if (feed) {
           const uint32_t n = (uint32_t)si * 4 + jb;
           mbar_wait(a_empty, (n & 1) ^ 1);
-          store_patch_split(sA, sA + GS_CHUNK, 8 * cq, r_, gg);
-          store_patch_split(sA + GS_BWD_STAGE, sA + GS_BWD_STAGE + GS_CHUNK, 8 * cq, z_, gg);
-          store_patch_split(sA + 2 * GS_BWD_STAGE, sA + 2 * GS_BWD_STAGE + GS_CHUNK, 8 * cq, gh_, gg);
-          fence_proxy_async();
+          tc_fence_after();
+          tmem_st_patch_split(tmem_lane + (uint32_t)(8 * cq), tmem_lane + GS_B_ALO + (uint32_t)(8 * cq), r_);
+          tmem_st_patch_split(tmem_lane + (uint32_t)(32 + 8 * cq), tmem_lane + GS_B_ALO + (uint32_t)(32 + 8 * cq), z_);
+          tmem_st_patch_split(tmem_lane + (uint32_t)(64 + 8 * cq), tmem_lane + GS_B_ALO + (uint32_t)(64 + 8 * cq), gh_);
+          tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full);
@@ -631,7 +645,7 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
   __syncthreads();
   if (warp == GS_GATE_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -687,9 +701,13 @@ int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const flo
   if (once_per_device(ONCE_GRU_BWD))
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
   const int rpt = gru_rows_per_tile(Rs);
+  GruBwdMaps im;
+  if (!tc_make_map3(&im.dY, dY, T, Rs, kH, rpt) || !tc_make_map3(&im.rzn, rzn, T, Rs, 3 * kH, rpt) || !tc_make_map3(&im.ghn, ghn, T, Rs, kH, rpt) ||
+      !tc_make_map3(&im.HU, HU, T + 1, Rs, kH, rpt))
+    return MAGPO_ERR_ARG;
   GruBwdArgs a{T, N, A, Rs, rpt, dY, rzn, ghn, HU, done, dgi, dgh};
   ProfScope ps(PROF_GRU, s, 6144.0 * (double)Rs * T);
-  gru_scan_bwd_kernel<<<(unsigned)ceil_div(Rs, rpt), GS_THREADS, GS_SMEM, s>>>(tmh, tml, a);
+  gru_scan_bwd_kernel<<<(unsigned)ceil_div(Rs, rpt), GS_THREADS, GS_SMEM, s>>>(tmh, tml, im, a);
   MAGPO_LAUNCH_OK();
   return MAGPO_OK;
 }
