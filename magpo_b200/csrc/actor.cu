@@ -182,7 +182,7 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
   float* dgi = w.gi;
   const float *wh_hi = nullptr, *wh_lo = nullptr;
   const bool scan = T > 1 && tc_enabled() && !g_force_stepwise && tc_lookup(p.Wh, &wh_hi, &wh_lo);
-  if (scan) MAGPO_TRY(gru_scan_bwd(s, T, N, A, w.dB, w.rzn, w.ghn, w.HU, done, wh_hi, wh_lo, dgi, w.dgh));
+  if (scan) MAGPO_TRY(gru_scan_bwd(s, T, N, A, w.dB, w.rzn, w.ghn, w.HU, done, wh_hi, wh_lo, dgi, w.dgh, g.bi, g.bhn));  // bias sums inside
   for (int t = T - 1; t >= 0 && !scan; --t) {
     const size_t o1 = (size_t)t * Rs * kH, o3 = (size_t)t * Rs * 3 * kH;
     const bool last = (t == T - 1);
@@ -197,9 +197,9 @@ int actor_backward(cudaStream_t s, const ActorP& p, const ActorT& pt, int T, int
       MAGPO_TRY(gemm_nn(s, Rs, kH, 3 * kH, w.dgh + o3, 3 * kH, wref(pt.WhT, kH, p.Wh, 3 * kH), nullptr, w.carry, kH, GEMM_ACCUMULATE));
   }
   MAGPO_TRY(gemm_tn(s, R, 3 * kH, kH, w.HU, kH, w.dgh, 3 * kH, g.Wh, 3 * kH));
-  MAGPO_TRY(colsum(s, R, kH, w.dgh + 2 * kH, 3 * kH, g.bhn));
+  if (!scan) MAGPO_TRY(colsum(s, R, kH, w.dgh + 2 * kH, 3 * kH, g.bhn));
   MAGPO_TRY(gemm_tn(s, R, 3 * kH, kH, w.e, kH, dgi, 3 * kH, g.Wi, 3 * kH));
-  MAGPO_TRY(colsum(s, R, 3 * kH, dgi, 3 * kH, g.bi));
+  if (!scan) MAGPO_TRY(colsum(s, R, 3 * kH, dgi, 3 * kH, g.bi));
   MAGPO_TRY(gemm_nn(s, R, kH, 3 * kH, dgi, 3 * kH, wref(pt.WiT, kH, p.Wi, 3 * kH), nullptr, w.dA, kH, 0));  // dA = dL/de (pre-relu mask next)
   if (thin_k_ok(d, kH, kH, w.dA, w.dA, kH)) {  // relu mask of the pre torso applied on the fly
     MAGPO_TRY(thin_k_bwd(s, R, d, kH, agents_view, d, w.dA, kH, w.e, g.pre_w, kH, g.pre_b));

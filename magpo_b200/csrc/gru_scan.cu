@@ -455,6 +455,8 @@ struct GruBwdArgs {
   const uint8_t* done;  // [T, N]
   float* dgi;           // [T, Rs, 384]  [da_r, da_z, da_n]
   float* dgh;           // [T, Rs, 384]  [da_r, da_z, da_n * r]
+  float* dbi;           // [384] += column sums of dgi (the input-side bias gradient), optional
+  float* dbhn;          // [128] += column sums of da_n * r (the hidden-side bias gradient of the candidate gate), optional
 };
 
 __global__ void __launch_bounds__(GS_THREADS, 1)
@@ -464,7 +466,8 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = base;                         // GS_STAGES x {hi 16K, lo 16K}
   uint8_t* sIn = sB + GS_STAGES * GS_BWD_STAGE;  // 6 staging boxes: dY, r, z, n, gh_n, hu columns of the next block (TMA-loaded)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + 6 * GS_CHUNK);
+  float* sCol = reinterpret_cast<float*>(sIn + 6 * GS_CHUNK);  // [4][128] column sums of da_r, da_z, da_n, da_n * r over this CTA's rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 4 * kH);
   uint64_t* b_full = bars;
   uint64_t* b_empty = bars + GS_STAGES;
   uint64_t* a_full = bars + 2 * GS_STAGES;   // the three A slots of a block (tensor memory) are handed over together
@@ -491,7 +494,11 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     mbar_init(in_full, 1);
     mbar_init(in_empty, GS_GATE_WARPS);
     fence_barrier_init();
-  } else if (warp == GS_GATE_WARPS) {
+  }
+  if (threadIdx.x < 4 * kH) sCol[threadIdx.x] = 0.f;
+  // the layout fills the 227 KiB to the last kilobyte: it relies on the (declared) 1 KiB alignment of the dynamic shared window
+  if (reinterpret_cast<uint8_t*>(tmem_ptr + 1) > smem_raw + GS_SMEM) __trap();
+  if (warp == GS_GATE_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -620,6 +627,28 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             cz[8 * jb + i] = dh * z;
             r_[i] = dar; z_[i] = daz; n_[i] = dan; gh_[i] = dan * r;  // reuse as output registers
           }
+        if (p.dbi) {
+          // bias gradients: this thread's 4 rows in registers, the 8 lanes that share its two columns by shuffles, one shared-memory
+          // add per column and warp (the column sums of dgi / dgh used to be two more passes over 2 GB)
+          float cs[8];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            cs[e] = r_[vidx(0, e)] + r_[vidx(1, e)] + r_[vidx(2, e)] + r_[vidx(3, e)];
+            cs[2 + e] = z_[vidx(0, e)] + z_[vidx(1, e)] + z_[vidx(2, e)] + z_[vidx(3, e)];
+            cs[4 + e] = n_[vidx(0, e)] + n_[vidx(1, e)] + n_[vidx(2, e)] + n_[vidx(3, e)];
+            cs[6 + e] = gh_[vidx(0, e)] + gh_[vidx(1, e)] + gh_[vidx(2, e)] + gh_[vidx(3, e)];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 4);
+            cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+            cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+          }
+          if (lane < 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(&sCol[(i >> 1) * kH + j0 + 2 * lane + (i & 1)], cs[i]);
+          }
+        }
         store_patch(r_, p.dgi + slab * (3 * kH), 3 * kH, j0, gg);
         store_patch(z_, p.dgi + slab * (3 * kH), 3 * kH, kH + j0, gg);
         store_patch(n_, p.dgi + slab * (3 * kH), 3 * kH, 2 * kH + j0, gg);
@@ -643,6 +672,11 @@ gru_scan_bwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbi && threadIdx.x < 4 * kH) {
+    const float v = sCol[threadIdx.x];
+    if (threadIdx.x < 3 * kH) atomicAdd(p.dbi + threadIdx.x, v);
+    else if (p.dbhn) atomicAdd(p.dbhn + (threadIdx.x - 3 * kH), v);
+  }
   if (warp == GS_GATE_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -694,7 +728,7 @@ int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const flo
 
 // Wh_hi/lo: TF32 images of W_h [128, 384] (un-transposed).
 int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const float* rzn, const float* ghn, const float* HU,
-                 const uint8_t* done, const float* Wh_hi, const float* Wh_lo, float* dgi, float* dgh) {
+                 const uint8_t* done, const float* Wh_hi, const float* Wh_lo, float* dgi, float* dgh, float* dbi, float* dbhn) {
   const int64_t Rs = (int64_t)N * A;
   CUtensorMap tmh, tml;
   if (!tc_make_map(&tmh, Wh_hi, kH, 3 * kH, 3 * kH, 128) || !tc_make_map(&tml, Wh_lo, kH, 3 * kH, 3 * kH, 128)) return MAGPO_ERR_ARG;
@@ -705,7 +739,7 @@ int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const flo
   if (!tc_make_map3(&im.dY, dY, T, Rs, kH, rpt) || !tc_make_map3(&im.rzn, rzn, T, Rs, 3 * kH, rpt) || !tc_make_map3(&im.ghn, ghn, T, Rs, kH, rpt) ||
       !tc_make_map3(&im.HU, HU, T + 1, Rs, kH, rpt))
     return MAGPO_ERR_ARG;
-  GruBwdArgs a{T, N, A, Rs, rpt, dY, rzn, ghn, HU, done, dgi, dgh};
+  GruBwdArgs a{T, N, A, Rs, rpt, dY, rzn, ghn, HU, done, dgi, dgh, dbi, dbhn};
   ProfScope ps(PROF_GRU, s, 6144.0 * (double)Rs * T);
   gru_scan_bwd_kernel<<<(unsigned)ceil_div(Rs, rpt), GS_THREADS, GS_SMEM, s>>>(tmh, tml, im, a);
   MAGPO_LAUNCH_OK();

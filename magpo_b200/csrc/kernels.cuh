@@ -67,7 +67,8 @@ int chain_tail_fwd(cudaStream_t s, int64_t R, const float* hmid, const float* re
 int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const float* WhT_hi, const float* WhT_lo, const float* bhn,
                  const uint8_t* done, float* rzn, float* ghn, float* Y, float* HU);
 int gru_scan_bwd(cudaStream_t s, int T, int N, int A, const float* dY, const float* rzn, const float* ghn, const float* HU,
-                 const uint8_t* done, const float* Wh_hi, const float* Wh_lo, float* dgi, float* dgh);
+                 const uint8_t* done, const float* Wh_hi, const float* Wh_lo, float* dgi, float* dgh, float* dbi /* [384] += colsum(dgi), optional */,
+                 float* dbhn /* [128] += colsum(dgh[:, 256:]), optional */);
 int colsum(cudaStream_t s, int64_t M, int N, const float* dY, int ldy, float* db);
 int transpose(cudaStream_t s, int R, int Cc, const float* in, float* out);
 
