@@ -152,9 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue =====================
-    const int et = threadIdx.x - 128;     // 0..127
     const int sub = warp & 3;             // TMEM sub-partition of this warp: lanes [32*sub, 32*sub+32)
-    const int row = sub * 32 + lane;      // row of the tile this thread owns
     const bool relu = p.flags & GEMM_RELU, accumulate = p.flags & GEMM_ACCUMULATE;
     const int nslab = p.BN / 32;
     const int acc_cols = p.stacked ? 2 * p.BN : p.BN;
@@ -177,10 +175,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        uint8_t* buf = sOut + (size_t)(slab_it & 1) * TC_CHUNK_BYTES;
-        if (et == 0) bulk_wait_read<1>();  // the store that last used this buffer has finished reading it
-        named_bar_sync(1, 128);
-        float4* dst_row = reinterpret_cast<float4*>(buf + (size_t)row * 128);
+        // every warp stages and stores its own 32 rows ([32 x 32 floats] boxes): no barrier between the epilogue warps
+        uint8_t* buf = sOut + (size_t)(slab_it & 1) * TC_CHUNK_BYTES + (size_t)sub * 4096;
+        if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer has finished reading it
+        __syncwarp();
+        float4* dst_row = reinterpret_cast<float4*>(buf + (size_t)lane * 128);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o;
@@ -189,18 +188,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           o.z = __uint_as_float(v[4 * j + 2]) + sBias[sl * 32 + 4 * j + 2];
           o.w = __uint_as_float(v[4 * j + 3]) + sBias[sl * 32 + 4 * j + 3];
           if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          dst_row[j ^ (row & 7)] = o;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+          dst_row[j ^ (lane & 7)] = o;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
         }
         fence_proxy_async();
-        named_bar_sync(1, 128);
-        if (et == 0) {
-          if (accumulate) tma_reduce_add_2d(&tmY, buf, n0 + sl * 32, tile * TC_BM);
-          else tma_store_2d(&tmY, buf, n0 + sl * 32, tile * TC_BM);
+        __syncwarp();
+        if (lane == 0) {
+          if (accumulate) tma_reduce_add_2d(&tmY, buf, n0 + sl * 32, tile * TC_BM + sub * 32);
+          else tma_store_2d(&tmY, buf, n0 + sl * 32, tile * TC_BM + sub * 32);
           bulk_commit();
         }
       }
     }
-    if (et == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   } else if (warp >= 8) {
     // ===================== converters: lo = x - tf32_trunc(x) =====================
     // The landed fp32 chunk is itself the hi operand: kind::tf32 reads the top 19 bits of each word, i.e. truncates. Only the
@@ -535,7 +534,7 @@ int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
   p.num_row_tiles = (int)ceil_div(M, TC_BM);
   CUtensorMap tmX, tmBh, tmBl, tmY;
   if (!make_map(&tmX, X, M, K, ldx, TC_BM) || !make_map(&tmBh, Bhi, N, K, ldb, p.BN) || !make_map(&tmBl, Blo, N, K, ldb, p.BN) ||
-      !make_map(&tmY, Y, M, N, ldy, TC_BM))
+      !make_map(&tmY, Y, M, N, ldy, 32))
     return MAGPO_ERR_ARG;
   if (once_per_device(ONCE_GEMM_TC))
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));

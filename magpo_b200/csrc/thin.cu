@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256)
 thin_k_fwd_kernel(int64_t R, int K, const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
                   const float* __restrict__ bias, float* __restrict__ Y, int ldy, int relu) {
   constexpr int ROWS = 256 / NQ;
-  constexpr int UN = KMAX <= 4 ? 4 : (KMAX <= 8 ? 2 : 1);
+  constexpr int UN = KMAX <= 4 ? 4 : 2;  // rows in flight per thread (KMAX = 16: 2 x 16 inputs next to the 16 float4 weights)
   const int c = threadIdx.x % NQ, rs = threadIdx.x / NQ;
   float4 w[KMAX];
 #pragma unroll

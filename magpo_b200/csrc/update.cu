@@ -365,7 +365,12 @@ int magpo_minibatch_grads(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetC
   // lie behind it) as soon as the learner's backward is done — on its own stream, under the guider's remaining backward — and the
   // guider's half at the end. Every rank issues the two all-reduces in this order.
   MagpoComm* comm = reduce_grads ? ctx().comm : nullptr;
-  if (comm) MAGPO_TRY(comm_allreduce(comm, s2, grads + gp.total, ap.total + 8, 0));
+  static int comm_split = -1;
+  if (comm_split < 0) {
+    const char* e = getenv("MAGPO_COMM_SPLIT");  // experiments: "0" = one all-reduce of the whole buffer after the guider's backward
+    comm_split = !(e && e[0] == '0');
+  }
+  if (comm && comm_split) MAGPO_TRY(comm_allreduce(comm, s2, grads + gp.total, ap.total + 8, 0));
   if (!(skip & 5)) {
     if (general)
       MAGPO_TRY(sable_g_train_backward(sg, net, guider, T, N, mb.agents_view, mb.step_count, mb.done, mb.action, mb.sable_h0.encoder,
@@ -373,11 +378,12 @@ int magpo_minibatch_grads(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetC
     else
       MAGPO_TRY(sable_train_backward(sg, gp, w.gt, b, w.sa, w.dlg, w.dvalue, gg));
   }
-  if (comm) MAGPO_TRY(comm_allreduce(comm, sg, grads, gp.total, 0));
+  if (comm && comm_split) MAGPO_TRY(comm_allreduce(comm, sg, grads, gp.total, 0));
   if (overlap) {
     MAGPO_CUDA_OK(cudaEventRecord(g_side.join, g_side.s));
     MAGPO_CUDA_OK(cudaStreamWaitEvent(s, g_side.join, 0));
   }
+  if (comm && !comm_split) MAGPO_TRY(comm_allreduce(comm, s, grads, gp.total + ap.total + 8, 0));
   return MAGPO_OK;
 }
 
