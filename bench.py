@@ -304,10 +304,22 @@ def run():
             tf = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
             traffic = None
             try:  # DRAM bytes per launch of the same kernel from the committed ncu launch list (profiles/)
-                prof = json.load(open(os.path.join(ROOT, "profiles", "r1_lbf_minibatch_launches.json" if args.env == "lbf" else
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r2_lbf_minibatch_launches.json" if args.env == "lbf" else
                                                   "r1_minibatch_launches.json")))
                 k = prof["kernels"]["gemm_tc_kernel"]
                 traffic = k["dram_bytes"] / k["launches"]
+                if args.env == "lbf" and args.num_envs == 4096:
+                    # time-weighted whole-update line: the ncu DRAM bytes of ONE minibatch (committed launch list) x the P*M minibatches of
+                    # a step over the live, overlapped update time of this run
+                    mb_bytes = sum(v["dram_bytes"] for v in prof["kernels"].values())
+                    n_mb = sysc.ppo_epochs * sysc.num_minibatches
+                    tokens = sysc.rollout_length * (sysc.num_envs * sysc.update_batch_size // sysc.num_minibatches) * lrn.net.n_agents
+                    upd_ms = out["phase_ms"]["update"]
+                    out["roofline_update"] = {
+                        "dram_bytes_per_minibatch": mb_bytes, "launches_per_minibatch": sum(v["launches"] for v in prof["kernels"].values()),
+                        "dram_bytes_per_token_and_pass": mb_bytes / tokens, "update_ms": upd_ms,
+                        "achieved_GBps": mb_bytes * n_mb / (upd_ms * 1e-3) / 1e9, "frac_of_measured_hbm": mb_bytes * n_mb / (upd_ms * 1e-3) / 1e9 / hb,
+                        "source": "profiles/r2_lbf_minibatch_launches.json (ncu dram__bytes_{read,write}.sum of one minibatch) / live update time"}
             except Exception:
                 pass
             out["roofline"] = {"kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32 x3, TMA-fed; all forward and dX GEMMs of both networks)",
@@ -326,6 +338,11 @@ def run():
                 k: {"achieved_GBps": round(brk[k]["work"] / (brk[k]["ms"] * 1e-3) / 1e9, 1) if brk[k]["ms"] else None,
                     "frac_of_measured_hbm": round(brk[k]["work"] / (brk[k]["ms"] * 1e-3) / 1e9 / hb, 4) if brk[k]["ms"] else None}
                 for k in ("gae", "env_step", "rowops", "loss", "optim", "pack", "sample")}
+            cb = C.c_double()
+            lib.magpo_prof_read_bytes(PROF_CATS.index("chain"), C.byref(cb))
+            if brk["chain"]["ms"]:  # the fused row-chain kernels of the guider's forward: algorithmic bytes = saved activations + inputs
+                out["roofline_hbm_kernels"]["chain"] = {"achieved_GBps": round(cb.value / (brk["chain"]["ms"] * 1e-3) / 1e9, 1),
+                                                        "frac_of_measured_hbm": round(cb.value / (brk["chain"]["ms"] * 1e-3) / 1e9 / hb, 4)}
             # "sample" is the rollout's fused per-step Sable kernel (encoder + decoder + sampling): its bytes are the retention
             # state stream (160 KiB per env-step at A = 3) plus observations / actions
             out["roofline_hbm_kernels"]["sable_step"] = out["roofline_hbm_kernels"].pop("sample")

@@ -13,8 +13,9 @@ python tools/profile_update.py --rollout-steps 4 > gpurun_out/pr_plain.log 2>&1 
 ncu $M --log-file gpurun_out/launches_${TAG}_rollout4.csv python tools/profile_update.py --rollout-steps 4 > gpurun_out/pr_ncu.log 2>&1
 for spec in $SPECS; do
   k=${spec%%:*}; s=${spec##*:}
+  extra=""; case "$k" in sable_step_kernel|lbf_step_kernel) extra="--rollout-steps 4";; esac
   timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$k" -s $s -c 1 -f \
-    -o gpurun_out/full_${TAG}_$k python tools/profile_update.py > gpurun_out/ncu_full_$k.log 2>&1
+    -o gpurun_out/full_${TAG}_$k python tools/profile_update.py $extra > gpurun_out/ncu_full_$k.log 2>&1
   tail -1 gpurun_out/ncu_full_$k.log
 done
 ls -la gpurun_out/full_${TAG}_*.ncu-rep
