@@ -238,19 +238,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // MN-major (M/N contiguous) 128B-swizzled UMMA operand whose 8-row groups are the K=8 steps of kind::tf32. Both operands are
 // split into TF32 hi/lo by the converter warps. Each CTA reduces a contiguous slab of rows into one TMEM accumulator and
 // adds it to dW with a TMA reduce-add, so the cross-CTA reduction needs no extra pass.
-constexpr int TN_RC = 32;          // rows per pipeline stage
-constexpr int TN_BOX = TN_RC * 128;  // bytes of one [32 x 32 floats] box
+// rows per pipeline stage: 32, or 64 where the stage stays small (narrow K and N): the per-stage hand-overs (barrier round trips of the
+// producer / converter / MMA roles) cost the same for 16 KiB as for 48 KiB, and the narrow GEMMs were bound by them
 
 struct TnParams {
-  int K, BN, stages, tmem_cols;
+  int K, BN, stages, tmem_cols, rc /* rows per stage */;
   int64_t M, rows_per_cta;
 };
 
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t box_bytes) {
   // 32-bit MN-major operands must use the 128B swizzle with a 32-byte base (UMMA layout type SWIZZLE_128B_BASE32B,
   // TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the atom is 4 K-rows x 128 B, a K=8 step spans two atoms.
   // LBO = stride between 32-float column blocks (one TMA box), SBO = stride between 4-row groups.
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(TN_BOX >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(box_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)1 << 61);
 }
 
@@ -259,6 +259,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   const __grid_constant__ CUtensorMap tmDW, const TnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int TN_RC = p.rc, TN_BOX = TN_RC * 128;  // one [rc rows x 32 floats] box
   const int x_bytes = (p.K / 32) * TN_BOX, y_bytes = (p.BN / 32) * TN_BOX;
   const int raw_bytes = x_bytes + y_bytes;  // per stage: [X hi | dY hi | X lo | dY lo]
   uint8_t* sStage = base;
@@ -318,12 +319,11 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc_fence_after();
           const uint32_t x_hi = smem_u32(sStage + (size_t)s * 2 * raw_bytes);
           const uint32_t y_hi = x_hi + x_bytes, x_lo = x_hi + raw_bytes, y_lo = y_hi + raw_bytes;
-#pragma unroll
           for (int g = 0; g < TN_RC / 8; ++g) {
             const uint32_t go = g * 1024;  // next 8-row group = next K=8 step
-            umma_tf32(tmem_base, umma_desc_mn_sw128(x_lo + go), umma_desc_mn_sw128(y_hi + go), idesc, (it | g) ? 1u : 0u);
-            umma_tf32(tmem_base, umma_desc_mn_sw128(x_hi + go), umma_desc_mn_sw128(y_lo + go), idesc, 1u);
-            umma_tf32(tmem_base, umma_desc_mn_sw128(x_hi + go), umma_desc_mn_sw128(y_hi + go), idesc, 1u);
+            umma_tf32(tmem_base, umma_desc_mn_sw128(x_lo + go, TN_BOX), umma_desc_mn_sw128(y_hi + go, TN_BOX), idesc, (it | g) ? 1u : 0u);
+            umma_tf32(tmem_base, umma_desc_mn_sw128(x_hi + go, TN_BOX), umma_desc_mn_sw128(y_lo + go, TN_BOX), idesc, 1u);
+            umma_tf32(tmem_base, umma_desc_mn_sw128(x_hi + go, TN_BOX), umma_desc_mn_sw128(y_hi + go, TN_BOX), idesc, 1u);
           }
           umma_commit(&empty[s]);
         }
@@ -552,11 +552,18 @@ static bool tn_plan(int N, int K, TnParams* p, uint32_t* smem_bytes) {
   const int cands[] = {256, 192, 128, 96, 64, 32};
   for (int bn : cands) {
     if (N % bn) continue;
-    const uint32_t raw = (uint32_t)(K / 32 + bn / 32) * TN_BOX;
+    static int rc_big = -1;
+    if (rc_big < 0) {
+      const char* e = getenv("MAGPO_TN_ROWS");  // experiments: 32 = always 32 rows per stage
+      rc_big = (e && atoi(e) == 32) ? 32 : 64;
+    }
+    const int rc = (K / 32 + bn / 32) <= 4 ? rc_big : 32;
+    const uint32_t raw = (uint32_t)(K / 32 + bn / 32) * (uint32_t)rc * 128u;
     const uint32_t fixed = 2 * TC_CHUNK_BYTES + 256 + 1024;
     if (fixed + 2 * 2 * raw > TC_SMEM_LIMIT) continue;
     p->K = K;
     p->BN = bn;
+    p->rc = rc;
     p->stages = std::min<int>(TC_MAX_STAGES, (int)((TC_SMEM_LIMIT - fixed) / (2 * raw)));
     int cols = 32;
     while (cols < bn) cols <<= 1;
@@ -583,6 +590,7 @@ int gemm_tc_tn(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx,
   if (!tn_plan(N, K, &p, &smem)) return MAGPO_ERR_UNSUPPORTED;
   p.M = M;
   const int n_tiles = N / p.BN;
+  const int TN_RC = p.rc;
   const int64_t chunks = ceil_div(M, TN_RC);
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(chunks, kNumSMs / n_tiles));
   p.rows_per_cta = ceil_div(chunks, gx) * TN_RC;

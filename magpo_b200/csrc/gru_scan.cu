@@ -10,12 +10,12 @@
 //     (8 stages of the 16 pieces of a step now that the A operand is gone from shared memory);
 //   * accumulators live in tensor memory; the gate math runs straight out of tcgen05.ld registers, fused with the loads of
 //     the batched input-side pre-activations and the stores of everything the backward needs. The gate warps read TMEM with
-//     the 16x256b fragment shape (4 lanes = 32 consecutive bytes of a row), so each of their global accesses covers whole
-//     32-byte sectors; a service warp keeps the next timestep's inputs flowing into L2 with cp.async.bulk.prefetch.
+//     the 16x256b fragment shape; their inputs and (forward) outputs travel through TMA-loaded / bulk-stored staging boxes in shared
+//     memory instead of 8-rows-x-32-B global accesses (the lg_throttle of round 1); a service warp issues the loads one block ahead.
 // Per timestep and tile the forward issues 16 pieces x 12 MMAs (M=128, N=96: the r|z|n columns of one block of 32 hidden
 // units, so that the gates of block jb run while the tensor core works on block jb+1), the backward 12 pieces x 12 MMAs
 // (N=128; the contraction index is ordered (block, gate) so that the MMAs of a block start as soon as its dgh is written).
-// 3xTF32 throughout (fp32-faithful). warps 0-15: gates, warp 16: TMA producer, warp 17: MMA issuer, warp 18: L2 prefetch
+// 3xTF32 throughout (fp32-faithful). warps 0-15: gates, warp 16: TMA producer of W_h, warp 17: MMA issuer, warp 18: TMA loader of the gate inputs
 // (warp 19 only donates its registers to the gate warps through setmaxnreg).
 #include <cuda.h>
 #include <stdlib.h>
@@ -149,34 +149,11 @@ __device__ __forceinline__ void unstage_patch(float* v, const uint8_t* box, int 
     v[vidx(rr, 1)] = x.y;
   }
 }
-// the patch as TF32 hi / lo images in a 128B-swizzled K-major [128 rows x 32 floats] chunk (c0 = first column, multiple of 8)
-__device__ __forceinline__ void store_patch_split(uint8_t* chunk_hi, uint8_t* chunk_lo, int c0, const float* v, const GateGeom& gg) {
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    float2 h, l;
-    split_tf32(v[vidx(rr, 0)], h.x, l.x);
-    split_tf32(v[vidx(rr, 1)], h.y, l.y);
-    const int row = gg.row[rr];
-    const int unit = ((c0 >> 2) + (gg.m >> 1)) ^ (row & 7);
-    const int off = row * 128 + unit * 16 + (gg.m & 1) * 8;
-    *reinterpret_cast<float2*>(chunk_hi + off) = h;
-    *reinterpret_cast<float2*>(chunk_lo + off) = l;
-  }
-}
 
 // The update only needs fp32-faithful (not bit-identical) gates: ex2.approx-based forms, abs error ~1e-7
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
-// one warp: pull `bytes` contiguous bytes (multiple of 16) towards L2
-__device__ __forceinline__ void l2_prefetch(const void* ptr, int64_t bytes, int lane) {
-  const int64_t per = ((bytes / 32 + 15) / 16) * 16;
-  const int64_t off = per * lane;
-  if (off >= bytes) return;
-  const int64_t n = (bytes - off < per ? bytes - off : per) & ~int64_t(15);
-  if (n > 0)
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(ptr) + off), "r"((uint32_t)n) : "memory");
-}
 
 __device__ __forceinline__ void regs_gate_warps() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;"); }
 __device__ __forceinline__ void regs_service_warps() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); }
