@@ -550,8 +550,13 @@ int gemm_tc(cudaStream_t s, int64_t M, int N, int K, const float* X, int ldx, co
 static bool tn_plan(int N, int K, TnParams* p, uint32_t* smem_bytes) {
   if ((K != 64 && K != 128) || N % 32) return false;
   const int cands[] = {256, 192, 128, 96, 64, 32};
+  static int max_bn = -1;
+  if (max_bn < 0) {
+    const char* e = getenv("MAGPO_TN_MAX_BN");  // experiments: cap the N tile of the weight-gradient GEMM
+    max_bn = e ? atoi(e) : 256;
+  }
   for (int bn : cands) {
-    if (N % bn) continue;
+    if (N % bn || bn > max_bn) continue;
     static int rc_big = -1;
     if (rc_big < 0) {
       const char* e = getenv("MAGPO_TN_ROWS");  // experiments: 32 = always 32 rows per stage
