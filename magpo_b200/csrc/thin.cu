@@ -129,6 +129,153 @@ thin_k_bwd_kernel(int64_t R, int K, const float* __restrict__ X, int ldx, const 
     for (int i = threadIdx.x; i < N; i += 256) atomicAdd(db + i, red[KMAX * N + i]);
 }
 
+
+// ---- N = 128 (the learner's pre-torso): a warp takes 32 consecutive rows per trip. The rows' K inputs are staged in shared memory with
+// coalesced loads (the next trip's are already in registers while this trip is computed), lane l owns output columns 4l..4l+3, so every
+// output row leaves / every dY row arrives as one coalesced 512-byte access and 32 rows per warp are in flight instead of one or two.
+template <int KMAX>
+__device__ __forceinline__ void k128_fetch(float (&v)[KMAX], const float* __restrict__ X, int ldx, int K, int64_t row0, int64_t R, int lane) {
+  if (ldx == K) {  // the 32 x K block is contiguous
+    const int64_t base = row0 * K, end = (row0 + 32 < R ? row0 + 32 : R) * K;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) v[i] = (i < K && base + lane + 32 * i < end) ? __ldg(X + base + lane + 32 * i) : 0.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) v[i] = (i < K && row0 + lane < R) ? __ldg(X + (row0 + lane) * ldx + i) : 0.f;
+  }
+}
+template <int KMAX>
+__device__ __forceinline__ void k128_stage(float* xs /*[32][KMAX]*/, const float (&v)[KMAX], int ldx, int K, int lane) {
+  if (ldx == K) {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i)
+      if (i < K) {
+        const int idx = lane + 32 * i;
+        xs[(idx / K) * KMAX + idx % K] = v[i];
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) xs[lane * KMAX + i] = v[i];
+  }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+thin_k128_fwd_kernel(int64_t R, int K, const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                     const float* __restrict__ bias, float* __restrict__ Y, int ldy, int relu) {
+  __shared__ __align__(16) float xs_all[8][32 * KMAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* xs = xs_all[warp];
+  float4 w[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    w[k] = k < K ? *reinterpret_cast<const float4*>(W + (size_t)k * ldw + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b = bias ? *reinterpret_cast<const float4*>(bias + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i < 32 * KMAX; i += 32) xs[i] = 0.f;  // the padding columns K..KMAX-1 stay zero
+  const int64_t nblk = (R + 31) / 32, stride = (int64_t)gridDim.x * 8;
+  int64_t blk = (int64_t)blockIdx.x * 8 + warp;
+  float v[KMAX];
+  if (blk < nblk) k128_fetch<KMAX>(v, X, ldx, K, blk * 32, R, lane);
+  for (; blk < nblk; blk += stride) {
+    __syncwarp();
+    k128_stage<KMAX>(xs, v, ldx, K, lane);
+    __syncwarp();
+    if (blk + stride < nblk) k128_fetch<KMAX>(v, X, ldx, K, (blk + stride) * 32, R, lane);
+    const int64_t row0 = blk * 32;
+    const int nrows = (int)(R - row0 < 32 ? R - row0 : 32);
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r) {
+      float4 acc = b;
+#pragma unroll
+      for (int q = 0; q < KMAX / 4; ++q) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + r * KMAX + 4 * q);
+        const float xk[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc.x = fmaf(xk[e], w[4 * q + e].x, acc.x); acc.y = fmaf(xk[e], w[4 * q + e].y, acc.y);
+          acc.z = fmaf(xk[e], w[4 * q + e].z, acc.z); acc.w = fmaf(xk[e], w[4 * q + e].w, acc.w);
+        }
+      }
+      if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      *reinterpret_cast<float4*>(Y + (row0 + r) * ldy + 4 * lane) = acc;
+    }
+  }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256, 2)
+thin_k128_bwd_kernel(int64_t R, int K, const float* __restrict__ X, int ldx, const float* __restrict__ dY, int lddy,
+                     const float* __restrict__ relu_out, float* __restrict__ dW, int lddw, float* __restrict__ db) {
+  constexpr int N = kH;
+  __shared__ __align__(16) float xs_all[8][32 * KMAX];
+  __shared__ float red[(KMAX + 1) * N];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* xs = xs_all[warp];
+  float4 acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i < 32 * KMAX; i += 32) xs[i] = 0.f;
+  const int64_t nblk = (R + 31) / 32, stride = (int64_t)gridDim.x * 8;
+  for (int64_t blk = (int64_t)blockIdx.x * 8 + warp; blk < nblk; blk += stride) {
+    {  // (no register prefetch here: the KMAX float4 accumulators need the registers for two CTAs per SM)
+      float v[KMAX];
+      k128_fetch<KMAX>(v, X, ldx, K, blk * 32, R, lane);
+      __syncwarp();
+      k128_stage<KMAX>(xs, v, ldx, K, lane);
+      __syncwarp();
+    }
+    const int64_t row0 = blk * 32;
+    const int nrows = (int)(R - row0 < 32 ? R - row0 : 32);
+    for (int r0 = 0; r0 < nrows; r0 += 4) {
+      // four rows of dY (and of the relu mask) in flight per lane before any of them is used
+      float4 dq[4], oq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = r0 + u < nrows;
+        dq[u] = ok ? __ldg(reinterpret_cast<const float4*>(dY + (row0 + r0 + u) * lddy + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        oq[u] = (ok && relu_out) ? __ldg(reinterpret_cast<const float4*>(relu_out + (row0 + r0 + u) * lddy + 4 * lane))
+                                 : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float4 d = dq[u];
+        if (!(oq[u].x > 0.f)) d.x = 0.f;
+        if (!(oq[u].y > 0.f)) d.y = 0.f;
+        if (!(oq[u].z > 0.f)) d.z = 0.f;
+        if (!(oq[u].w > 0.f)) d.w = 0.f;
+        bs.x += d.x; bs.y += d.y; bs.z += d.z; bs.w += d.w;
+        const int r = r0 + u < nrows ? r0 + u : 0;  // d is zero past the last row
+#pragma unroll
+        for (int q = 0; q < KMAX / 4; ++q) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xs + r * KMAX + 4 * q);
+          const float xk[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[4 * q + e].x = fmaf(xk[e], d.x, acc[4 * q + e].x); acc[4 * q + e].y = fmaf(xk[e], d.y, acc[4 * q + e].y);
+            acc[4 * q + e].z = fmaf(xk[e], d.z, acc[4 * q + e].z); acc[4 * q + e].w = fmaf(xk[e], d.w, acc[4 * q + e].w);
+          }
+        }
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < (KMAX + 1) * N; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const int c = lane;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) {
+      atomicAdd(&red[k * N + 4 * c + 0], acc[k].x); atomicAdd(&red[k * N + 4 * c + 1], acc[k].y);
+      atomicAdd(&red[k * N + 4 * c + 2], acc[k].z); atomicAdd(&red[k * N + 4 * c + 3], acc[k].w);
+    }
+  atomicAdd(&red[KMAX * N + 4 * c + 0], bs.x); atomicAdd(&red[KMAX * N + 4 * c + 1], bs.y);
+  atomicAdd(&red[KMAX * N + 4 * c + 2], bs.z); atomicAdd(&red[KMAX * N + 4 * c + 3], bs.w);
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * N; i += 256) atomicAdd(dW + (size_t)(i / N) * lddw + i % N, red[i]);
+  if (db)
+    for (int i = threadIdx.x; i < N; i += 256) atomicAdd(db + i, red[KMAX * N + i]);
+}
+
 // ---------------------------------------------------------------------------------------------- thin N (K = 128)
 // warp = row; lane holds columns 4l..4l+3 of the 128-wide input. Wt (shared) is W^T padded to [NV][128].
 template <int NV>
@@ -413,7 +560,12 @@ int thin_k_fwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx,
   if (!thin_k_ok(K, N, ldw, W, Y, ldy) || (bias && (reinterpret_cast<uintptr_t>(bias) & 15))) return MAGPO_ERR_UNSUPPORTED;
   ProfScope ps(PROF_ROWOPS, s, 4.0 * R * (K + N));
 #define THIN_K_FWD(NQ, KM) thin_k_fwd_kernel<NQ, KM><<<thin_grid(R, 256 / NQ), 256, 0, s>>>(R, K, X, ldx, W, ldw, bias, Y, ldy, relu)
-  if (N == kH) { if (K <= 4) THIN_K_FWD(32, 4); else if (K <= 8) THIN_K_FWD(32, 8); else THIN_K_FWD(32, 16); }
+  if (N == kH) {
+    const unsigned g128 = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(R, 256), (int64_t)kNumSMs * 3));
+#define THIN_K128_FWD(KM) thin_k128_fwd_kernel<KM><<<g128, 256, 0, s>>>(R, K, X, ldx, W, ldw, bias, Y, ldy, relu)
+    if (K <= 4) THIN_K128_FWD(4); else if (K <= 8) THIN_K128_FWD(8); else THIN_K128_FWD(16);
+#undef THIN_K128_FWD
+  }
   else { if (K <= 4) THIN_K_FWD(16, 4); else if (K <= 8) THIN_K_FWD(16, 8); else THIN_K_FWD(16, 16); }
 #undef THIN_K_FWD
   MAGPO_LAUNCH_OK();
@@ -427,7 +579,12 @@ int thin_k_bwd(cudaStream_t s, int64_t R, int K, int N, const float* X, int ldx,
   ProfScope ps(PROF_ROWOPS, s, 4.0 * R * (K + N));
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(R, 64), (int64_t)kNumSMs * 4));
 #define THIN_K_BWD(NQ, KM) thin_k_bwd_kernel<NQ, KM><<<grid, 256, 0, s>>>(R, K, X, ldx, dY, lddy, relu_out, dW, lddw, db)
-  if (N == kH) { if (K <= 4) THIN_K_BWD(32, 4); else if (K <= 8) THIN_K_BWD(32, 8); else THIN_K_BWD(32, 16); }
+  if (N == kH) {
+    const unsigned g128 = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(R, 256), (int64_t)kNumSMs * 4));
+#define THIN_K128_BWD(KM) thin_k128_bwd_kernel<KM><<<g128, 256, 0, s>>>(R, K, X, ldx, dY, lddy, relu_out, dW, lddw, db)
+    if (K <= 4) THIN_K128_BWD(4); else if (K <= 8) THIN_K128_BWD(8); else THIN_K128_BWD(16);
+#undef THIN_K128_BWD
+  }
   else { if (K <= 4) THIN_K_BWD(16, 4); else if (K <= 8) THIN_K_BWD(16, 8); else THIN_K_BWD(16, 16); }
 #undef THIN_K_BWD
   MAGPO_LAUNCH_OK();
