@@ -544,6 +544,96 @@ obs_embed_bwd_kernel(int64_t R, int d, const float* __restrict__ obs, const floa
   if (threadIdx.x < d) atomicAdd(dscale + threadIdx.x, red[KMAX * kD + threadIdx.x]);
 }
 
+
+// obs_embed_bwd with the row-batch mapping of thin_k128: a warp takes 32 consecutive rows per trip, stages their observations in shared
+// memory (coalesced), lane l normalises row l once (the old kernel recomputed the row's RMS in every lane and fetched the K inputs with K
+// broadcast loads per row), then every row costs one coalesced 256-byte dz load and K/4 broadcast LDS.128.
+template <int KMAX>
+__global__ void __launch_bounds__(256, 2)
+obs_embed_rows_bwd_kernel(int64_t R, int d, const float* __restrict__ obs, const float* __restrict__ obs_scale,
+                          const float* __restrict__ Wobs, const float* __restrict__ dz0, float* __restrict__ dWobs,
+                          float* __restrict__ dscale) {
+  __shared__ __align__(16) float xs_all[8][32 * KMAX];
+  __shared__ float red[KMAX * kD + KMAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* xs = xs_all[warp];
+  float2 w[KMAX], acc[KMAX];
+  float sc[KMAX], ds[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    w[k] = k < d ? *reinterpret_cast<const float2*>(Wobs + (size_t)k * kD + 2 * lane) : make_float2(0.f, 0.f);
+    sc[k] = k < d ? obs_scale[k] : 0.f;
+    acc[k] = make_float2(0.f, 0.f);
+    ds[k] = 0.f;
+  }
+  for (int i = lane; i < 32 * KMAX; i += 32) xs[i] = 0.f;
+  const float inv_d = 1.0f / (float)d;
+  const int64_t nblk = (R + 31) / 32, stride = (int64_t)gridDim.x * 8;
+  for (int64_t blk = (int64_t)blockIdx.x * 8 + warp; blk < nblk; blk += stride) {
+    {
+      float v[KMAX];
+      k128_fetch<KMAX>(v, obs, d, d, blk * 32, R, lane);
+      __syncwarp();
+      k128_stage<KMAX>(xs, v, d, d, lane);
+      __syncwarp();
+      // lane l: row l -> x * rstd (rows past R are zero: rstd finite, products zero)
+      float x[KMAX], ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < KMAX / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(xs + lane * KMAX + 4 * q);
+        x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) ss = fmaf(x[k], x[k], ss);
+      const float rstd0 = rsqrtf(ss * inv_d + kEps);
+#pragma unroll
+      for (int q = 0; q < KMAX / 4; ++q)
+        *reinterpret_cast<float4*>(xs + lane * KMAX + 4 * q) =
+            make_float4(x[4 * q] * rstd0, x[4 * q + 1] * rstd0, x[4 * q + 2] * rstd0, x[4 * q + 3] * rstd0);
+      __syncwarp();
+    }
+    const int64_t row0 = blk * 32;
+    const int nrows = (int)(R - row0 < 32 ? R - row0 : 32);
+    for (int r0 = 0; r0 < nrows; r0 += 4) {
+      float2 dq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        dq[u] = r0 + u < nrows ? __ldg(reinterpret_cast<const float2*>(dz0 + (row0 + r0 + u) * kD + 2 * lane)) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u < nrows ? r0 + u : 0;  // dz is zero past the last row
+        const float2 dz = dq[u];
+#pragma unroll
+        for (int q = 0; q < KMAX / 4; ++q) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xs + r * KMAX + 4 * q);
+          const float xn[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = 4 * q + e;
+            const float o = xn[e] * sc[k];
+            acc[k].x = fmaf(o, dz.x, acc[k].x);
+            acc[k].y = fmaf(o, dz.y, acc[k].y);
+            ds[k] = fmaf(dz.x * w[k].x + dz.y * w[k].y, xn[e], ds[k]);  // lane partial of d(on_k) * x_k * rstd
+          }
+        }
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < KMAX * kD + KMAX; i += 256) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < d) {
+      atomicAdd(&red[k * kD + 2 * lane], acc[k].x);
+      atomicAdd(&red[k * kD + 2 * lane + 1], acc[k].y);
+      const float t = warp_sum(ds[k]);
+      if (lane == 0) atomicAdd(&red[KMAX * kD + k], t);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d * kD; i += 256) atomicAdd(dWobs + i, red[i]);
+  if (threadIdx.x < d) atomicAdd(dscale + threadIdx.x, red[KMAX * kD + threadIdx.x]);
+}
+
 }  // namespace
 
 bool thin_k_ok(int K, int N, int ldw, const float* W, const float* Y, int ldy) {
@@ -635,7 +725,7 @@ int obs_embed_bwd(cudaStream_t s, int64_t R, int d, const float* obs, const floa
   if (!obs_embed_ok(d)) return MAGPO_ERR_UNSUPPORTED;
   ProfScope ps(PROF_ROWOPS, s, R * (4.0 * d + 256.0));
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(R, 64), (int64_t)kNumSMs * 4));
-#define OBS_BWD(KM) obs_embed_bwd_kernel<KM><<<grid, 256, 0, s>>>(R, d, obs, obs_scale, Wobs, dz0, dWobs, dscale)
+#define OBS_BWD(KM) obs_embed_rows_bwd_kernel<KM><<<grid, 256, 0, s>>>(R, d, obs, obs_scale, Wobs, dz0, dWobs, dscale)
   if (d <= 4) OBS_BWD(4); else if (d <= 8) OBS_BWD(8); else OBS_BWD(16);
 #undef OBS_BWD
   MAGPO_LAUNCH_OK();
