@@ -470,81 +470,6 @@ obs_embed_fwd_kernel(int64_t R, int d, const float* __restrict__ obs, const floa
   }
 }
 
-template <int KMAX>
-__global__ void __launch_bounds__(256, 2)
-obs_embed_bwd_kernel(int64_t R, int d, const float* __restrict__ obs, const float* __restrict__ obs_scale,
-                     const float* __restrict__ Wobs, const float* __restrict__ dz0, float* __restrict__ dWobs,
-                     float* __restrict__ dscale) {
-  constexpr int UN = KMAX <= 4 ? 4 : (KMAX <= 8 ? 2 : 1);
-  __shared__ float red[KMAX * kD + KMAX];
-  const int lane = threadIdx.x & 31;
-  float2 w[KMAX], acc[KMAX];
-  float sc[KMAX], ds[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    w[k] = k < d ? *reinterpret_cast<const float2*>(Wobs + (size_t)k * kD + 2 * lane) : make_float2(0.f, 0.f);
-    sc[k] = k < d ? obs_scale[k] : 0.f;
-    acc[k] = make_float2(0.f, 0.f);
-    ds[k] = 0.f;
-  }
-  const float inv_d = 1.0f / (float)d;
-  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), stride = (int64_t)gridDim.x * 8;
-  // software-pipelined over rows: the loads of the next group of UN rows are in flight while the current group is reduced
-  float x[UN][KMAX], xn_[UN][KMAX];
-  float2 dz[UN], dzn[UN];
-#pragma unroll
-  for (int u = 0; u < UN; ++u) {
-    const int64_t row = w0 + u * stride;
-    const bool ok = row < R;
-    dz[u] = ok ? ld2(dz0, row, kD, lane) : make_float2(0.f, 0.f);
-    load_thin_row<KMAX>(x[u], obs, row, d, d, ok);
-  }
-  for (int64_t row0 = w0; row0 < R; row0 += UN * stride) {
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int64_t row = row0 + (UN + u) * stride;
-      const bool ok = row < R;
-      dzn[u] = ok ? ld2(dz0, row, kD, lane) : make_float2(0.f, 0.f);
-      load_thin_row<KMAX>(xn_[u], obs, row, d, d, ok);
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      float ss = 0.f;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) ss = fmaf(x[u][k], x[u][k], ss);
-      const float rstd0 = rsqrtf(ss * inv_d + kEps);
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        const float xn = x[u][k] * rstd0;
-        const float o = xn * sc[k];
-        acc[k].x = fmaf(o, dz[u].x, acc[k].x);
-        acc[k].y = fmaf(o, dz[u].y, acc[k].y);
-        ds[k] = fmaf(dz[u].x * w[k].x + dz[u].y * w[k].y, xn, ds[k]);  // lane partial of d(on_k) * x_k * rstd
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      dz[u] = dzn[u];
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) x[u][k] = xn_[u][k];
-    }
-  }
-  for (int i = threadIdx.x; i < KMAX * kD + KMAX; i += 256) red[i] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k)
-    if (k < d) {
-      atomicAdd(&red[k * kD + 2 * lane], acc[k].x);
-      atomicAdd(&red[k * kD + 2 * lane + 1], acc[k].y);
-      const float t = warp_sum(ds[k]);
-      if (lane == 0) atomicAdd(&red[KMAX * kD + k], t);
-    }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d * kD; i += 256) atomicAdd(dWobs + i, red[i]);
-  if (threadIdx.x < d) atomicAdd(dscale + threadIdx.x, red[KMAX * kD + threadIdx.x]);
-}
-
-
 // obs_embed_bwd with the row-batch mapping of thin_k128: a warp takes 32 consecutive rows per trip, stages their observations in shared
 // memory (coalesced), lane l normalises row l once (the old kernel recomputed the row's RMS in every lane and fetched the K inputs with K
 // broadcast loads per row), then every row costs one coalesced 256-byte dz load and K/4 broadcast LDS.128.
