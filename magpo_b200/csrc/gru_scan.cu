@@ -314,6 +314,8 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     const int sp = warp & 3, cq = warp >> 2;
     const GateGeom gg = make_geom(sp, lane, tile_row0, p.Rs, p.rpt);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(sp * 32) << 16);
+    const bool grp_live = 32 * sp < p.rpt && tile_row0 + 32 * sp < p.Rs;  // this warp's 32 rows hold rows of the tile
+    const bool grp_leader = cq == 0 && lane == 0;
     float h[32];  // masked previous state: block jb at [8 jb, 8 jb + 8)
     float bh[8];
 #pragma unroll
@@ -373,25 +375,30 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             h[8 * jb + i] = keep[rr] ? hn : 0.0f;
           }
         if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 3);
-        if (threadIdx.x == 0) bulk_wait_read<0>();  // the previous block's bulk stores have read the staging boxes
-        named_bar_sync(1, GS_GATE_THREADS);
-        stage_patch(sOut + 0 * GS_CHUNK, 8 * cq, gi_r, gg);
-        stage_patch(sOut + 1 * GS_CHUNK, 8 * cq, gi_z, gg);
-        stage_patch(sOut + 2 * GS_CHUNK, 8 * cq, gi_n, gg);
-        stage_patch(sOut + 3 * GS_CHUNK, 8 * cq, reinterpret_cast<const float*>(ar), gg);
-        stage_patch(sOut + 4 * GS_CHUNK, 8 * cq, y_, gg);
-        stage_patch(sOut + 5 * GS_CHUNK, 8 * cq, &h[8 * jb], gg);
-        fence_proxy_async();
-        named_bar_sync(1, GS_GATE_THREADS);
-        if (threadIdx.x == 0) {
-          const int r0 = (int)tile_row0;
-          tma_store_3d(&om.rzn, sOut + 0 * GS_CHUNK, 32 * jb, r0, t);
-          tma_store_3d(&om.rzn, sOut + 1 * GS_CHUNK, kH + 32 * jb, r0, t);
-          tma_store_3d(&om.rzn, sOut + 2 * GS_CHUNK, 2 * kH + 32 * jb, r0, t);
-          tma_store_3d(&om.ghn, sOut + 3 * GS_CHUNK, 32 * jb, r0, t);
-          tma_store_3d(&om.Y, sOut + 4 * GS_CHUNK, 32 * jb, r0, t);
-          tma_store_3d(&om.HU, sOut + 5 * GS_CHUNK, 32 * jb, r0, t + 1);
-          bulk_commit();
+        // staging + bulk stores per group of the 4 warps that share 32 rows (sub-boxes of [32 rows x 32 floats]): the groups do not wait
+        // for each other, a 128-thread barrier instead of a 512-thread one
+        if (grp_live) {
+          if (grp_leader) bulk_wait_read<0>();  // the previous block's bulk stores of this group have read its sub-boxes
+          named_bar_sync(1 + sp, 128);
+          stage_patch(sOut + 0 * GS_CHUNK, 8 * cq, gi_r, gg);
+          stage_patch(sOut + 1 * GS_CHUNK, 8 * cq, gi_z, gg);
+          stage_patch(sOut + 2 * GS_CHUNK, 8 * cq, gi_n, gg);
+          stage_patch(sOut + 3 * GS_CHUNK, 8 * cq, reinterpret_cast<const float*>(ar), gg);
+          stage_patch(sOut + 4 * GS_CHUNK, 8 * cq, y_, gg);
+          stage_patch(sOut + 5 * GS_CHUNK, 8 * cq, &h[8 * jb], gg);
+          fence_proxy_async();
+          named_bar_sync(1 + sp, 128);
+          if (grp_leader) {
+            const int r0 = (int)tile_row0 + 32 * sp;
+            const uint8_t* src = sOut + sp * 4096;
+            tma_store_3d(&om.rzn, src + 0 * GS_CHUNK, 32 * jb, r0, t);
+            tma_store_3d(&om.rzn, src + 1 * GS_CHUNK, kH + 32 * jb, r0, t);
+            tma_store_3d(&om.rzn, src + 2 * GS_CHUNK, 2 * kH + 32 * jb, r0, t);
+            tma_store_3d(&om.ghn, src + 3 * GS_CHUNK, 32 * jb, r0, t);
+            tma_store_3d(&om.Y, src + 4 * GS_CHUNK, 32 * jb, r0, t);
+            tma_store_3d(&om.HU, src + 5 * GS_CHUNK, 32 * jb, r0, t + 1);
+            bulk_commit();
+          }
         }
         if (threadIdx.x == 0) GS_STAMP(2, (t * 4 + jb) * 6 + 4);
       }
@@ -408,7 +415,7 @@ gru_scan_fwd_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
       }
     }
   }
-  if (threadIdx.x == 0) bulk_wait_all();
+  if (threadIdx.x < GS_GATE_THREADS && (threadIdx.x >> 5) < 4 && (threadIdx.x & 31) == 0) bulk_wait_all();  // the group leaders
   tc_fence_before();
   __syncthreads();
   if (warp == GS_GATE_WARPS) {
@@ -692,8 +699,9 @@ int gru_scan_fwd(cudaStream_t s, int T, int N, int A, const float* gi, const flo
     MAGPO_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
   const int rpt = gru_rows_per_tile(Rs);
   GruOutMaps om;
-  if (!tc_make_map3(&om.gi, gi, T, Rs, 3 * kH, rpt) || !tc_make_map3(&om.rzn, rzn, T, Rs, 3 * kH, rpt) || !tc_make_map3(&om.ghn, ghn, T, Rs, kH, rpt) || !tc_make_map3(&om.Y, Y, T, Rs, kH, rpt) ||
-      !tc_make_map3(&om.HU, HU, T + 1, Rs, kH, rpt))
+  const int ob = std::min(rpt, 32);  // the outputs leave per group of 32 rows
+  if (!tc_make_map3(&om.gi, gi, T, Rs, 3 * kH, rpt) || !tc_make_map3(&om.rzn, rzn, T, Rs, 3 * kH, ob) || !tc_make_map3(&om.ghn, ghn, T, Rs, kH, ob) ||
+      !tc_make_map3(&om.Y, Y, T, Rs, kH, ob) || !tc_make_map3(&om.HU, HU, T + 1, Rs, kH, ob))
     return MAGPO_ERR_ARG;
   GruFwdArgs a{g_gru_dbg, T, N, A, Rs, rpt, gi, bhn, done, rzn, ghn, Y, HU};
   // per row and step: 3xTF32 MMAs are the pipe work; bytes: gi 1536 read, rzn+ghn+Y+HU 3072 written
