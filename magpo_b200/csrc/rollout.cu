@@ -118,6 +118,19 @@ __global__ void copy_zero_done_kernel(int64_t B, int64_t quads /* float4 per env
 
 inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n, 256); }
 
+// The learner's GRU push (rec_magpo.py:146-159) needs only the observations, not the guider's actions, and nothing reads the learner's
+// hidden state before the rollout ends: instead of 5 small launches per env step it can run once per `chunk` env steps as one batched
+// pre-torso + input projection and one persistent GRU scan over the chunk's timesteps (MAGPO_ROLLOUT_LEARNER_CHUNK; default 1 = per step).
+inline int learner_chunk_steps() {
+  static int c = -1;
+  if (c < 0) {
+    const char* e = getenv("MAGPO_ROLLOUT_LEARNER_CHUNK");
+    c = e ? atoi(e) : 1;
+    if (c < 1) c = 1;
+  }
+  return c;
+}
+
 struct RolloutWs {
   SableActs sa;
   ActorActs aa;
@@ -128,10 +141,24 @@ struct RolloutWs {
   uint32_t* sample_keys;
   void* gws;  // general guider shapes (generic.cuh): the step workspace of sable_g_get_actions instead of the default path's buffers
   size_t gws_bytes;
+  ActorActs ac;  // the learner's state push in chunks of `chunk` env steps (persistent GRU scan instead of per-step launches)
+  int chunk;
   void plan(Arena& ar, const MagpoNetCfg* net, int B, int T) {
     const int64_t R = (int64_t)B * net->n_agents;
     aa.plan(ar, R, R, net->action_dim, false);
     at.plan(ar, net->action_dim);
+    chunk = std::min(T, learner_chunk_steps());
+    ac = ActorActs{};
+    if (chunk > 1) {
+      const size_t rH = (size_t)chunk * R * kH;
+      ac.e = ar.get<float>(rH);
+      ac.gi = ar.get<float>(3 * rH);
+      ac.gh = ar.get<float>((size_t)R * 3 * kH);
+      ac.HU = ar.get<float>(rH + (size_t)R * kH);
+      ac.Y = ar.get<float>(rH);
+      ac.rzn = ar.get<float>(3 * rH);
+      ac.ghn = ar.get<float>(rH);
+    }
     sample_keys = ar.get<uint32_t>((size_t)(T + 1) * net->n_agents * 2);
     gws = nullptr; gws_bytes = 0;
     const NetShape shape = NetShape::of(net);
@@ -336,11 +363,19 @@ int magpo_rollout(MagpoContext* ctx_, magpo_stream_t s_, const MagpoNetCfg* net,
     const int32_t* stepc = traj.step_count + (size_t)t * BA;
     const uint8_t* prev_done = traj.done + (size_t)t * B;
     int32_t* act = traj.action + (size_t)t * BA;
-    if (overlap) {  // observation slot t and done[t] are complete on `s` here
+    const bool chunked = w.chunk > 1 && atp && !sys->sable_only;
+    const bool push_now = !chunked || (t + 1) % w.chunk == 0 || t == T - 1;
+    if (overlap && push_now) {  // observation slot t and done[t] are complete on `s` here
       MAGPO_CUDA_OK(cudaEventRecord(g_rside.fork, s));
       MAGPO_CUDA_OK(cudaStreamWaitEvent(s2, g_rside.fork, 0));
     }
-    if (!sys->sable_only) MAGPO_TRY(actor_forward(s2, ap, atp, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
+    if (chunked && push_now) {
+      const int t0 = (t / w.chunk) * w.chunk, len = t - t0 + 1;
+      MAGPO_TRY(actor_forward(s2, ap, atp, len, B, A, d, a, traj.agents_view + (size_t)t0 * BA * d, traj.done + (size_t)t0 * B, policy_h, w.ac,
+                              nullptr, policy_h));
+    } else if (!chunked && !sys->sable_only) {
+      MAGPO_TRY(actor_forward(s2, ap, atp, 1, B, A, d, a, obs, prev_done, policy_h, w.aa, nullptr, policy_h));
+    }
     MAGPO_TRY(get_actions(s, net, B, E, gp, gtp, kappa, obs, mask, stepc, prev_done, w.sample_keys + (size_t)t * A * 2, hs,
                           false, act, traj.log_prob + (size_t)t * BA, traj.value + (size_t)t * BA, nullptr, w));
     MagpoTimeStep o = ts;
