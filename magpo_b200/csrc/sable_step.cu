@@ -152,8 +152,10 @@ __device__ __forceinline__ void prefetch_state(const float* H) {
 
 // state rows r0..r0+7 of env state H. KEEP = false: evict-first (the last read of the state in this launch). KEEP = true: default
 // policy — a decoder state is read once per agent, and next to evict-first streams the lines of an earlier agent's pass survive in
-// L2 until the next agent's pass instead of coming from HBM again (tools/step_l2_experiment.sh: LBF rollout 49.8 -> 48.4 ms,
-// RWARE shard 23.3 -> 22.3 ms; explicit evict_last / evict_normal createpolicy operands measured no better)
+// L2 longer (tools/step_l2_experiment.sh: RWARE shard, 1024 envs x 4 agents, whose states fit L2: rollout 23.3 -> 22.3 ms in both
+// A/B runs; LBF, 8192 envs x 2 agents: 49.8 -> 48.4 ms in one A/B run and no difference in two others, DRAM bytes per launch
+// unchanged under ncu; explicit evict_last / evict_normal createpolicy operands and a second L2 prefetch between the passes
+// measured no better)
 template <bool KEEP = false>
 __device__ __forceinline__ void load_rows(float2 (&h)[8], const float* __restrict__ H, int r0, int lane) {
 #pragma unroll
